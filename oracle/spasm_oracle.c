@@ -1,0 +1,1553 @@
+/*
+ * spasm_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT THE PRODUCT).
+ *
+ * A plain-C restatement of libspasm's echelonization hot path, the library that
+ * SpaSM.jl binds through Spasm_jll (/root/reference/src/SpaSM.jl:7,14).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library; the product (spasm.jl_b200/) never does.
+ *
+ * PARITY STATUS: **parity unpinned** beyond the reference's own goldens.  libspasm's
+ * sources (github.com/cbouilla/spasm, un-vendored, no version pin: Project.toml:15,19-24)
+ * are absent from /root/reference and from this machine, so this file restates the
+ * published algorithm anchored on what IS in the reference:
+ *   - value representation and field ops           src/SpaSM.jl:73-88, :383-390
+ *   - struct layouts                               src/SpaSM.jl:126-134, :234-243, :262-270, :325-343
+ *   - triangular-solve contract                    src/SpaSM.jl:694-713
+ *   - prototypes of schur / pivots / ffpack        src/SpaSM.jl:760-770, :775-778, :804-812
+ *   - phase order + log strings                    README.md:19-41
+ *   - kernel sign / row order goldens              test/runtests.jl:17-24, README.md:43-48
+ * It is pinned against those goldens in tests/test_oracle_golden.py.
+ *
+ * Determinism rules (DESIGN.md "parity semantics"): results are those of libspasm's
+ * single-thread sequential order, with four documented normalisations that make the
+ * result independent of thread count and reproducible by an order-deterministic GPU code:
+ *   (N1) computed rows (Schur rows, GPLU/dense U rows after the leading pivot entry, kernel
+ *        rows after the leading (j,-1), rref rows, L rows) store their entries in increasing
+ *        column order — the order the reference's own `sparse()` canonicalises to
+ *        (src/SpaSM.jl:1017-1020) — instead of DFS-pattern order;
+ *   (N2) pivots of one round enter U ordered by (height in the pivot DAG descending, row
+ *        index ascending) — a topological order, like upstream's DFS order;
+ *   (N3) rows of S / K / R are emitted in input order (not OpenMP completion order);
+ *   (N4) libc rand() in the density estimate is replaced by a seeded splitmix64.
+ */
+#define _GNU_SOURCE
+#include "../include/spasm_b200.h"
+
+#include <assert.h>
+#include <inttypes.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int (*logcallback)(const char *) = NULL;
+
+const char *spasm_b200_backend(void) { return "cpu-oracle"; }
+
+/* src/SpaSM.jl:34-46 — text goes to the callback when installed, else stderr */
+static void logprintf(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (logcallback != NULL)
+    logcallback(buf);
+  else
+    fputs(buf, stderr);
+}
+
+/* ------------------------------------------------------------------ field (spasm_ZZp.c) */
+
+/* src/SpaSM.jl:73-76 */
+void spasm_field_init(i64 p, spasm_field F) {
+  F->p = p;
+  F->halfp = p / 2;
+  F->mhalfp = p / 2 - p + 1;
+  F->dinvp = 1.0 / (double)p;
+}
+
+/* src/SpaSM.jl:83-88 */
+static inline spasm_ZZp NORMALISE(const spasm_field F, i64 x) {
+  if (x < F->mhalfp)
+    x += F->p;
+  else if (x > F->halfp)
+    x -= F->p;
+  return (spasm_ZZp)x;
+}
+
+spasm_ZZp spasm_ZZp_init(const spasm_field F, i64 x) { return NORMALISE(F, x % F->p); }
+spasm_ZZp spasm_ZZp_add(const spasm_field F, spasm_ZZp a, spasm_ZZp b) { return NORMALISE(F, (i64)a + (i64)b); }
+spasm_ZZp spasm_ZZp_sub(const spasm_field F, spasm_ZZp a, spasm_ZZp b) { return NORMALISE(F, (i64)a - (i64)b); }
+
+/* src/SpaSM.jl:385 — i64 product minus (double quotient estimate)*p, then one conditional +-p */
+spasm_ZZp spasm_ZZp_mul(const spasm_field F, spasm_ZZp a, spasm_ZZp b) {
+  i64 q = (i64)(((double)a) * ((double)b) * F->dinvp);
+  return NORMALISE(F, (i64)a * (i64)b - q * F->p);
+}
+
+/* src/SpaSM.jl:386 — extended Euclid on the non-negative representative */
+spasm_ZZp spasm_ZZp_inverse(const spasm_field F, spasm_ZZp a) {
+  i64 p = F->p;
+  i64 r0 = (a < 0) ? (i64)a + p : (i64)a, r1 = p;
+  i64 s0 = 1, s1 = 0;
+  while (r1 != 0) {
+    i64 q = r0 / r1;
+    i64 t = r0 - q * r1;
+    r0 = r1;
+    r1 = t;
+    t = s0 - q * s1;
+    s0 = s1;
+    s1 = t;
+  }
+  assert(r0 == 1);
+  return NORMALISE(F, s0 % p);
+}
+
+/* src/SpaSM.jl:387-390 */
+spasm_ZZp spasm_ZZp_axpy(const spasm_field F, spasm_ZZp a, spasm_ZZp x, spasm_ZZp y) {
+  i64 q = (i64)((((double)a) * ((double)x) + (double)y) * F->dinvp);
+  return NORMALISE(F, (i64)a * (i64)x + (i64)y - q * F->p);
+}
+
+/* ------------------------------------------------------------------ util (spasm_util.c) */
+
+double spasm_wtime(void) {
+  struct timeval ts;
+  gettimeofday(&ts, NULL);
+  return (double)ts.tv_sec + ts.tv_usec / 1e6;
+}
+
+int spasm_get_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int spasm_get_thread_num(void) {
+#ifdef _OPENMP
+  return omp_get_thread_num();
+#else
+  return 0;
+#endif
+}
+
+void *spasm_malloc(i64 size) {
+  void *x = malloc(size > 0 ? (size_t)size : 1);
+  if (x == NULL) {
+    perror("spasm oracle: malloc failed");
+    abort();
+  }
+  return x;
+}
+
+void *spasm_calloc(i64 count, i64 size) {
+  void *x = calloc(count > 0 ? (size_t)count : 1, size > 0 ? (size_t)size : 1);
+  if (x == NULL) {
+    perror("spasm oracle: calloc failed");
+    abort();
+  }
+  return x;
+}
+
+void *spasm_realloc(void *ptr, i64 size) {
+  void *x = realloc(ptr, size > 0 ? (size_t)size : 1);
+  if (x == NULL) {
+    perror("spasm oracle: realloc failed");
+    abort();
+  }
+  return x;
+}
+
+i64 spasm_nnz(const struct spasm_csr *A) { return A->p[A->n]; }
+
+/* src/SpaSM.jl:441 — the caller writes p/j/x in place afterwards (:949-966) */
+struct spasm_csr *spasm_csr_alloc(int n, int m, i64 nzmax, i64 prime, bool with_values) {
+  struct spasm_csr *A = spasm_malloc(sizeof(*A));
+  spasm_field_init(prime, A->field);
+  A->m = m;
+  A->n = n;
+  A->nzmax = nzmax;
+  A->p = spasm_malloc((i64)(n + 1) * sizeof(i64));
+  A->j = spasm_malloc(nzmax * sizeof(int));
+  A->x = with_values ? spasm_malloc(nzmax * sizeof(spasm_ZZp)) : NULL;
+  A->p[0] = 0;
+  return A;
+}
+
+void spasm_csr_realloc(struct spasm_csr *A, i64 nzmax) {
+  if (nzmax < 0) nzmax = spasm_nnz(A);
+  if (nzmax == A->nzmax) return;
+  A->j = spasm_realloc(A->j, nzmax * sizeof(int));
+  if (A->x != NULL) A->x = spasm_realloc(A->x, nzmax * sizeof(spasm_ZZp));
+  A->nzmax = nzmax;
+}
+
+void spasm_csr_resize(struct spasm_csr *A, int n, int m) {
+  A->m = m;
+  if (A->n < n) {
+    A->p = spasm_realloc(A->p, (i64)(n + 1) * sizeof(i64));
+    for (int i = A->n; i < n + 1; i++) A->p[i] = A->p[A->n];
+  }
+  A->n = n;
+}
+
+void spasm_csr_free(struct spasm_csr *A) {
+  if (A == NULL) return;
+  free(A->p);
+  free(A->j);
+  free(A->x);
+  free(A);
+}
+
+struct spasm_triplet *spasm_triplet_alloc(int n, int m, i64 nzmax, i64 prime, bool with_values) {
+  struct spasm_triplet *A = spasm_malloc(sizeof(*A));
+  A->m = m;
+  A->n = n;
+  A->nzmax = nzmax;
+  spasm_field_init(prime, A->field);
+  A->nz = 0;
+  A->i = spasm_malloc(nzmax * sizeof(int));
+  A->j = spasm_malloc(nzmax * sizeof(int));
+  A->x = with_values ? spasm_malloc(nzmax * sizeof(spasm_ZZp)) : NULL;
+  return A;
+}
+
+void spasm_triplet_realloc(struct spasm_triplet *A, i64 nzmax) {
+  if (nzmax < 0) nzmax = A->nz;
+  A->i = spasm_realloc(A->i, nzmax * sizeof(int));
+  A->j = spasm_realloc(A->j, nzmax * sizeof(int));
+  if (A->x != NULL) A->x = spasm_realloc(A->x, nzmax * sizeof(spasm_ZZp));
+  A->nzmax = nzmax;
+}
+
+void spasm_triplet_free(struct spasm_triplet *A) {
+  if (A == NULL) return;
+  free(A->i);
+  free(A->j);
+  free(A->x);
+  free(A);
+}
+
+/* src/SpaSM.jl:463 — frees U/L/qinv/p/Ltmp too (the Julia views are own=false, :289-292) */
+void spasm_lu_free(struct spasm_lu *N) {
+  if (N == NULL) return;
+  free(N->qinv);
+  free(N->p);
+  spasm_csr_free(N->U);
+  spasm_csr_free(N->L);
+  spasm_triplet_free(N->Ltmp);
+  free(N);
+}
+
+/* ------------------------------------------------------------------ triplet (spasm_triplet.c) */
+
+/* src/SpaSM.jl:486 */
+void spasm_add_entry(struct spasm_triplet *T, int i, int j, i64 x) {
+  assert(i >= 0 && j >= 0);
+  spasm_ZZp xp = spasm_ZZp_init(T->field, x);
+  if (xp == 0) return;
+  if (T->nz == T->nzmax) spasm_triplet_realloc(T, 1 + 2 * T->nzmax);
+  if (T->x != NULL) T->x[T->nz] = xp;
+  T->i[T->nz] = i;
+  T->j[T->nz] = j;
+  T->nz += 1;
+  if (i + 1 > T->n) T->n = i + 1;
+  if (j + 1 > T->m) T->m = j + 1;
+}
+
+/* src/SpaSM.jl:491 */
+void spasm_triplet_transpose(struct spasm_triplet *T) {
+  int *tmp = T->i;
+  T->i = T->j;
+  T->j = tmp;
+  int t = T->m;
+  T->m = T->n;
+  T->n = t;
+}
+
+/* src/SpaSM.jl:493 — stable bucket by row; duplicates summed, zero sums dropped */
+struct spasm_csr *spasm_compress(const struct spasm_triplet *T) {
+  int m = T->m, n = T->n;
+  i64 nz = T->nz;
+  struct spasm_csr *C = spasm_csr_alloc(n, m, nz, T->field->p, T->x != NULL);
+  i64 *w = spasm_calloc(n + 1, sizeof(i64));
+  for (i64 e = 0; e < nz; e++) w[T->i[e]] += 1;
+  i64 sum = 0;
+  for (int i = 0; i < n; i++) {
+    C->p[i] = sum;
+    sum += w[i];
+    w[i] = C->p[i];
+  }
+  C->p[n] = sum;
+  for (i64 e = 0; e < nz; e++) {
+    i64 px = w[T->i[e]]++;
+    C->j[px] = T->j[e];
+    if (C->x != NULL) C->x[px] = T->x[e];
+  }
+  /* sum duplicates (first occurrence keeps its position) */
+  i64 *pos = spasm_malloc((i64)m * sizeof(i64));
+  for (int j = 0; j < m; j++) pos[j] = -1;
+  i64 out = 0;
+  for (int i = 0; i < n; i++) {
+    i64 start = out, p0 = C->p[i], p1 = C->p[i + 1];
+    for (i64 px = p0; px < p1; px++) {
+      int j = C->j[px];
+      if (pos[j] >= start) {
+        if (C->x != NULL) C->x[pos[j]] = spasm_ZZp_add(C->field, C->x[pos[j]], C->x[px]);
+      } else {
+        pos[j] = out;
+        C->j[out] = j;
+        if (C->x != NULL) C->x[out] = C->x[px];
+        out++;
+      }
+    }
+    if (C->x != NULL) { /* drop zero sums */
+      i64 o2 = start;
+      for (i64 px = start; px < out; px++) {
+        pos[C->j[px]] = -1;
+        if (C->x[px] != 0) {
+          C->j[o2] = C->j[px];
+          C->x[o2] = C->x[px];
+          o2++;
+        }
+      }
+      out = o2;
+    } else {
+      for (i64 px = start; px < out; px++) pos[C->j[px]] = -1;
+    }
+    C->p[i] = start;
+  }
+  C->p[n] = out;
+  free(pos);
+  free(w);
+  return C;
+}
+
+/* ------------------------------------------------------------------ SMS I/O (spasm_io.c, src/SpaSM.jl:498-529,1029-1086) */
+
+struct spasm_triplet *spasm_triplet_load(FILE *f, i64 prime, u8 *hash) {
+  int n, m;
+  char type;
+  if (fscanf(f, "%d %d %c\n", &n, &m, &type) != 3) {
+    logprintf("[spasm_triplet_load] bad SMS file (header)\n");
+    return NULL;
+  }
+  struct spasm_triplet *T = spasm_triplet_alloc(n, m, 1, prime, true);
+  i64 i, j, x;
+  while (fscanf(f, "%" SCNd64 " %" SCNd64 " %" SCNd64 "\n", &i, &j, &x) == 3) {
+    if (i == 0 && j == 0 && x == 0) break;
+    spasm_add_entry(T, (int)(i - 1), (int)(j - 1), x);
+  }
+  if (hash != NULL) memset(hash, 0, 32); /* SHA-256 certificate hashing is out of scope */
+  return T;
+}
+
+void spasm_triplet_save(const struct spasm_triplet *A, FILE *f) {
+  fprintf(f, "%d %d M\n", A->n, A->m);
+  for (i64 px = 0; px < A->nz; px++)
+    fprintf(f, "%d %d %d\n", A->i[px] + 1, A->j[px] + 1, (A->x != NULL) ? A->x[px] : 1);
+  fprintf(f, "0 0 0\n");
+}
+
+void spasm_csr_save(const struct spasm_csr *A, FILE *f) {
+  fprintf(f, "%d %d M\n", A->n, A->m);
+  for (int i = 0; i < A->n; i++)
+    for (i64 px = A->p[i]; px < A->p[i + 1]; px++)
+      fprintf(f, "%d %d %d\n", i + 1, A->j[px] + 1, (A->x != NULL) ? A->x[px] : 1);
+  fprintf(f, "0 0 0\n");
+}
+
+/* ------------------------------------------------------------------ transpose (spasm_transpose.c) */
+
+/* src/SpaSM.jl:589 (one argument), test/runtests.jl:12-15 (values survive).  Counting sort,
+ * stable in row order: each row of T is sorted by original row index. */
+struct spasm_csr *spasm_transpose(const struct spasm_csr *A) {
+  int m = A->m, n = A->n;
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  const spasm_ZZp *Ax = A->x;
+  struct spasm_csr *T = spasm_csr_alloc(m, n, spasm_nnz(A), A->field->p, Ax != NULL);
+  i64 *Tp = T->p;
+  int *Tj = T->j;
+  spasm_ZZp *Tx = T->x;
+  i64 *w = spasm_calloc(m + 1, sizeof(i64));
+  for (int i = 0; i < n; i++)
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) w[Aj[px]] += 1;
+  i64 sum = 0;
+  for (int j = 0; j < m; j++) {
+    Tp[j] = sum;
+    sum += w[j];
+    w[j] = Tp[j];
+  }
+  Tp[m] = sum;
+  for (int i = 0; i < n; i++)
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) {
+      i64 py = w[Aj[px]]++;
+      Tj[py] = i;
+      if (Tx != NULL) Tx[py] = Ax[px];
+    }
+  free(w);
+  return T;
+}
+
+/* ------------------------------------------------------------------ scatter / spmv */
+
+/* src/SpaSM.jl:619-620: x += beta*A[i] */
+void spasm_scatter(const struct spasm_csr *A, int i, spasm_ZZp beta, spasm_ZZp *x) {
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  const spasm_ZZp *Ax = A->x;
+  for (i64 px = Ap[i]; px < Ap[i + 1]; px++) {
+    int j = Aj[px];
+    x[j] = spasm_ZZp_axpy(A->field, beta, Ax[px], x[j]);
+  }
+}
+
+/* src/SpaSM.jl:640-644: y <- x.A + y */
+void spasm_xApy(const spasm_ZZp *x, const struct spasm_csr *A, spasm_ZZp *y) {
+  for (int i = 0; i < A->n; i++)
+    if (x[i] != 0) spasm_scatter(A, i, x[i], y);
+}
+
+/* src/SpaSM.jl:653-657: y <- A.x + y */
+void spasm_Axpy(const struct spasm_csr *A, const spasm_ZZp *x, spasm_ZZp *y) {
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  const spasm_ZZp *Ax = A->x;
+  for (int i = 0; i < A->n; i++) {
+    spasm_ZZp acc = y[i];
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) acc = spasm_ZZp_axpy(A->field, Ax[px], x[Aj[px]], acc);
+    y[i] = acc;
+  }
+}
+
+/* ------------------------------------------------------------------ reach / triangular solve */
+
+/* src/SpaSM.jl:627.  Iterative DFS on columns: successors of column j are the columns of row
+ * qinv[j] of G (none when qinv[j] < 0).  xj[0..head] is the recursion stack, xj[top..] the
+ * output (reverse post-order).  pstack holds the resume offset inside the row. */
+int spasm_dfs(int jstart, const struct spasm_csr *G, int top, int *xj, int *pstack, int *marks, const int *qinv) {
+  const i64 *Gp = G->p;
+  const int *Gj = G->j;
+  int head = 0;
+  xj[0] = jstart;
+  while (head >= 0) {
+    int j = xj[head];
+    int i = (qinv != NULL) ? qinv[j] : j;
+    if (!marks[j]) {
+      marks[j] = 1;
+      pstack[head] = 0;
+    }
+    int done = 1;
+    if (i >= 0) {
+      i64 p0 = Gp[i], p1 = Gp[i + 1];
+      for (i64 px = p0 + pstack[head]; px < p1; px++) {
+        int jj = Gj[px];
+        if (marks[jj]) continue;
+        pstack[head] = (int)(px - p0) + 1;
+        xj[++head] = jj;
+        done = 0;
+        break;
+      }
+    }
+    if (done) {
+      head--;
+      xj[--top] = j;
+    }
+  }
+  return top;
+}
+
+/* reach with one column optionally treated as non-pivotal (mask < 0: none) — used by rref */
+static int reach_masked(const struct spasm_csr *A, const struct spasm_csr *B, int k, int l, int *xj,
+                        const int *qinv, int mask, int *qtmp_slot) {
+  (void)qtmp_slot;
+  (void)mask;
+  const i64 *Bp = B->p;
+  const int *Bj = B->j;
+  int m = A->m;
+  int top = l;
+  int *pstack = xj + m;
+  int *marks = pstack + m;
+  for (i64 px = Bp[k]; px < Bp[k + 1]; px++)
+    if (!marks[Bj[px]]) top = spasm_dfs(Bj[px], A, top, xj, pstack, marks, qinv);
+  for (int px = top; px < l; px++) marks[xj[px]] = 0;
+  return top;
+}
+
+/* src/SpaSM.jl:628 */
+int spasm_reach(const struct spasm_csr *A, const struct spasm_csr *B, int k, int l, int *xj, const int *qinv) {
+  return reach_masked(A, B, k, l, xj, qinv, -1, NULL);
+}
+
+/* src/SpaSM.jl:694-722.  Solve x.U = B[k].  xj: 3m ints, zero on entry and on exit; x: m values,
+ * uninitialised on entry.  Returns top; pattern = xj[top:m] in topological order.
+ * Postcondition: x_b.U + x_a == B[k]  (x_b: pivotal columns, x_a: the others). */
+int spasm_sparse_triangular_solve(const struct spasm_csr *U, const struct spasm_csr *B, int k, int *xj,
+                                  spasm_ZZp *x, const int *qinv) {
+  int m = U->m;
+  const i64 *Bp = B->p;
+  const int *Bj = B->j;
+  const spasm_ZZp *Bx = B->x;
+  int top = spasm_reach(U, B, k, m, xj, qinv);
+  for (int px = top; px < m; px++) x[xj[px]] = 0;
+  for (i64 px = Bp[k]; px < Bp[k + 1]; px++) x[Bj[px]] = Bx[px];
+  for (int px = top; px < m; px++) {
+    int j = xj[px];
+    int i = qinv[j];
+    if (i < 0) continue;
+    spasm_ZZp save = x[j];
+    if (save == 0) continue; /* numerically nothing to do (the pattern stays structural) */
+    spasm_scatter(U, i, spasm_ZZp_sub(U->field, 0, save), x);
+    x[j] = save; /* U[i] has a 1 on column j: the scatter zeroed it */
+  }
+  return top;
+}
+
+/* src/SpaSM.jl:680-692: x.U = b, dense.  q[i] = pivot column of row i.  b destroyed. */
+bool spasm_dense_forward_solve(const struct spasm_csr *U, spasm_ZZp *b, spasm_ZZp *x, const int *q) {
+  int n = U->n, m = U->m;
+  for (int i = 0; i < n; i++) {
+    int j = q[i];
+    x[i] = b[j];
+    if (b[j] != 0) spasm_scatter(U, i, spasm_ZZp_sub(U->field, 0, b[j]), b);
+  }
+  for (int j = 0; j < m; j++)
+    if (b[j] != 0) return false;
+  return true;
+}
+
+/* src/SpaSM.jl:664-677: x.L = b, dense.  p[j] = row holding the "diagonal" entry of column j.
+ * L is n x r; rows without a diagonal get x = 0.  b destroyed. */
+bool spasm_dense_back_solve(const struct spasm_csr *L, spasm_ZZp *b, spasm_ZZp *x, const int *p) {
+  int n = L->n, r = L->m;
+  const i64 *Lp = L->p;
+  const int *Lj = L->j;
+  const spasm_ZZp *Lx = L->x;
+  for (int i = 0; i < n; i++) x[i] = 0;
+  for (int k = r - 1; k >= 0; k--) {
+    int i = (p != NULL) ? p[k] : k;
+    spasm_ZZp diag = 0;
+    for (i64 px = Lp[i]; px < Lp[i + 1]; px++)
+      if (Lj[px] == k) {
+        diag = Lx[px];
+        break;
+      }
+    assert(diag != 0);
+    spasm_ZZp alpha = spasm_ZZp_inverse(L->field, diag);
+    x[i] = spasm_ZZp_mul(L->field, alpha, b[k]);
+    if (x[i] != 0) spasm_scatter(L, i, spasm_ZZp_sub(L->field, 0, x[i]), b);
+  }
+  return true;
+}
+
+/* ------------------------------------------------------------------ seeded PRNG (normalisation N4) */
+
+#define SPASM_SEED 0x5a5a5a5a2e6306e0ULL
+static u64 prng_state = SPASM_SEED;
+static u64 splitmix64(u64 *s) {
+  u64 z = (*s += 0x9e3779b97f4a7c15ULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+void spasm_b200_seed(u64 seed) { prng_state = seed; }
+
+/* ------------------------------------------------------------------ small sort helper (normalisation N1) */
+
+static int cmp_int(const void *a, const void *b) {
+  int x = *(const int *)a, y = *(const int *)b;
+  return (x > y) - (x < y);
+}
+static void sort_ints(int *a, int n) {
+  if (n < 24) {
+    for (int i = 1; i < n; i++) {
+      int v = a[i], k = i - 1;
+      while (k >= 0 && a[k] > v) {
+        a[k + 1] = a[k];
+        k--;
+      }
+      a[k + 1] = v;
+    }
+  } else
+    qsort(a, n, sizeof(int), cmp_int);
+}
+
+/* ------------------------------------------------------------------ structural pivots (spasm_pivots.c) */
+
+static int row_weight(const struct spasm_csr *A, int i) { return (int)(A->p[i + 1] - A->p[i]); }
+
+/* Faugère-Lachartre (README.md:21): pivot of column j = sparsest row whose leftmost entry is j,
+ * first row wins ties. */
+static int find_FL_pivots(const struct spasm_csr *A, int *pinv, int *qinv) {
+  int n = A->n;
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  int npiv = 0;
+  for (int i = 0; i < n; i++) {
+    int j = -1;
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++)
+      if (j == -1 || Aj[px] < j) j = Aj[px];
+    if (j == -1) continue; /* empty row */
+    if (qinv[j] == -1) {
+      pinv[i] = j;
+      qinv[j] = i;
+      npiv++;
+    } else if (row_weight(A, i) < row_weight(A, qinv[j])) {
+      pinv[qinv[j]] = -1;
+      pinv[i] = j;
+      qinv[j] = i;
+    }
+  }
+  return npiv;
+}
+
+/* "Faugère-Lachartre on columns" (README.md:22): a non-pivotal row can take as pivot its first
+ * entry (storage order) on a column that occurs in no pivotal row; taking it closes every column
+ * of that row. */
+static int find_FL_column_pivots(const struct spasm_csr *A, int *pinv, int *qinv) {
+  int n = A->n, m = A->m;
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  int npiv = 0;
+  char *w = spasm_malloc(m);
+  memset(w, 1, m);
+  for (int i = 0; i < n; i++) {
+    if (pinv[i] < 0) continue;
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) w[Aj[px]] = 0;
+  }
+  for (int i = 0; i < n; i++) {
+    if (pinv[i] >= 0) continue;
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) {
+      int j = Aj[px];
+      if (w[j] == 0 || qinv[j] >= 0) continue;
+      pinv[i] = j;
+      qinv[j] = i;
+      npiv++;
+      for (i64 py = Ap[i]; py < Ap[i + 1]; py++) w[Aj[py]] = 0;
+      break;
+    }
+  }
+  free(w);
+  return npiv;
+}
+
+/* greedy alternating cycle-free search (README.md:23).  For each non-pivotal row: BFS from its
+ * pivotal columns through pivot rows; a non-pivotal entry of the row that is never reached can be
+ * a pivot without creating a cycle; the first such entry in storage order is taken.  Sequential
+ * row order is the parity semantics. */
+static int find_cycle_free_pivots(const struct spasm_csr *A, int *pinv, int *qinv) {
+  int n = A->n, m = A->m;
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  int npiv = 0;
+  signed char *w = spasm_calloc(m, 1);
+  int *queue = spasm_malloc((i64)m * sizeof(int));
+  for (int i = 0; i < n; i++) {
+    if (pinv[i] >= 0) continue;
+    int head = 0, tail = 0, surviving = 0;
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) {
+      int j = Aj[px];
+      if (w[j] != 0) continue; /* duplicate column in a row: ignore */
+      if (qinv[j] < 0) {
+        w[j] = 1;
+        surviving++;
+      } else {
+        w[j] = -1;
+        queue[tail++] = j;
+      }
+    }
+    while (head < tail && surviving > 0) {
+      int j = queue[head++];
+      int I = qinv[j];
+      if (I < 0) continue;
+      for (i64 px = Ap[I]; px < Ap[I + 1]; px++) {
+        int jj = Aj[px];
+        if (w[jj] < 0) continue;
+        if (w[jj] > 0) surviving--;
+        w[jj] = -1;
+        queue[tail++] = jj;
+      }
+    }
+    if (surviving > 0) {
+      for (i64 px = Ap[i]; px < Ap[i + 1]; px++) {
+        int j = Aj[px];
+        if (w[j] == 1) {
+          pinv[i] = j;
+          qinv[j] = i;
+          npiv++;
+          break;
+        }
+      }
+    }
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) w[Aj[px]] = 0;
+    for (int px = 0; px < tail; px++) w[queue[px]] = 0;
+  }
+  free(w);
+  free(queue);
+  return npiv;
+}
+
+/* Normalisation N2.  height(i) = 0 if pivot row i holds no other pivotal column, else
+ * 1 + max height of the pivot rows of those columns.  p[0:npiv] = pivot rows by (height desc,
+ * row asc) so that each row of U only references pivot columns of LATER rows of U;
+ * p[npiv:n] = the other rows in increasing order. */
+static void reorder_pivots(const struct spasm_csr *A, const int *pinv, const int *qinv, int npiv, int *p) {
+  int n = A->n;
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  int *height = spasm_malloc((i64)n * sizeof(int));
+  int *stack = spasm_malloc((i64)(npiv + 1) * sizeof(int));
+  i64 *resume = spasm_malloc((i64)(npiv + 1) * sizeof(i64));
+  for (int i = 0; i < n; i++) height[i] = -1; /* -1 unknown, -2 on stack */
+  int maxh = 0;
+  for (int s = 0; s < n; s++) {
+    if (pinv[s] < 0 || height[s] >= 0) continue;
+    int head = 0;
+    stack[0] = s;
+    resume[0] = Ap[s];
+    height[s] = -2;
+    while (head >= 0) {
+      int i = stack[head];
+      int descended = 0;
+      for (i64 px = resume[head]; px < Ap[i + 1]; px++) {
+        int j = Aj[px];
+        if (j == pinv[i]) continue;
+        int i2 = qinv[j];
+        if (i2 < 0) continue;
+        if (height[i2] == -1) {
+          resume[head] = px; /* revisit this entry once i2 is known */
+          height[i2] = -2;
+          stack[++head] = i2;
+          resume[head] = Ap[i2];
+          descended = 1;
+          break;
+        }
+        assert(height[i2] != -2 && "structural pivots contain a cycle");
+      }
+      if (descended) continue;
+      int h = 0;
+      for (i64 px = Ap[i]; px < Ap[i + 1]; px++) {
+        int j = Aj[px];
+        if (j == pinv[i]) continue;
+        int i2 = qinv[j];
+        if (i2 >= 0 && height[i2] + 1 > h) h = height[i2] + 1;
+      }
+      height[i] = h;
+      if (h > maxh) maxh = h;
+      head--;
+    }
+  }
+  /* counting sort by height descending, stable in row index */
+  i64 *cnt = spasm_calloc(maxh + 2, sizeof(i64));
+  for (int i = 0; i < n; i++)
+    if (pinv[i] >= 0) cnt[maxh - height[i] + 1]++;
+  for (int h = 0; h <= maxh; h++) cnt[h + 1] += cnt[h];
+  for (int i = 0; i < n; i++)
+    if (pinv[i] >= 0) p[cnt[maxh - height[i]]++] = i;
+  int k = npiv;
+  for (int i = 0; i < n; i++)
+    if (pinv[i] < 0) p[k++] = i;
+  assert(k == n);
+  free(cnt);
+  free(resume);
+  free(stack);
+  free(height);
+}
+
+static void csr_ensure_room(struct spasm_csr *U, i64 need) {
+  if (need > U->nzmax) spasm_csr_realloc(U, 2 * U->nzmax + need);
+}
+
+static void U_ensure_rows(struct spasm_csr *U, int rows) {
+  /* U->p was allocated for the full row count of the input; nothing to do unless exceeded */
+  (void)U;
+  (void)rows;
+}
+
+/* prototype: src/SpaSM.jl:776-777.  Finds structural pivots of A, writes the permutation p
+ * (pivotal rows first, see reorder_pivots), appends the normalised pivot rows to fact->U and
+ * records them in fact->qinv (and in Ltmp / fact->p when L is requested).  Returns npiv. */
+int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, struct spasm_lu *fact, int *p,
+                                    struct echelonize_opts *opts) {
+  int n = A->n, m = A->m;
+  const i64 *Ap = A->p;
+  const int *Aj = A->j;
+  const spasm_ZZp *Ax = A->x;
+  struct spasm_csr *U = fact->U;
+  struct spasm_triplet *L = fact->Ltmp;
+  int *Uqinv = fact->qinv;
+  int *Lp = fact->p;
+  int *pinv = spasm_malloc((i64)n * sizeof(int));
+  int *qinv = spasm_malloc((i64)m * sizeof(int));
+  for (int i = 0; i < n; i++) pinv[i] = -1;
+  for (int j = 0; j < m; j++) qinv[j] = -1;
+
+  double start = spasm_wtime();
+  int npiv = find_FL_pivots(A, pinv, qinv);
+  logprintf("[pivots] Faugère-Lachartre: %d pivots found [%.1fs]\n", npiv, spasm_wtime() - start);
+  start = spasm_wtime();
+  int k = find_FL_column_pivots(A, pinv, qinv);
+  npiv += k;
+  logprintf("[pivots] ``Faugère-Lachartre on columns'': %d pivots found [%.1fs]\n", k, spasm_wtime() - start);
+  if (opts == NULL || opts->enable_greedy_pivot_search) {
+    start = spasm_wtime();
+    k = find_cycle_free_pivots(A, pinv, qinv);
+    npiv += k;
+    logprintf("[pivots] greedy alternating cycle-free search: %d pivots found [%.1fs]\n", k, spasm_wtime() - start);
+  }
+  logprintf("[pivots] %d pivots found\n", npiv);
+
+  reorder_pivots(A, pinv, qinv, npiv, p);
+
+  /* copy + normalise the pivotal rows into U: (j, 1) first, the rest scaled, in storage order */
+  for (int kk = 0; kk < npiv; kk++) {
+    int i = p[kk];
+    int j = pinv[i];
+    int i_orig = (p_in != NULL) ? p_in[i] : i;
+    i64 len = Ap[i + 1] - Ap[i];
+    csr_ensure_room(U, spasm_nnz(U) + len);
+    U_ensure_rows(U, U->n + 1);
+    i64 unz = U->p[U->n];
+    spasm_ZZp pivot = 0;
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++)
+      if (Aj[px] == j) {
+        pivot = Ax[px];
+        break;
+      }
+    assert(pivot != 0);
+    spasm_ZZp alpha = spasm_ZZp_inverse(A->field, pivot);
+    Uqinv[j] = U->n;
+    U->j[unz] = j;
+    U->x[unz] = 1;
+    unz++;
+    int seen_pivot = 0;
+    for (i64 px = Ap[i]; px < Ap[i + 1]; px++) {
+      if (Aj[px] == j && !seen_pivot) {
+        seen_pivot = 1;
+        continue;
+      }
+      U->j[unz] = Aj[px];
+      U->x[unz] = spasm_ZZp_mul(A->field, alpha, Ax[px]);
+      unz++;
+    }
+    if (L != NULL) {
+      spasm_add_entry(L, i_orig, U->n, pivot);
+      Lp[U->n] = i_orig;
+    }
+    U->n += 1;
+    U->p[U->n] = unz;
+  }
+  free(pinv);
+  free(qinv);
+  return npiv;
+}
+
+/* ------------------------------------------------------------------ Schur complement (spasm_schur.c) */
+
+/* prototype: src/SpaSM.jl:763-764; log line README.md:25.  R sampled rows (seeded PRNG, N4). */
+double spasm_schur_estimate_density(const struct spasm_csr *A, const int *p, int n, const struct spasm_csr *U,
+                                    const int *qinv, int R) {
+  if (n == 0) return 0;
+  int m = A->m;
+  if (m == U->n) return 0;
+  i64 nnz = 0;
+  spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
+  int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
+  for (int i = 0; i < R; i++) {
+    int inew = p[splitmix64(&prng_state) % (u64)n];
+    int top = spasm_sparse_triangular_solve(U, A, inew, xj, x, qinv);
+    for (int px = top; px < m; px++) {
+      int j = xj[px];
+      if (qinv[j] < 0 && x[j] != 0) nnz += 1;
+    }
+  }
+  free(x);
+  free(xj);
+  return ((double)nnz) / (m - U->n) / R;
+}
+
+struct rowbuf {
+  int *j;
+  spasm_ZZp *x;
+  i64 n, cap;
+};
+static void rowbuf_push(struct rowbuf *b, int j, spasm_ZZp x) {
+  if (b->n == b->cap) {
+    b->cap = 2 * b->cap + 1024;
+    b->j = spasm_realloc(b->j, b->cap * sizeof(int));
+    b->x = spasm_realloc(b->x, b->cap * sizeof(spasm_ZZp));
+  }
+  b->j[b->n] = j;
+  b->x[b->n] = x;
+  b->n++;
+}
+
+/* work counters filled by spasm_schur / spasm_kernel (algorithmic bytes are data
+ * dependent and counted by the oracle during its own run) */
+i64 spasm_b200_last_bytes = 0; /* B_schur */
+i64 spasm_b200_last_macs = 0;  /* MAC_schur */
+
+/* prototype: src/SpaSM.jl:761-762; log line README.md:26.  For each row p[k], k < n, of A:
+ * eliminate against U; entries on non-pivotal columns form row k of S (same m columns, no
+ * renumbering); with L != NULL the multipliers go to L as (orig row, U row, value).
+ * Rows are emitted in input order (N3), entries in increasing column order (N1). */
+struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, const struct spasm_lu *fact,
+                              double est_density, struct spasm_triplet *L, const int *p_in, int *p_out) {
+  (void)est_density;
+  int m = A->m;
+  const struct spasm_csr *U = fact->U;
+  const int *qinv = fact->qinv;
+  const i64 *Up = U->p;
+  double start = spasm_wtime();
+  int nthreads = spasm_get_num_threads();
+  struct rowbuf *S_buf = spasm_calloc(nthreads, sizeof(*S_buf));
+  struct rowbuf *L_buf = spasm_calloc(nthreads, sizeof(*L_buf));
+  i64 *cnt = spasm_calloc(n + 1, sizeof(i64));
+  i64 *lcnt = spasm_calloc(n + 1, sizeof(i64));
+  i64 *off = spasm_malloc((i64)(n + 1) * sizeof(i64));
+  i64 *loff = spasm_malloc((i64)(n + 1) * sizeof(i64));
+  int *owner = spasm_malloc((i64)(n + 1) * sizeof(int));
+  i64 bytes = 0, macs = 0;
+#pragma omp parallel reduction(+ : bytes, macs)
+  {
+    int tid = spasm_get_thread_num();
+    spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
+    int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
+    int *cols = spasm_malloc((i64)m * sizeof(int));
+#pragma omp for schedule(dynamic, 64)
+    for (int k = 0; k < n; k++) {
+      int i = p[k];
+      int top = spasm_sparse_triangular_solve(U, A, i, xj, x, qinv);
+      int nc = 0, nl = 0;
+      bytes += 8 * (A->p[i + 1] - A->p[i]) + 8;
+      for (int px = top; px < m; px++) {
+        int j = xj[px];
+        if (x[j] == 0) continue;
+        if (qinv[j] < 0)
+          cols[nc++] = j;
+        else {
+          int r = qinv[j];
+          bytes += 8 * (Up[r + 1] - Up[r]) + 8;
+          macs += Up[r + 1] - Up[r];
+          if (L != NULL) cols[m - 1 - (nl++)] = j;
+        }
+      }
+      sort_ints(cols, nc);
+      owner[k] = tid;
+      off[k] = S_buf[tid].n;
+      cnt[k] = nc;
+      for (int c = 0; c < nc; c++) rowbuf_push(&S_buf[tid], cols[c], x[cols[c]]);
+      bytes += 8 * (i64)nc + 8;
+      if (L != NULL) {
+        /* multipliers, stored by increasing U row */
+        int *lc = cols + (m - nl);
+        for (int c = 0; c < nl; c++) lc[c] = qinv[lc[c]];
+        sort_ints(lc, nl);
+        loff[k] = L_buf[tid].n;
+        lcnt[k] = nl;
+        for (int c = 0; c < nl; c++) {
+          int r = lc[c];
+          int j = U->j[Up[r]]; /* pivot column = first stored entry of U row r */
+          rowbuf_push(&L_buf[tid], r, x[j]);
+        }
+      }
+    }
+    free(x);
+    free(xj);
+    free(cols);
+  }
+  i64 snz = 0;
+  for (int k = 0; k < n; k++) snz += cnt[k];
+  struct spasm_csr *S = spasm_csr_alloc(n, m, snz, A->field->p, true);
+  i64 pos = 0;
+  for (int k = 0; k < n; k++) {
+    S->p[k] = pos;
+    struct rowbuf *b = &S_buf[owner[k]];
+    memcpy(S->j + pos, b->j + off[k], cnt[k] * sizeof(int));
+    memcpy(S->x + pos, b->x + off[k], cnt[k] * sizeof(spasm_ZZp));
+    pos += cnt[k];
+    int i = p[k];
+    int i_orig = (p_in != NULL) ? p_in[i] : i;
+    if (p_out != NULL) p_out[k] = i_orig;
+    if (L != NULL) {
+      struct rowbuf *lb = &L_buf[owner[k]];
+      for (i64 c = 0; c < lcnt[k]; c++) spasm_add_entry(L, i_orig, lb->j[loff[k] + c], lb->x[loff[k] + c]);
+    }
+  }
+  S->p[n] = pos;
+  for (int t = 0; t < nthreads; t++) {
+    free(S_buf[t].j);
+    free(S_buf[t].x);
+    free(L_buf[t].j);
+    free(L_buf[t].x);
+  }
+  free(S_buf);
+  free(L_buf);
+  free(cnt);
+  free(lcnt);
+  free(off);
+  free(loff);
+  free(owner);
+  spasm_b200_last_bytes = bytes;
+  spasm_b200_last_macs = macs;
+  double density = (n > 0 && m > U->n) ? (double)snz / ((double)n * (m - U->n)) : 0.0;
+  logprintf("Schur complement: %d * %d [%" PRId64 " nz / density= %.3f], %.1fs\n", n, m, snz, density,
+            spasm_wtime() - start);
+  return S;
+}
+
+/* ------------------------------------------------------------------ dense tail (replaces spasm_ffpack_rref, src/SpaSM.jl:805) */
+
+/* In-place Gauss-Jordan with leftmost pivots.  The reduced row echelon form is unique, so the
+ * VALUES equal what FFPACK's RREF produces; pivcol = column rank profile. */
+int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, int *pivcol) {
+  spasm_field F;
+  spasm_field_init(prime, F);
+  int rank = 0;
+  const int use_double = (prime < (1LL << 26));
+  const double dp = (double)prime, dinv = 1.0 / (double)prime;
+  for (int c = 0; c < m && rank < n; c++) {
+    int piv = -1;
+    for (int r = rank; r < n; r++)
+      if (A[(i64)r * ldA + c] != 0) {
+        piv = r;
+        break;
+      }
+    if (piv < 0) continue;
+    spasm_ZZp *P = A + (i64)rank * ldA;
+    if (piv != rank) {
+      spasm_ZZp *Q = A + (i64)piv * ldA;
+      for (int k = 0; k < m; k++) {
+        spasm_ZZp t = P[k];
+        P[k] = Q[k];
+        Q[k] = t;
+      }
+    }
+    spasm_ZZp alpha = spasm_ZZp_inverse(F, P[c]);
+    if (alpha != 1)
+      for (int k = c; k < m; k++) P[k] = spasm_ZZp_mul(F, alpha, P[k]);
+#pragma omp parallel for schedule(static) if ((i64)n * (m - c) > 200000)
+    for (int r = 0; r < n; r++) {
+      if (r == rank) continue;
+      spasm_ZZp *Rw = A + (i64)r * ldA;
+      spasm_ZZp f = Rw[c];
+      if (f == 0) continue;
+      if (use_double) {
+        const double mf = -(double)f;
+        const double half = (double)F->halfp, mhalf = (double)F->mhalfp;
+        for (int k = c; k < m; k++) {
+          double t = (double)Rw[k] + mf * (double)P[k];
+          double q = rint(t * dinv);
+          t -= q * dp;
+          if (t > half) t -= dp;
+          if (t < mhalf) t += dp;
+          Rw[k] = (spasm_ZZp)t;
+        }
+      } else {
+        spasm_ZZp mf = spasm_ZZp_sub(F, 0, f);
+        for (int k = c; k < m; k++) Rw[k] = spasm_ZZp_axpy(F, mf, P[k], Rw[k]);
+      }
+    }
+    pivcol[rank] = c;
+    rank++;
+  }
+  return rank;
+}
+
+/* ------------------------------------------------------------------ echelonize (spasm_echelonize.c) */
+
+/* src/SpaSM.jl:817 — defaults per SURVEY.md §8a4 */
+void spasm_echelonize_init_opts(struct echelonize_opts *opts) {
+  opts->enable_greedy_pivot_search = 1;
+  opts->enable_tall_and_skinny = 1;
+  opts->enable_dense = 1;
+  opts->enable_GPLU = 1;
+  opts->L = 0;
+  opts->complete = 0;
+  opts->min_pivot_proportion = 0.1;
+  opts->max_round = 3;
+  opts->sparsity_threshold = 0.05;
+  opts->dense_block_size = 1000;
+  opts->low_rank_ratio = 0.5;
+  opts->tall_and_skinny_ratio = 5;
+  opts->low_rank_start_weight = -1;
+}
+
+/* sparse tail (README.md:34-36): row by row, eliminate against the growing U, pivot on the
+ * leftmost surviving non-pivotal column, normalise, append. */
+static void echelonize_GPLU(const struct spasm_csr *A, const int *p, int n, const int *p_in, struct spasm_lu *fact,
+                            struct echelonize_opts *opts) {
+  (void)opts;
+  int m = A->m;
+  struct spasm_csr *U = fact->U;
+  struct spasm_triplet *L = fact->Ltmp;
+  int *Uqinv = fact->qinv;
+  int *Lp = fact->p;
+  logprintf("[echelonize/GPLU] processing matrix of dimension %d x %d\n", n, m);
+  spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
+  int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
+  int *cols = spasm_malloc((i64)m * sizeof(int));
+  for (int k = 0; k < n; k++) {
+    if (U->n == m) {
+      logprintf("\n[echelonize/GPLU] full rank reached\n");
+      break;
+    }
+    int i = p[k];
+    int i_orig = (p_in != NULL) ? p_in[i] : i;
+    int top = spasm_sparse_triangular_solve(U, A, i, xj, x, Uqinv);
+    int jpiv = m, nc = 0, nl = 0;
+    for (int px = top; px < m; px++) {
+      int j = xj[px];
+      if (x[j] == 0) continue;
+      if (Uqinv[j] < 0) {
+        cols[nc++] = j;
+        if (j < jpiv) jpiv = j;
+      } else if (L != NULL)
+        cols[m - 1 - (nl++)] = Uqinv[j];
+    }
+    if (L != NULL) {
+      int *lc = cols + (m - nl);
+      sort_ints(lc, nl);
+      for (int c = 0; c < nl; c++) {
+        int r = lc[c];
+        spasm_add_entry(L, i_orig, r, x[U->j[U->p[r]]]);
+      }
+    }
+    if (jpiv == m) continue; /* the row reduced to zero */
+    if (L != NULL) {
+      Lp[U->n] = i_orig;
+      spasm_add_entry(L, i_orig, U->n, x[jpiv]);
+    }
+    sort_ints(cols, nc);
+    csr_ensure_room(U, spasm_nnz(U) + nc);
+    i64 unz = U->p[U->n];
+    Uqinv[jpiv] = U->n;
+    U->j[unz] = jpiv;
+    U->x[unz] = 1;
+    unz++;
+    spasm_ZZp beta = spasm_ZZp_inverse(A->field, x[jpiv]);
+    for (int c = 0; c < nc; c++) {
+      int j = cols[c];
+      if (j == jpiv) continue;
+      U->j[unz] = j;
+      U->x[unz] = spasm_ZZp_mul(A->field, beta, x[j]);
+      unz++;
+    }
+    U->n += 1;
+    U->p[U->n] = unz;
+  }
+  free(x);
+  free(xj);
+  free(cols);
+}
+
+/* dense tail (prototypes src/SpaSM.jl:765-766, :805): blocks of dense_block_size
+ * rows are eliminated against U, gathered on the non-pivotal columns, put in RREF; the reduced
+ * rows are appended to U as (pivot col, 1) then the non-pivot part in increasing column order. */
+static void echelonize_dense(const struct spasm_csr *A, const int *p, int n, const int *p_in, struct spasm_lu *fact,
+                             struct echelonize_opts *opts) {
+  (void)p_in;
+  int m = A->m;
+  struct spasm_csr *U = fact->U;
+  int *Uqinv = fact->qinv;
+  i64 prime = A->field->p;
+  int block = opts->dense_block_size > 0 ? opts->dense_block_size : 1000;
+  spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
+  int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
+  int *q = spasm_malloc((i64)m * sizeof(int));
+  int *qpos = spasm_malloc((i64)m * sizeof(int));
+  int processed = 0;
+  while (processed < n) {
+    int Sm = m - U->n;
+    if (Sm == 0) break;
+    int Sn = (n - processed < block) ? n - processed : block;
+    logprintf("[echelonize/dense] processing dense schur complement of dimension %d x %d; block size=%d\n",
+              n - processed, Sm, block);
+    int c = 0;
+    for (int j = 0; j < m; j++) {
+      qpos[j] = -1;
+      if (Uqinv[j] < 0) {
+        q[c] = j;
+        qpos[j] = c++;
+      }
+    }
+    assert(c == Sm);
+    spasm_ZZp *S = spasm_calloc((i64)Sn * Sm, sizeof(spasm_ZZp));
+    int *pivcol = spasm_malloc((i64)Sn * sizeof(int));
+    for (int k = 0; k < Sn; k++) {
+      int i = p[processed + k];
+      int top = spasm_sparse_triangular_solve(U, A, i, xj, x, Uqinv);
+      for (int px = top; px < m; px++) {
+        int j = xj[px];
+        if (Uqinv[j] < 0) S[(i64)k * Sm + qpos[j]] = x[j];
+      }
+    }
+    int rr = spasm_dense_rref(prime, Sn, Sm, S, Sm, pivcol);
+    for (int i = 0; i < rr; i++) {
+      const spasm_ZZp *row = S + (i64)i * Sm;
+      i64 cntnz = 0;
+      for (int k = 0; k < Sm; k++)
+        if (row[k] != 0) cntnz++;
+      csr_ensure_room(U, spasm_nnz(U) + cntnz);
+      i64 unz = U->p[U->n];
+      int jp = q[pivcol[i]];
+      Uqinv[jp] = U->n;
+      U->j[unz] = jp;
+      U->x[unz] = 1;
+      unz++;
+      for (int k = 0; k < Sm; k++) {
+        if (k == pivcol[i] || row[k] == 0) continue;
+        U->j[unz] = q[k];
+        U->x[unz] = row[k];
+        unz++;
+      }
+      U->n += 1;
+      U->p[U->n] = unz;
+    }
+    free(S);
+    free(pivcol);
+    processed += Sn;
+    logprintf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U->n);
+  }
+  free(x);
+  free(xj);
+  free(q);
+  free(qpos);
+}
+
+/* src/SpaSM.jl:860-866 — THE entry point.  Loop (README.md:19-32): structural pivots -> density
+ * estimate -> Schur complement, at most max_round times; then finish dense or GPLU. */
+struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_opts *opts) {
+  struct echelonize_opts default_opts;
+  if (opts == NULL) {
+    spasm_echelonize_init_opts(&default_opts);
+    opts = &default_opts;
+  }
+  int n = A->n, m = A->m;
+  i64 prime = A->field->p;
+  prng_state = SPASM_SEED;
+  logprintf("[echelonize] Start on %d x %d matrix with %" PRId64 " nnz\n", n, m, spasm_nnz(A));
+  if (opts->complete) opts->L = 1;
+
+  struct spasm_csr *U = spasm_csr_alloc(n, m, spasm_nnz(A), prime, true);
+  int *Uqinv = spasm_malloc((i64)m * sizeof(int));
+  U->n = 0;
+  for (int j = 0; j < m; j++) Uqinv[j] = -1;
+  struct spasm_triplet *L = NULL;
+  int *Lp = NULL;
+  if (opts->L) {
+    L = spasm_triplet_alloc(n, n, spasm_nnz(A), prime, true);
+    L->n = n;
+    i64 plen = (n > m) ? n : m; /* the Julia view wraps U.m entries (src/SpaSM.jl:297-300) */
+    Lp = spasm_malloc(plen * sizeof(int));
+    for (i64 j = 0; j < plen; j++) Lp[j] = -1;
+  }
+  struct spasm_lu *fact = spasm_malloc(sizeof(*fact));
+  fact->L = NULL;
+  fact->U = U;
+  fact->qinv = Uqinv;
+  fact->p = Lp;
+  fact->Ltmp = L;
+  fact->r = 0;
+  fact->complete = 0;
+
+  int *p = spasm_malloc((i64)(n > 0 ? n : 1) * sizeof(int));
+  for (int i = 0; i < n; i++) p[i] = i;
+  double start = spasm_wtime();
+  double density = (n > 0 && m > 0) ? (double)spasm_nnz(A) / n / m : 0.0;
+  int npiv = 0;
+  const int *p_in = NULL;
+  int *p_in_owned = NULL;
+  const struct spasm_csr *cur = A;
+  int finished = 0; /* 1: nothing left to do */
+  int go_dense = 0;
+
+  for (int round = 0; round < opts->max_round; round++) {
+    logprintf("[echelonize] round %d\n", round);
+    npiv = spasm_pivots_extract_structural(cur, p_in, fact, p, opts);
+    int rem_rows = n - npiv, rem_cols = m - U->n;
+    if (rem_rows == 0 || rem_cols == 0) {
+      finished = 1;
+      break;
+    }
+    int bound = (n < rem_cols) ? n : rem_cols;
+    if (npiv < opts->min_pivot_proportion * bound) {
+      logprintf("[echelonize] not enough pivots found; stopping\n");
+      break;
+    }
+    density = spasm_schur_estimate_density(cur, p + npiv, rem_rows, U, Uqinv, 100);
+    logprintf("Schur complement is %d x %d, estimated density : %.2f (%" PRId64 " byte)\n", rem_rows, rem_cols, density,
+              (i64)(4.0 * density * rem_rows * rem_cols));
+    if (density > opts->sparsity_threshold && opts->enable_dense) {
+      logprintf("[echelonize] Schur complement is dense; stopping\n");
+      go_dense = 1;
+      break;
+    }
+    int *p_out = spasm_malloc((i64)rem_rows * sizeof(int));
+    struct spasm_csr *S = spasm_schur(cur, p + npiv, rem_rows, fact, density, L, p_in, p_out);
+    if (cur != A) spasm_csr_free((struct spasm_csr *)cur);
+    free(p_in_owned);
+    cur = S;
+    p_in = p_in_owned = p_out;
+    n = S->n;
+    npiv = 0;
+    for (int i = 0; i < n; i++) p[i] = i;
+    density = (n > 0 && rem_cols > 0) ? (double)spasm_nnz(S) / n / rem_cols : 0.0;
+  }
+
+  if (!finished) {
+    int rem_rows = n - npiv;
+    double aspect_ratio = (double)rem_rows / m;
+    logprintf("[echelonize] finishing; density = %.3f; aspect ratio = %.1f\n", density, aspect_ratio);
+    if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
+      echelonize_GPLU(cur, p + npiv, rem_rows, p_in, fact, opts);
+    else if (opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
+      echelonize_dense(cur, p + npiv, rem_rows, p_in, fact, opts);
+    else if (opts->enable_GPLU)
+      echelonize_GPLU(cur, p + npiv, rem_rows, p_in, fact, opts);
+    else if (opts->enable_dense)
+      echelonize_dense(cur, p + npiv, rem_rows, p_in, fact, opts);
+    else
+      logprintf("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
+  }
+
+  if (cur != A) spasm_csr_free((struct spasm_csr *)cur);
+  free(p_in_owned);
+  free(p);
+  fact->r = U->n;
+  spasm_csr_resize(U, U->n, m);
+  spasm_csr_realloc(U, -1);
+  if (opts->L) {
+    /* L: n x r, rows sorted by U-row index (N1) */
+    L->m = (U->n > 0) ? U->n : L->m;
+    struct spasm_csr *Lc = spasm_compress(L);
+    spasm_csr_resize(Lc, A->n, U->n);
+    for (int i = 0; i < Lc->n; i++) {
+      /* insertion sort by column, rows are short */
+      for (i64 a = Lc->p[i] + 1; a < Lc->p[i + 1]; a++) {
+        int cj = Lc->j[a];
+        spasm_ZZp cx = Lc->x[a];
+        i64 b = a - 1;
+        while (b >= Lc->p[i] && Lc->j[b] > cj) {
+          Lc->j[b + 1] = Lc->j[b];
+          Lc->x[b + 1] = Lc->x[b];
+          b--;
+        }
+        Lc->j[b + 1] = cj;
+        Lc->x[b + 1] = cx;
+      }
+    }
+    fact->L = Lc;
+    spasm_triplet_free(L);
+    fact->Ltmp = NULL;
+    fact->complete = 1;
+  }
+  logprintf("[echelonize] Done in %.1fs. Rank %d, %" PRId64 " nz in basis\n", spasm_wtime() - start, U->n,
+            spasm_nnz(U));
+  return fact;
+}
+
+/* ------------------------------------------------------------------ rref (spasm_rref.c, src/SpaSM.jl:871) */
+
+/* Each row of U reduced against all OTHER pivot rows.  Row i of R: (pivot col, 1) first, then the
+ * non-pivotal columns in increasing order.  Rqinv[pivot col] = i, -1 elsewhere. */
+struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv) {
+  const struct spasm_csr *U = fact->U;
+  const int *Uqinv = fact->qinv;
+  int n = U->n, m = U->m;
+  const i64 *Up = U->p;
+  const int *Uj = U->j;
+  i64 *cnt = spasm_calloc(n + 1, sizeof(i64));
+  struct rowbuf buf = {0};
+  spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
+  int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
+  int *cols = spasm_malloc((i64)m * sizeof(int));
+  int *qinv = spasm_malloc((i64)m * sizeof(int));
+  memcpy(qinv, Uqinv, (i64)m * sizeof(int));
+  for (int j = 0; j < m; j++) Rqinv[j] = -1;
+  for (int i = 0; i < n; i++) {
+    int jp = Uj[Up[i]];
+    assert(qinv[jp] == i);
+    qinv[jp] = -1; /* mask: do not eliminate the row against itself */
+    int top = spasm_sparse_triangular_solve(U, U, i, xj, x, qinv);
+    qinv[jp] = i;
+    int nc = 0;
+    for (int px = top; px < m; px++) {
+      int j = xj[px];
+      if (j != jp && qinv[j] < 0 && x[j] != 0) cols[nc++] = j;
+    }
+    sort_ints(cols, nc);
+    rowbuf_push(&buf, jp, 1);
+    for (int c = 0; c < nc; c++) rowbuf_push(&buf, cols[c], x[cols[c]]);
+    cnt[i] = nc + 1;
+    Rqinv[jp] = i;
+  }
+  struct spasm_csr *R = spasm_csr_alloc(n, m, buf.n, U->field->p, true);
+  i64 pos = 0;
+  for (int i = 0; i < n; i++) {
+    R->p[i] = pos;
+    pos += cnt[i];
+  }
+  R->p[n] = pos;
+  memcpy(R->j, buf.j, buf.n * sizeof(int));
+  memcpy(R->x, buf.x, buf.n * sizeof(spasm_ZZp));
+  free(buf.j);
+  free(buf.x);
+  free(cnt);
+  free(x);
+  free(xj);
+  free(cols);
+  free(qinv);
+  return R;
+}
+
+/* ------------------------------------------------------------------ kernel (spasm_kernel.c, src/SpaSM.jl:876-882) */
+
+/* README.md:39-41; goldens test/runtests.jl:17-24.  K is (m-r) x m, one row per non-pivotal
+ * column j in increasing j: (j, -1) first, then (pivot col of U row i, y_i) in increasing column
+ * order, where y solves the triangular system on Ut seeded by column j of U. */
+struct spasm_csr *spasm_kernel(const struct spasm_lu *fact) {
+  const struct spasm_csr *U = fact->U;
+  const int *qinv = fact->qinv;
+  int r = U->n, m = U->m;
+  double start = spasm_wtime();
+  logprintf("[kernel] start. U is %d x %d (%" PRId64 " nnz). Transposing U\n", r, m, spasm_nnz(U));
+  struct spasm_csr *Ut = spasm_transpose(U);
+  int *Utqinv = spasm_malloc((i64)(r > 0 ? r : 1) * sizeof(int));
+  for (int j = 0; j < m; j++)
+    if (qinv[j] >= 0) Utqinv[qinv[j]] = j;
+  int nfree = m - r;
+  i64 *cnt = spasm_calloc(nfree + 1, sizeof(i64));
+  i64 *off = spasm_malloc((i64)(nfree + 1) * sizeof(i64));
+  int *owner = spasm_malloc((i64)(nfree + 1) * sizeof(int));
+  int *freecol = spasm_malloc((i64)(nfree + 1) * sizeof(int));
+  int nf = 0;
+  for (int j = 0; j < m; j++)
+    if (qinv[j] < 0) freecol[nf++] = j;
+  assert(nf == nfree);
+  int nthreads = spasm_get_num_threads();
+  struct rowbuf *K_buf = spasm_calloc(nthreads, sizeof(*K_buf));
+  i64 bytes = 0, macs = 0;
+  const spasm_ZZp minus_one = spasm_ZZp_init(U->field, -1);
+#pragma omp parallel reduction(+ : bytes, macs)
+  {
+    int tid = spasm_get_thread_num();
+    int rr = (r > 0) ? r : 1;
+    spasm_ZZp *x = spasm_malloc((i64)rr * sizeof(*x));
+    int *xj = spasm_calloc(3 * (i64)rr, sizeof(int));
+    int *cols = spasm_malloc((i64)rr * sizeof(int));
+#pragma omp for schedule(dynamic, 64)
+    for (int f = 0; f < nfree; f++) {
+      int j = freecol[f];
+      int top = (r > 0) ? spasm_sparse_triangular_solve(Ut, Ut, j, xj, x, Utqinv) : 0;
+      int nc = 0;
+      bytes += 8 * (Ut->p[j + 1] - Ut->p[j]) + 8;
+      for (int px = top; px < r; px++) {
+        int i = xj[px];
+        if (x[i] == 0) continue;
+        cols[nc++] = Utqinv[i];
+        int tr = Utqinv[i];
+        bytes += 8 * (Ut->p[tr + 1] - Ut->p[tr]) + 8;
+        macs += Ut->p[tr + 1] - Ut->p[tr];
+      }
+      sort_ints(cols, nc);
+      owner[f] = tid;
+      off[f] = K_buf[tid].n;
+      cnt[f] = nc + 1;
+      rowbuf_push(&K_buf[tid], j, minus_one);
+      for (int c = 0; c < nc; c++) rowbuf_push(&K_buf[tid], cols[c], x[qinv[cols[c]]]);
+      bytes += 8 * (i64)(nc + 1) + 8;
+    }
+    free(x);
+    free(xj);
+    free(cols);
+  }
+  i64 knz = 0;
+  for (int f = 0; f < nfree; f++) knz += cnt[f];
+  struct spasm_csr *K = spasm_csr_alloc(nfree, m, knz, U->field->p, true);
+  i64 pos = 0;
+  for (int f = 0; f < nfree; f++) {
+    K->p[f] = pos;
+    struct rowbuf *b = &K_buf[owner[f]];
+    memcpy(K->j + pos, b->j + off[f], cnt[f] * sizeof(int));
+    memcpy(K->x + pos, b->x + off[f], cnt[f] * sizeof(spasm_ZZp));
+    pos += cnt[f];
+  }
+  K->p[nfree] = pos;
+  logprintf("kernel: %d/%d, |K| = %" PRId64 "\n", nfree, nfree, knz);
+  for (int t = 0; t < nthreads; t++) {
+    free(K_buf[t].j);
+    free(K_buf[t].x);
+  }
+  free(K_buf);
+  free(cnt);
+  free(off);
+  free(owner);
+  free(freecol);
+  free(Utqinv);
+  spasm_csr_free(Ut);
+  spasm_b200_last_bytes = bytes;
+  spasm_b200_last_macs = macs;
+  logprintf("[kernel] done in %.1fs. NNZ(K) = %" PRId64 "\n", spasm_wtime() - start, knz);
+  return K;
+}
+
+/* ------------------------------------------------------------------ solve (spasm_solve.c, src/SpaSM.jl:895-923) */
+
+/* x.A = b through A = L.U: z.U = b (forward), x.L = z (back).  b has U->m entries, x has L->n
+ * (= rows of A) entries.  Returns false when b is not in the row space. */
+bool spasm_solve(const struct spasm_lu *fact, const spasm_ZZp *b, spasm_ZZp *x) {
+  const struct spasm_csr *L = fact->L;
+  const struct spasm_csr *U = fact->U;
+  assert(L != NULL);
+  int m = U->m, r = U->n;
+  spasm_ZZp *y = spasm_malloc((i64)m * sizeof(*y));
+  spasm_ZZp *z = spasm_malloc((i64)(r > 0 ? r : 1) * sizeof(*z));
+  int *Uq = spasm_malloc((i64)(r > 0 ? r : 1) * sizeof(int));
+  for (int j = 0; j < m; j++)
+    if (fact->qinv[j] >= 0) Uq[fact->qinv[j]] = j;
+  memcpy(y, b, (i64)m * sizeof(*y));
+  bool ok = spasm_dense_forward_solve(U, y, z, Uq);
+  if (ok) spasm_dense_back_solve(L, z, x, fact->p);
+  free(y);
+  free(z);
+  free(Uq);
+  return ok;
+}
+
+/* src/SpaSM.jl:915-923: X.A = B row by row; X is B->n x (rows of A); ok[k] tells which rows hold. */
+struct spasm_csr *spasm_gesv(const struct spasm_lu *fact, const struct spasm_csr *B, bool *ok) {
+  const struct spasm_csr *L = fact->L;
+  assert(L != NULL);
+  int n = L->n, m = fact->U->m;
+  struct rowbuf buf = {0};
+  struct spasm_csr *X = spasm_csr_alloc(B->n, n, 0, B->field->p, true);
+  spasm_ZZp *b = spasm_malloc((i64)m * sizeof(*b));
+  spasm_ZZp *x = spasm_malloc((i64)(n > 0 ? n : 1) * sizeof(*x));
+  for (int k = 0; k < B->n; k++) {
+    X->p[k] = buf.n;
+    memset(b, 0, (i64)m * sizeof(*b));
+    for (i64 px = B->p[k]; px < B->p[k + 1]; px++) b[B->j[px]] = B->x[px];
+    ok[k] = spasm_solve(fact, b, x);
+    if (!ok[k]) continue;
+    for (int i = 0; i < n; i++)
+      if (x[i] != 0) rowbuf_push(&buf, i, x[i]);
+  }
+  X->p[B->n] = buf.n;
+  spasm_csr_realloc(X, buf.n);
+  memcpy(X->j, buf.j, buf.n * sizeof(int));
+  memcpy(X->x, buf.x, buf.n * sizeof(spasm_ZZp));
+  free(buf.j);
+  free(buf.x);
+  free(b);
+  free(x);
+  return X;
+}
