@@ -142,8 +142,8 @@ void spasm_xApy(const spasm_ZZp *x, const struct spasm_csr *A, spasm_ZZp *y); /*
 void spasm_Axpy(const struct spasm_csr *A, const spasm_ZZp *x, spasm_ZZp *y); /* y += A.x */
 
 /* ---- spasm_reach.c / spasm_triangular.c  (src/SpaSM.jl:627-628, :673-722) ---- */
-int spasm_dfs(int j, const struct spasm_csr *G, int top, int *xj, int *pstack, int *marks, const int *qinv);
-int spasm_reach(const struct spasm_csr *A, const struct spasm_csr *B, int k, int l, int *xj, const int *qinv);
+/* spasm_dfs / spasm_reach are quoted but NOT bound by the reference ("we don't expose these",
+ * src/SpaSM.jl:625-629): they are internal to the CPU algorithm and have no GPU counterpart. */
 int spasm_sparse_triangular_solve(const struct spasm_csr *U, const struct spasm_csr *B, int k, int *xj,
                                   spasm_ZZp *x, const int *qinv); /* :694-722 */
 bool spasm_dense_back_solve(const struct spasm_csr *L, spasm_ZZp *b, spasm_ZZp *x, const int *p); /* :673 */
@@ -173,8 +173,9 @@ struct spasm_csr *spasm_gesv(const struct spasm_lu *fact, const struct spasm_csr
  * column pivcol[i]; pivcol is increasing = column rank profile).  Returns the rank. */
 int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, int *pivcol);
 
-/* ---- library identification (not in libspasm) ---- */
+/* ---- library identification and instrumentation (not in libspasm) ---- */
 const char *spasm_b200_backend(void); /* "cuda-sm_100a" for the product, "cpu-oracle" for oracle/ */
+void spasm_b200_seed(u64 seed);       /* re-seed the PRNG of the density estimate (normalisation N4) */
 
 #ifdef __cplusplus
 }

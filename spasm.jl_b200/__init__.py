@@ -136,8 +136,6 @@ ABI = {
     "spasm_scatter": (None, [_P(_CSR), C.c_int32, C.c_int32, _P(C.c_int32)]),
     "spasm_xApy": (None, [_P(C.c_int32), _P(_CSR), _P(C.c_int32)]),
     "spasm_Axpy": (None, [_P(_CSR), _P(C.c_int32), _P(C.c_int32)]),
-    "spasm_dfs": (C.c_int32, [C.c_int32, _P(_CSR), C.c_int32, _P(C.c_int32), _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
-    "spasm_reach": (C.c_int32, [_P(_CSR), _P(_CSR), C.c_int32, C.c_int32, _P(C.c_int32), _P(C.c_int32)]),
     "spasm_sparse_triangular_solve": (C.c_int32, [_P(_CSR), _P(_CSR), C.c_int32, _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
     "spasm_dense_back_solve": (C.c_bool, [_P(_CSR), _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
     "spasm_dense_forward_solve": (C.c_bool, [_P(_CSR), _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
@@ -152,6 +150,7 @@ ABI = {
     "spasm_gesv": (_P(_CSR), [_P(_LU), _P(_CSR), _P(C.c_bool)]),
     "spasm_dense_rref": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32, _P(C.c_int32), C.c_int64, _P(C.c_int32)]),
     "spasm_b200_backend": (C.c_char_p, []),
+    "spasm_b200_seed": (None, [C.c_uint64]),
 }
 DATA_SYMBOLS = ["logcallback"]
 

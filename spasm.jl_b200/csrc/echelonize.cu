@@ -1,0 +1,475 @@
+// echelonize.cu — spasm_echelonize (src/SpaSM.jl:860-866) and its round loop on the GPU:
+// structural pivots -> density estimate -> Schur complement, at most max_round times, then the
+// dense or GPLU tail (README.md:19-38).  All matrices stay resident in HBM
+// between phases; only scalars (counts, densities) and the final factor cross PCIe.
+#include <algorithm>
+
+#include "dense.cuh"
+#include "pivots.cuh"
+
+namespace sb {
+
+extern WorkStats g_last_stats;
+
+static u64 g_seed_state = 0;
+static const u64 SEED0 = 0x5a5a5a5a2e6306e0ULL;
+static u64 sm64(u64 &s) {
+  u64 z = (s += 0x9e3779b97f4a7c15ULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+
+struct Echelon {
+  Fp F;
+  int64_t prime;
+  int n0, m;
+  DCsr U;
+  DBuf<int> Uqinv;
+  spasm_triplet *L = nullptr;  // host (only with opts->L)
+  int *Lp = nullptr;           // host
+  double t_pivots = 0, t_schur = 0, t_tail = 0;
+};
+
+// structural pivots of `cur` appended to U.  p (device, [n]) returns the permutation.
+static int structural_round(Echelon &E, const DCsr &cur, const std::vector<int> &p_in, bool greedy, PivotSearch &P) {
+  int counts[3];
+  double t0 = spasm_wtime();
+  find_structural_pivots(cur, greedy, P, counts);
+  sync();
+  logf("[pivots] Faugère-Lachartre: %d pivots found [%.1fs]\n", counts[0], spasm_wtime() - t0);
+  logf("[pivots] ``Faugère-Lachartre on columns'': %d pivots found [%.1fs]\n", counts[1], 0.0);
+  if (greedy) logf("[pivots] greedy alternating cycle-free search: %d pivots found [%.1fs]\n", counts[2], 0.0);
+  logf("[pivots] %d pivots found\n", P.npiv);
+  const int urow0 = E.U.n;
+  DBuf<uint32_t> pivval;
+  extract_pivot_rows(cur, P, E.U, E.Uqinv, E.F, pivval);
+  if (E.L != nullptr && P.npiv > 0) {
+    std::vector<int> hp(P.npiv);
+    std::vector<uint32_t> hv(P.npiv);
+    P.p.download(hp.data(), P.npiv);
+    pivval.download(hv.data(), P.npiv);
+    sync();
+    for (int k = 0; k < P.npiv; k++) {
+      int i = hp[k], i_orig = p_in.empty() ? i : p_in[i];
+      spasm_add_entry(E.L, i_orig, urow0 + k, (i64)hv[k]);
+      E.Lp[urow0 + k] = i_orig;
+    }
+  }
+  return P.npiv;
+}
+
+__global__ void k_gather_idx(const int *__restrict__ src, const int *__restrict__ idx, int n, int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+static double estimate_density(Echelon &E, const DCsr &cur, const int *rows_dev, int nrows, int R_) {
+  if (nrows == 0 || E.m == E.U.n) return 0;
+  std::vector<int> idx(R_);
+  for (int i = 0; i < R_; i++) idx[i] = (int)(sm64(g_seed_state) % (u64)nrows);
+  DBuf<int> didx(R_), sample(R_);
+  didx.upload(idx.data(), R_);
+  k_gather_idx<<<cdiv(R_, 128), 128, 0, stream()>>>(rows_dev, didx.p, R_, sample.p);
+  DBuf<PDesc> pdesc;
+  build_pdesc_U(E.U, E.Uqinv.p, pdesc);
+  SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, E.m};
+  SolveRows B{cur.p.p, cur.j.p, cur.x.p, sample.p, R_, nullptr};
+  SolveEmit Em;
+  Em.count_only = true;
+  SolveResult R;
+  solve_rows(G, B, Em, E.F, R);
+  return ((double)R.nnz) / (E.m - E.U.n) / R_;
+}
+
+static void add_L_entries(Echelon &E, const SolveResult &R, const std::vector<int> &orig_rows) {
+  const int n = (int)orig_rows.size();
+  std::vector<long long> lp(n + 1);
+  std::vector<int> lj(R.lnnz);
+  std::vector<uint32_t> lx(R.lnnz);
+  R.lp.download(lp.data(), n + 1);
+  if (R.lnnz) R.lj.download(lj.data(), R.lnnz), R.lx.download(lx.data(), R.lnnz);
+  sync();
+  for (int k = 0; k < n; k++)
+    for (long long e = lp[k]; e < lp[k + 1]; e++) spasm_add_entry(E.L, orig_rows[k], lj[e], (i64)lx[e]);
+}
+
+// ------------------------------------------------------------------ GPLU tail
+// Row-by-row semantics (README.md:34-36) reproduced by speculative batches: a batch of rows is
+// reduced against the current U in parallel; one warp then walks the batch in order and accepts
+// rows until it meets one that holds a column pivoted earlier in the same batch (that row needs
+// the new pivot row, so it and everything after it is re-solved in the next batch).
+__global__ void k_gplu_commit(const long long *__restrict__ Rp, const int *__restrict__ Rj, int wn, unsigned char *__restrict__ newpiv,
+                              int urows, int m, int *__restrict__ out /* [0]=ncommit [1]=npivots */, int *__restrict__ pivt) {
+  const int lane = threadIdx.x;
+  int np = 0, t = 0;
+  for (; t < wn; t++) {
+    if (urows + np == m) break;  // every column is pivotal: the remaining rows reduce to zero
+    const long long a = Rp[t], b = Rp[t + 1];
+    int conflict = 0;
+    for (long long e = a + lane; e < b; e += 32) conflict |= newpiv[Rj[e]];
+    if (__any_sync(0xffffffffu, conflict)) break;
+    if (b > a) {
+      if (lane == 0) {
+        newpiv[Rj[a]] = 1;  // entries are sorted: the first one is the leftmost column
+        pivt[np] = t;
+      }
+      np++;
+      __syncwarp();
+    }
+  }
+  if (urows + np == m) t = wn;
+  if (lane == 0) out[0] = t, out[1] = np;
+}
+__global__ void k_gplu_lens(const long long *__restrict__ Rp, const int *__restrict__ pivt, int np, int *__restrict__ len) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < np) len[k] = (int)(Rp[pivt[k] + 1] - Rp[pivt[k]]);
+  if (k == np) len[k] = 0;
+}
+template <bool SMALL>
+__global__ void k_gplu_append(const long long *__restrict__ Rp, const int *__restrict__ Rj, const uint32_t *__restrict__ Rx,
+                              const int *__restrict__ pivt, int np, const long long *__restrict__ pos, long long ubase, int urow0,
+                              long long *__restrict__ Up, int *__restrict__ Uj, uint32_t *__restrict__ Ux, int *__restrict__ Uqinv,
+                              unsigned char *__restrict__ newpiv, uint32_t *__restrict__ pivval, Fp F) {
+  int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= np) return;
+  const int t = pivt[k];
+  const long long a = Rp[t], b = Rp[t + 1], dst = ubase + pos[k];
+  const uint32_t pv = Rx[a];
+  const uint32_t beta = dev_inv(pv, F.p);
+  if (lane == 0) {
+    const int jp = Rj[a];
+    Uj[dst] = jp;
+    Ux[dst] = 1;
+    Uqinv[jp] = urow0 + k;
+    newpiv[jp] = 0;
+    Up[urow0 + k + 1] = dst + (b - a);
+    pivval[k] = pv;
+  }
+  for (long long e = a + 1 + lane; e < b; e += 32) {
+    Uj[dst + (e - a)] = Rj[e];
+    Ux[dst + (e - a)] = mulmod<SMALL>(beta, Rx[e], F);
+  }
+}
+
+static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, int nrows, const std::vector<int> &orig_rows) {
+  cudaStream_t s = stream();
+  const int m = E.m;
+  logf("[echelonize/GPLU] processing matrix of dimension %d x %d\n", nrows, m);
+  DBuf<unsigned char> newpiv(m);
+  newpiv.zero();
+  DBuf<int> out(2), pivt, len;
+  DBuf<long long> pos;
+  DBuf<PDesc> pdesc;
+  DBuf<uint32_t> pivval;
+  int batch = 256;
+  for (int done = 0; done < nrows;) {
+    if (E.U.n == m) {
+      logf("\n[echelonize/GPLU] full rank reached\n");
+      break;
+    }
+    const int wn = std::min(batch, nrows - done);
+    build_pdesc_U(E.U, E.Uqinv.p, pdesc);
+    SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m};
+    SolveRows B{cur.p.p, cur.j.p, cur.x.p, rows_dev + done, wn, nullptr};
+    SolveEmit Em;
+    Em.want_L = (E.L != nullptr);
+    SolveResult R;
+    solve_rows(G, B, Em, E.F, R);
+    pivt.alloc(wn);
+    k_gplu_commit<<<1, 32, 0, s>>>(R.p.p, R.j.p, wn, newpiv.p, E.U.n, m, out.p, pivt.p);
+    int h[2];
+    out.download(h, 2);
+    sync();
+    const int ncommit = h[0], np = h[1];
+    const int urow0 = E.U.n;
+    if (np > 0) {
+      len.alloc(np + 1);
+      pos.alloc(np + 1);
+      pivval.alloc(np);
+      k_gplu_lens<<<cdiv(np + 1, 256), 256, 0, s>>>(R.p.p, pivt.p, np, len.p);
+      exclusive_scan_i32_to_i64(len.p, pos.p, np + 1);
+      const long long add = fetch(pos.p + np);
+      csr_reserve(E.U, E.U.nnz + add, E.U.n + np);
+      if (E.F.small)
+        k_gplu_append<true><<<cdiv((long long)np * 32, 256), 256, 0, s>>>(R.p.p, R.j.p, R.x.p, pivt.p, np, pos.p, E.U.nnz, E.U.n, E.U.p.p,
+                                                                         E.U.j.p, E.U.x.p, E.Uqinv.p, newpiv.p, pivval.p, E.F);
+      else
+        k_gplu_append<false><<<cdiv((long long)np * 32, 256), 256, 0, s>>>(R.p.p, R.j.p, R.x.p, pivt.p, np, pos.p, E.U.nnz, E.U.n, E.U.p.p,
+                                                                          E.U.j.p, E.U.x.p, E.Uqinv.p, newpiv.p, pivval.p, E.F);
+      CK(cudaGetLastError());
+      E.U.nnz += add;
+      E.U.n += np;
+    }
+    if (E.L != nullptr) {
+      // multipliers of the committed rows, then the pivot entries
+      std::vector<long long> lp(wn + 1);
+      std::vector<int> lj(R.lnnz), ht(std::max(np, 1));
+      std::vector<uint32_t> lx(R.lnnz), hv(std::max(np, 1));
+      R.lp.download(lp.data(), wn + 1);
+      if (R.lnnz) R.lj.download(lj.data(), R.lnnz), R.lx.download(lx.data(), R.lnnz);
+      if (np) pivt.download(ht.data(), np), pivval.download(hv.data(), np);
+      sync();
+      int kp = 0;
+      for (int t = 0; t < ncommit; t++) {
+        const int i_orig = orig_rows[done + t];
+        for (long long e = lp[t]; e < lp[t + 1]; e++) spasm_add_entry(E.L, i_orig, lj[e], (i64)lx[e]);
+        if (kp < np && ht[kp] == t) {
+          E.Lp[urow0 + kp] = i_orig;
+          spasm_add_entry(E.L, i_orig, urow0 + kp, (i64)hv[kp]);
+          kp++;
+        }
+      }
+    }
+    done += ncommit;
+    batch = (ncommit == wn) ? std::min(batch * 2, 16384) : std::max(32, std::min(batch, 2 * ncommit + 32));
+  }
+}
+
+// ------------------------------------------------------------------ the driver
+static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
+  require_gpu();
+  echelonize_opts defaults;
+  if (opts == nullptr) {
+    spasm_echelonize_init_opts(&defaults);
+    opts = &defaults;
+  }
+  const int n0 = A->n, m = A->m;
+  const int64_t prime = A->field->p;
+  g_seed_state = SEED0;
+  const double start = spasm_wtime();
+  logf("[echelonize] Start on %d x %d matrix with %lld nnz\n", n0, m, (long long)spasm_nnz(A));
+  if (opts->complete) opts->L = 1;
+
+  Echelon E;
+  E.F = make_field(prime);
+  E.prime = prime, E.n0 = n0, E.m = m;
+  E.U.n = 0, E.U.m = m, E.U.nnz = 0;
+  E.U.p.alloc(n0 + 2);
+  E.U.p.zero();
+  E.U.j.alloc(std::max<int64_t>(spasm_nnz(A), 16));
+  E.U.x.alloc(std::max<int64_t>(spasm_nnz(A), 16));
+  E.Uqinv.alloc(std::max(m, 1));
+  E.Uqinv.fill_ff();
+  if (opts->L) {
+    E.L = spasm_triplet_alloc(n0, n0, std::max<i64>(spasm_nnz(A), 16), prime, true);
+    const i64 plen = std::max(n0, m) + 1;
+    E.Lp = (int *)spasm_malloc(plen * (i64)sizeof(int));
+    for (i64 i = 0; i < plen; i++) E.Lp[i] = -1;
+  }
+
+  DCsr A0, S;
+  upload_csr(A, A0, E.F);
+  const DCsr *cur = &A0;
+  int n = n0, npiv = 0;
+  std::vector<int> p_in;  // current row -> original row (empty: identity)
+  double density = (n0 > 0 && m > 0) ? (double)spasm_nnz(A) / n0 / m : 0.0;
+  bool finished = false, go_dense = false;
+  PivotSearch P;
+  P.p.alloc(std::max(n, 1));
+
+  for (int round = 0; round < opts->max_round; round++) {
+    logf("[echelonize] round %d\n", round);
+    double t0 = spasm_wtime();
+    npiv = structural_round(E, *cur, p_in, opts->enable_greedy_pivot_search, P);
+    E.t_pivots += spasm_wtime() - t0;
+    const int rem_rows = n - npiv, rem_cols = m - E.U.n;
+    if (rem_rows == 0 || rem_cols == 0) {
+      finished = true;
+      break;
+    }
+    const int bound = std::min(n, rem_cols);
+    if (npiv < opts->min_pivot_proportion * bound) {
+      logf("[echelonize] not enough pivots found; stopping\n");
+      break;
+    }
+    t0 = spasm_wtime();
+    density = estimate_density(E, *cur, P.p.p + npiv, rem_rows, 100);
+    logf("Schur complement is %d x %d, estimated density : %.2f (%lld byte)\n", rem_rows, rem_cols, density,
+         (long long)(4.0 * density * rem_rows * rem_cols));
+    if (density > opts->sparsity_threshold && opts->enable_dense) {
+      logf("[echelonize] Schur complement is dense; stopping\n");
+      go_dense = true;
+      break;
+    }
+    // ---- Schur complement on the non-pivotal rows
+    DBuf<PDesc> pdesc;
+    build_pdesc_U(E.U, E.Uqinv.p, pdesc);
+    SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m};
+    SolveRows B{cur->p.p, cur->j.p, cur->x.p, P.p.p + npiv, rem_rows, nullptr};
+    SolveEmit Em;
+    Em.want_L = (E.L != nullptr);
+    SolveResult R;
+    solve_rows(G, B, Em, E.F, R);
+    g_last_stats = R.stats;
+    std::vector<int> hp(rem_rows), p_out(rem_rows);
+    CK(cudaMemcpyAsync(hp.data(), P.p.p + npiv, (size_t)rem_rows * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    sync();
+    for (int k = 0; k < rem_rows; k++) p_out[k] = p_in.empty() ? hp[k] : p_in[hp[k]];
+    if (E.L != nullptr) add_L_entries(E, R, p_out);
+    DCsr Snew;
+    Snew.n = rem_rows, Snew.m = m, Snew.nnz = R.nnz;
+    Snew.p = std::move(R.p);
+    Snew.j = std::move(R.j);
+    Snew.x = std::move(R.x);
+    S = std::move(Snew);
+    cur = &S;
+    p_in.swap(p_out);
+    n = rem_rows;
+    npiv = 0;
+    density = (n > 0 && rem_cols > 0) ? (double)S.nnz / n / rem_cols : 0.0;
+    logf("Schur complement: %d * %d [%lld nz / density= %.3f], %.1fs\n", n, m, (long long)S.nnz, density, spasm_wtime() - t0);
+    E.t_schur += spasm_wtime() - t0;
+    // identity permutation for the finish stage if the loop ends here
+    if (P.p.n < (size_t)n) P.p.alloc(n);
+    {
+      std::vector<int> id(n);
+      for (int i = 0; i < n; i++) id[i] = i;
+      P.p.upload(id.data(), n);
+      sync();
+    }
+  }
+
+  if (!finished) {
+    const int rem_rows = n - npiv;
+    const double aspect_ratio = (double)rem_rows / m;
+    logf("[echelonize] finishing; density = %.3f; aspect ratio = %.1f\n", density, aspect_ratio);
+    std::vector<int> orig(rem_rows);
+    if (E.L != nullptr) {
+      std::vector<int> hp(rem_rows);
+      CK(cudaMemcpyAsync(hp.data(), P.p.p + npiv, (size_t)rem_rows * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+      sync();
+      for (int k = 0; k < rem_rows; k++) orig[k] = p_in.empty() ? hp[k] : p_in[hp[k]];
+    }
+    const double t0 = spasm_wtime();
+    if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
+      echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
+    else if (opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
+      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size);
+    else if (opts->enable_GPLU)
+      echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
+    else if (opts->enable_dense)
+      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size);
+    else
+      logf("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
+    E.t_tail += spasm_wtime() - t0;
+  }
+
+  // ---- the factor goes back to host memory (plain malloc arrays: src/SpaSM.jl:279-304 unsafe_loads them)
+  spasm_lu *fact = (spasm_lu *)spasm_malloc(sizeof(spasm_lu));
+  E.U.m = m;
+  {
+    spasm_csr *Uh = spasm_csr_alloc(E.U.n, m, E.U.nnz, prime, true);
+    CK(cudaMemcpyAsync(Uh->p, E.U.p.p, (size_t)(E.U.n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream()));
+    if (E.U.nnz) {
+      CK(cudaMemcpyAsync(Uh->j, E.U.j.p, (size_t)E.U.nnz * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+      DBuf<int> bal(E.U.nnz);
+      convert_to_balanced(E.U.x.p, bal.p, E.U.nnz, E.F);
+      CK(cudaMemcpyAsync(Uh->x, bal.p, (size_t)E.U.nnz * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    }
+    fact->U = Uh;
+  }
+  fact->qinv = (int *)spasm_malloc((i64)std::max(m, 1) * (i64)sizeof(int));
+  CK(cudaMemcpyAsync(fact->qinv, E.Uqinv.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  sync();
+  fact->r = E.U.n;
+  fact->complete = 0;
+  fact->L = nullptr;
+  fact->p = E.Lp;
+  fact->Ltmp = nullptr;
+  if (opts->L) {
+    // L: n0 x r, every row by increasing U-row index (N1)
+    E.L->n = n0;
+    E.L->m = std::max(E.U.n, 1);
+    spasm_csr *Lc = spasm_compress(E.L);
+    Lc->m = E.U.n;
+    for (int i = 0; i < Lc->n; i++) {
+      const i64 a = Lc->p[i], b = Lc->p[i + 1];
+      std::vector<std::pair<int, spasm_ZZp>> row(b - a);
+      for (i64 e = a; e < b; e++) row[e - a] = {Lc->j[e], Lc->x[e]};
+      std::sort(row.begin(), row.end());
+      for (i64 e = a; e < b; e++) Lc->j[e] = row[e - a].first, Lc->x[e] = row[e - a].second;
+    }
+    fact->L = Lc;
+    spasm_triplet_free(E.L);
+    fact->complete = 1;
+  }
+  logf("[echelonize] Done in %.1fs. Rank %d, %lld nz in basis\n", spasm_wtime() - start, fact->r, (long long)E.U.nnz);
+  return fact;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_opts *opts) {
+  try {
+    return echelonize_impl(A, opts);
+  } catch (const std::exception &e) {
+    logf("[spasm_b200] spasm_echelonize failed: %s\n", e.what());
+    return nullptr;
+  }
+}
+
+void spasm_lu_free(struct spasm_lu *N) {
+  if (!N) return;
+  free(N->qinv);
+  free(N->p);
+  spasm_csr_free(N->U);
+  spasm_csr_free(N->L);
+  spasm_triplet_free(N->Ltmp);
+  free(N);
+}
+
+// prototype src/SpaSM.jl:776-777: host structs in, host structs out (one round of structural pivots)
+int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, struct spasm_lu *fact, int *p,
+                                    struct echelonize_opts *opts) {
+  try {
+    require_gpu();
+    Echelon E;
+    E.prime = A->field->p;
+    E.F = make_field(E.prime);
+    E.n0 = A->n, E.m = A->m;
+    spasm_csr *Uh = fact->U;
+    upload_csr(Uh, E.U, E.F);
+    E.U.p.grow(Uh->n + A->n + 2);
+    E.Uqinv.alloc(std::max(A->m, 1));
+    E.Uqinv.upload(fact->qinv, A->m);
+    E.L = fact->Ltmp;
+    E.Lp = fact->p;
+    DCsr dA;
+    upload_csr(A, dA, E.F);
+    std::vector<int> pin;
+    if (p_in) pin.assign(p_in, p_in + A->n);
+    PivotSearch P;
+    const int urows0 = E.U.n;
+    const int npiv = structural_round(E, dA, pin, opts == nullptr || opts->enable_greedy_pivot_search, P);
+    if (A->n) P.p.download(p, A->n);
+    // write the grown U back into the caller's struct
+    const i64 unz = E.U.nnz;
+    if (unz > Uh->nzmax) spasm_csr_realloc(Uh, unz);
+    std::vector<long long> up(E.U.n + 1);
+    E.U.p.download(up.data(), E.U.n + 1);
+    sync();
+    for (int i = urows0; i <= E.U.n; i++) Uh->p[i] = up[i];
+    if (unz) {
+      const i64 old = up[urows0];
+      CK(cudaMemcpyAsync(Uh->j + old, E.U.j.p + old, (size_t)(unz - old) * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+      std::vector<uint32_t> hx(unz - old);
+      CK(cudaMemcpyAsync(hx.data(), E.U.x.p + old, (size_t)(unz - old) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream()));
+      sync();
+      for (i64 e = old; e < unz; e++) Uh->x[e] = to_bal(hx[e - old], E.F);
+    }
+    Uh->n = E.U.n;
+    E.Uqinv.download(fact->qinv, A->m);
+    sync();
+    return npiv;
+  } catch (const std::exception &e) {
+    logf("[spasm_b200] spasm_pivots_extract_structural failed: %s\n", e.what());
+    return -1;
+  }
+}
+
+}  // extern "C"

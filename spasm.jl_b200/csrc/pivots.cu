@@ -1,0 +1,480 @@
+// pivots.cu — structural pivot search on the GPU (replaces spasm_pivots_extract_structural,
+// prototype src/SpaSM.jl:775-778; phases README.md:21-24; algorithm SURVEY.md A.4).
+//
+// All three searches reproduce the SEQUENTIAL (single-thread libspasm) result exactly:
+//  * Faugère-Lachartre: per leading column arg-min of (weight,row) -> one 64-bit atomicMin per row.
+//  * FL on columns: order-dependent greedy, run as deterministic reservation rounds: every
+//    undecided row reserves its still-open columns with atomicMin(row id); a row that holds all
+//    its reservations cannot be influenced by any smaller undecided row and decides exactly as the
+//    sequential scan would.
+//  * greedy alternating cycle-free search: windows of rows run their BFS speculatively in parallel
+//    (one warp each, private generation-stamped marks), then one warp commits the window in row
+//    order, CONTINUING the BFS of a row from the pivots committed before it in the same window
+//    (reachability is monotone in the pivot set, so the continued closure equals the sequential
+//    one; a row that failed speculatively stays failed).
+//  * reorder: heights in the pivot DAG by relaxation, then a stable sort (normalisation N2).
+#include <cub/cub.cuh>
+
+#include "pivots.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------ Faugère-Lachartre
+__global__ void k_fl_scan(const long long *__restrict__ Ap, const int *__restrict__ Aj, int n,
+                          unsigned long long *__restrict__ best) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  long long a = Ap[i], b = Ap[i + 1];
+  if (a == b) return;
+  int mn = 0x7fffffff;
+  for (long long e = a + lane; e < b; e += 32) mn = min(mn, Aj[e]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if (lane == 0) atomicMin(&best[mn], ((unsigned long long)(unsigned)(b - a) << 32) | (unsigned)i);
+}
+__global__ void k_fl_commit(const unsigned long long *__restrict__ best, int m, int *__restrict__ pinv,
+                            int *__restrict__ qinv, int *__restrict__ npiv) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  unsigned long long b = best[j];
+  if (b == ~0ULL) return;
+  int i = (int)(b & 0xffffffffu);
+  pinv[i] = j;
+  qinv[j] = i;
+  atomicAdd(npiv, 1);
+}
+
+// ------------------------------------------------------------------ FL on columns
+__global__ void k_flc_close_pivot_rows(const long long *__restrict__ Ap, const int *__restrict__ Aj, int n,
+                                       const int *__restrict__ pinv, unsigned char *__restrict__ open) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n || pinv[i] < 0) return;
+  for (long long e = Ap[i] + lane; e < Ap[i + 1]; e += 32) open[Aj[e]] = 0;
+}
+// state[i]: 0 undecided, 1 decided
+__global__ void k_flc_reserve(const long long *__restrict__ Ap, const int *__restrict__ Aj, int n,
+                              const int *__restrict__ pinv, const int *__restrict__ qinv,
+                              const unsigned char *__restrict__ open, unsigned char *__restrict__ state,
+                              unsigned long long *__restrict__ res, unsigned round) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n || pinv[i] >= 0 || state[i]) return;
+  const unsigned long long key = ((unsigned long long)(~round) << 32) | (unsigned)i;
+  int any = 0;
+  for (long long e = Ap[i] + lane; e < Ap[i + 1]; e += 32) {
+    int j = Aj[e];
+    if (open[j] && qinv[j] < 0) {
+      atomicMin(&res[j], key);
+      any = 1;
+    }
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (!any && lane == 0) state[i] = 1;  // nothing open on this row, and columns never reopen
+}
+__global__ void k_flc_commit(const long long *__restrict__ Ap, const int *__restrict__ Aj, int n, int *__restrict__ pinv,
+                             int *__restrict__ qinv, unsigned char *__restrict__ open, unsigned char *__restrict__ state,
+                             const unsigned long long *__restrict__ res, unsigned round, int *__restrict__ counters) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n || pinv[i] >= 0 || state[i]) return;
+  const unsigned long long key = ((unsigned long long)(~round) << 32) | (unsigned)i;
+  const long long a = Ap[i], b = Ap[i + 1];
+  int ready = 1;
+  long long first = -1;  // position of the first eligible entry in storage order
+  for (long long e0 = a; e0 < b; e0 += 32) {
+    long long e = e0 + lane;
+    int elig = 0, mine = 1;
+    if (e < b) {
+      int j = Aj[e];
+      if (open[j] && qinv[j] < 0) {
+        elig = 1;
+        mine = (res[j] == key);
+      }
+    }
+    unsigned em = __ballot_sync(0xffffffffu, elig);
+    if (!__all_sync(0xffffffffu, mine)) ready = 0;
+    if (first < 0 && em) first = e0 + (__ffs(em) - 1);
+  }
+  if (!ready) {
+    if (lane == 0) counters[1] = 1;  // someone is still undecided
+    return;
+  }
+  if (first < 0) {
+    if (lane == 0) state[i] = 1;
+    return;
+  }
+  const int jp = Aj[first];
+  __syncwarp();
+  for (long long e = a + lane; e < b; e += 32) open[Aj[e]] = 0;
+  if (lane == 0) {
+    pinv[i] = jp;
+    qinv[jp] = i;
+    state[i] = 1;
+    atomicAdd(&counters[0], 1);
+  }
+}
+
+// ------------------------------------------------------------------ greedy cycle-free search
+static constexpr unsigned ST_CAND = 1, ST_SEEN = 2, ST_EXP = 3;
+
+struct GreedyArgs {
+  const long long *Ap;
+  const int *Aj;
+  int n, m;
+  int *pinv, *qinv;
+  const int *cand;  // non-pivotal rows, increasing
+  int ncand;
+  unsigned short *marks;  // [W][m]   (gen << 2 | state)
+  int *queue;             // [W][qcap]
+  int qcap;
+  int *surv, *head, *tail;  // [W]
+  int *newcol;              // [W]
+  int *npiv;
+};
+
+__device__ __forceinline__ unsigned mark_state(unsigned short s, unsigned gen) { return ((unsigned)s >> 2) == gen ? (s & 3u) : 0u; }
+
+// expand queued pivotal columns until the queue is empty or no candidate survives
+__device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *marks, int *q, int &head, int &tail, int &surviving,
+                                        unsigned gen, int lane) {
+  while (head < tail && surviving > 0) {
+    const int j = q[head++];
+    const int I = g.qinv[j];
+    if (I < 0) continue;
+    const long long a = g.Ap[I], b = g.Ap[I + 1];
+    for (long long e0 = a; e0 < b; e0 += 32) {
+      long long e = e0 + lane;
+      int push = 0, killed = 0, jj = 0;
+      if (e < b) {
+        jj = g.Aj[e];
+        unsigned st = mark_state(marks[jj], gen);
+        if (st == 0 || st == ST_CAND) {
+          killed = (st == ST_CAND);
+          if (g.qinv[jj] >= 0) {
+            marks[jj] = (unsigned short)((gen << 2) | ST_EXP);
+            push = 1;
+          } else
+            marks[jj] = (unsigned short)((gen << 2) | ST_SEEN);
+        }
+      }
+      unsigned pm = __ballot_sync(0xffffffffu, push);
+      surviving -= __popc(__ballot_sync(0xffffffffu, killed));
+      if (push) q[tail + __popc(pm & ((1u << lane) - 1u))] = jj;
+      tail += __popc(pm);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void k_greedy_speculate(GreedyArgs g, int w0, int wn, unsigned gen) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= wn) return;
+  const int i = g.cand[w0 + t];
+  unsigned short *marks = g.marks + (size_t)t * g.m;
+  int *q = g.queue + (size_t)t * g.qcap;
+  int head = 0, tail = 0, surviving = 0;
+  const long long a = g.Ap[i], b = g.Ap[i + 1];
+  for (long long e0 = a; e0 < b; e0 += 32) {
+    long long e = e0 + lane;
+    int push = 0, isc = 0, j = 0;
+    if (e < b) {
+      j = g.Aj[e];
+      if (g.qinv[j] < 0) {
+        marks[j] = (unsigned short)((gen << 2) | ST_CAND);
+        isc = 1;
+      } else {
+        marks[j] = (unsigned short)((gen << 2) | ST_EXP);
+        push = 1;
+      }
+    }
+    unsigned pm = __ballot_sync(0xffffffffu, push);
+    surviving += __popc(__ballot_sync(0xffffffffu, isc));
+    if (push) q[tail + __popc(pm & ((1u << lane) - 1u))] = j;
+    tail += __popc(pm);
+  }
+  __syncwarp();
+  bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+  if (lane == 0) g.surv[t] = surviving, g.head[t] = head, g.tail[t] = tail;
+}
+
+// one warp walks the window in row order
+__global__ void k_greedy_commit(GreedyArgs g, int w0, int wn, unsigned gen) {
+  const int lane = threadIdx.x;
+  int nnew = 0;
+  for (int t = 0; t < wn; t++) {
+    int surviving = g.surv[t];
+    if (surviving == 0) continue;  // failed speculatively: more pivots only reach more
+    const int i = g.cand[w0 + t];
+    unsigned short *marks = g.marks + (size_t)t * g.m;
+    int *q = g.queue + (size_t)t * g.qcap;
+    int head = g.head[t], tail = g.tail[t];
+    // pivots committed earlier in this window that this row has touched
+    for (int b0 = 0; b0 < nnew && surviving > 0; b0 += 32) {
+      int jn = (b0 + lane < nnew) ? g.newcol[b0 + lane] : -1;
+      unsigned st = jn >= 0 ? mark_state(marks[jn], gen) : 0u;
+      unsigned hit = __ballot_sync(0xffffffffu, st == ST_CAND || st == ST_SEEN);
+      while (hit && surviving > 0) {
+        int src = __ffs(hit) - 1;
+        hit &= hit - 1;
+        int jc = __shfl_sync(0xffffffffu, jn, src);
+        unsigned s2 = mark_state(marks[jc], gen);  // may have been expanded by a continuation just before
+        if (s2 == ST_EXP) continue;
+        if (s2 == ST_CAND) surviving--;
+        __syncwarp();
+        if (lane == 0) {
+          marks[jc] = (unsigned short)((gen << 2) | ST_EXP);
+          q[tail] = jc;
+        }
+        tail++;
+        __syncwarp();
+        bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+      }
+    }
+    if (surviving <= 0) continue;
+    // first surviving candidate in storage order
+    const long long a = g.Ap[i], b = g.Ap[i + 1];
+    int jp = -1;
+    for (long long e0 = a; e0 < b && jp < 0; e0 += 32) {
+      long long e = e0 + lane;
+      int j = e < b ? g.Aj[e] : -1;
+      unsigned c = __ballot_sync(0xffffffffu, j >= 0 && mark_state(marks[j], gen) == ST_CAND);
+      if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
+    }
+    if (jp >= 0) {
+      if (lane == 0) {
+        g.pinv[i] = jp;
+        g.qinv[jp] = i;
+        g.newcol[nnew] = jp;
+        atomicAdd(g.npiv, 1);
+      }
+      nnew++;
+      __syncwarp();
+      __threadfence_block();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ reorder (heights) + extraction
+__global__ void k_height_relax(const long long *__restrict__ Ap, const int *__restrict__ Aj, int n,
+                               const int *__restrict__ pinv, const int *__restrict__ qinv, int *__restrict__ height,
+                               int *__restrict__ changed) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int jp = pinv[i];
+  if (jp < 0) return;
+  int h = 0;
+  for (long long e = Ap[i] + lane; e < Ap[i + 1]; e += 32) {
+    int j = Aj[e];
+    if (j == jp) continue;
+    int i2 = qinv[j];
+    if (i2 >= 0) h = max(h, ((volatile int *)height)[i2] + 1);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
+  if (lane == 0 && h > height[i]) {
+    height[i] = h;
+    *changed = 1;
+  }
+}
+__global__ void k_flag_rows(const int *__restrict__ pinv, int n, int want_pivotal, int *__restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = ((pinv[i] >= 0) == (want_pivotal != 0));
+  if (i == n) flag[i] = 0;
+}
+__global__ void k_compact_rows(const int *__restrict__ flag, const long long *__restrict__ pos, int n, int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[pos[i]] = i;
+}
+__global__ void k_sort_keys(const int *__restrict__ rows, int npiv, const int *__restrict__ height, int maxh, unsigned *__restrict__ keys) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < npiv) keys[k] = (unsigned)(maxh - height[rows[k]]);
+}
+__global__ void k_row_lens(const long long *__restrict__ Ap, const int *__restrict__ p, int npiv, int *__restrict__ len) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < npiv) len[k] = (int)(Ap[p[k] + 1] - Ap[p[k]]);
+  if (k == npiv) len[k] = 0;
+}
+template <bool SMALL>
+__global__ void k_extract(const long long *__restrict__ Ap, const int *__restrict__ Aj, const uint32_t *__restrict__ Ax,
+                          const int *__restrict__ p, const int *__restrict__ pinv, int npiv, const long long *__restrict__ pos,
+                          long long ubase, int urow0, long long *__restrict__ Up, int *__restrict__ Uj,
+                          uint32_t *__restrict__ Ux, int *__restrict__ Uqinv, uint32_t *__restrict__ pivval, Fp F) {
+  int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= npiv) return;
+  const int i = p[k], jp = pinv[i];
+  const long long a = Ap[i], b = Ap[i + 1], dst = ubase + pos[k];
+  // locate the pivot entry (first occurrence of column jp)
+  long long pe = -1;
+  for (long long e0 = a; e0 < b && pe < 0; e0 += 32) {
+    long long e = e0 + lane;
+    unsigned hit = __ballot_sync(0xffffffffu, e < b && Aj[e] == jp);
+    if (hit) pe = e0 + (__ffs(hit) - 1);
+  }
+  const uint32_t pv = Ax[pe];
+  const uint32_t alpha = dev_inv(pv, F.p);
+  if (lane == 0) {
+    Uj[dst] = jp;
+    Ux[dst] = 1;
+    Uqinv[jp] = urow0 + k;
+    Up[urow0 + k + 1] = dst + (b - a);
+    pivval[k] = pv;
+  }
+  for (long long e = a + lane; e < b; e += 32) {
+    if (e == pe) continue;
+    long long d = dst + 1 + (e - a) - (e > pe ? 1 : 0);
+    Uj[d] = Aj[e];
+    Ux[d] = mulmod<SMALL>(alpha, Ax[e], F);
+  }
+}
+
+int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int counts[3]) {
+  const int n = A.n, m = A.m;
+  cudaStream_t s = stream();
+  P.pinv.alloc(n);
+  P.qinv.alloc(m);
+  P.p.alloc(n);
+  P.pinv.fill_ff();
+  P.qinv.fill_ff();
+  counts[0] = counts[1] = counts[2] = 0;
+  if (n == 0 || m == 0 || A.nnz == 0) {
+    P.npiv = 0;
+    if (n) {
+      DBuf<int> flag(n + 1);
+      DBuf<long long> pos(n + 1);
+      k_flag_rows<<<cdiv(n + 1, 256), 256, 0, s>>>(P.pinv.p, n, 0, flag.p);
+      exclusive_scan_i32_to_i64(flag.p, pos.p, n + 1);
+      k_compact_rows<<<cdiv(n, 256), 256, 0, s>>>(flag.p, pos.p, n, P.p.p);
+    }
+    return 0;
+  }
+  DBuf<int> ctr(4);
+  ctr.zero();
+  const int rowblocks = cdiv((long long)n * 32, 256);
+  {  // FL
+    DBuf<unsigned long long> best(m);
+    best.fill_ff();
+    k_fl_scan<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, best.p);
+    k_fl_commit<<<cdiv(m, 256), 256, 0, s>>>(best.p, m, P.pinv.p, P.qinv.p, ctr.p);
+    CK(cudaGetLastError());
+    counts[0] = fetch(ctr.p);
+  }
+  {  // FL on columns
+    DBuf<unsigned char> open(m), state(n);
+    DBuf<unsigned long long> res(m);
+    CK(cudaMemsetAsync(open.p, 1, m, s));
+    state.zero();
+    res.fill_ff();
+    k_flc_close_pivot_rows<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, open.p);
+    ctr.zero();
+    for (unsigned round = 0;; round++) {
+      CK(cudaMemsetAsync(ctr.p + 1, 0, sizeof(int), s));
+      k_flc_reserve<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, P.qinv.p, open.p, state.p, res.p, round);
+      k_flc_commit<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, P.qinv.p, open.p, state.p, res.p, round, ctr.p);
+      CK(cudaGetLastError());
+      if (fetch(ctr.p + 1) == 0) break;
+    }
+    counts[1] = fetch(ctr.p);
+  }
+  if (greedy) {
+    DBuf<int> flag(n + 1), cand;
+    DBuf<long long> pos(n + 1);
+    k_flag_rows<<<cdiv(n + 1, 256), 256, 0, s>>>(P.pinv.p, n, 0, flag.p);
+    exclusive_scan_i32_to_i64(flag.p, pos.p, n + 1);
+    const int ncand = (int)fetch(pos.p + n);
+    if (ncand > 0) {
+      cand.alloc(ncand);
+      k_compact_rows<<<cdiv(n, 256), 256, 0, s>>>(flag.p, pos.p, n, cand.p);
+      const int qcap = std::min(n, m) + 1;
+      const size_t per = (size_t)m * 2 + (size_t)qcap * 4;
+      size_t budget = std::min<size_t>(dev_free_bytes() / 4, (size_t)12 << 30);
+      int W = (int)std::max<size_t>(32, std::min<size_t>(4096, budget / per));
+      W = std::min(W, ncand);
+      DBuf<unsigned short> marks((size_t)W * m);
+      DBuf<int> queue((size_t)W * qcap), surv(W), head(W), tail(W), newcol(W);
+      marks.zero();
+      ctr.zero();
+      GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, queue.p, qcap, surv.p, head.p, tail.p, newcol.p, ctr.p};
+      unsigned gen = 1;
+      for (int w0 = 0; w0 < ncand; w0 += W) {
+        int wn = std::min(W, ncand - w0);
+        k_greedy_speculate<<<cdiv((long long)wn * 32, 256), 256, 0, s>>>(g, w0, wn, gen);
+        k_greedy_commit<<<1, 32, 0, s>>>(g, w0, wn, gen);
+        gen++;
+        if (gen == (1u << 14)) {
+          marks.zero();
+          gen = 1;
+        }
+      }
+      CK(cudaGetLastError());
+      counts[2] = fetch(ctr.p);
+    }
+  }
+  const int npiv = counts[0] + counts[1] + counts[2];
+  P.npiv = npiv;
+  // ---- reorder: p[0:npiv] by (height desc, row asc), p[npiv:n] the other rows increasing
+  {
+    DBuf<int> flag(n + 1), prow(std::max(npiv, 1));
+    DBuf<long long> pos(n + 1);
+    k_flag_rows<<<cdiv(n + 1, 256), 256, 0, s>>>(P.pinv.p, n, 1, flag.p);
+    exclusive_scan_i32_to_i64(flag.p, pos.p, n + 1);
+    k_compact_rows<<<cdiv(n, 256), 256, 0, s>>>(flag.p, pos.p, n, prow.p);
+    k_flag_rows<<<cdiv(n + 1, 256), 256, 0, s>>>(P.pinv.p, n, 0, flag.p);
+    exclusive_scan_i32_to_i64(flag.p, pos.p, n + 1);
+    k_compact_rows<<<cdiv(n, 256), 256, 0, s>>>(flag.p, pos.p, n, P.p.p + npiv);
+    if (npiv > 0) {
+      DBuf<int> height(n);
+      height.zero();
+      int iters = 0;
+      for (;;) {
+        CK(cudaMemsetAsync(ctr.p + 2, 0, sizeof(int), s));
+        for (int rep = 0; rep < 4; rep++)
+          k_height_relax<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, P.qinv.p, height.p, ctr.p + 2);
+        iters += 4;
+        if (fetch(ctr.p + 2) == 0) break;
+        if (iters > n + 8) throw Error("structural pivots contain a cycle");
+      }
+      // max height
+      DBuf<int> mx(1);
+      size_t tmp = 0;
+      cub::DeviceReduce::Max(nullptr, tmp, height.p, mx.p, n, s);
+      DBuf<char> t1(tmp);
+      cub::DeviceReduce::Max(t1.p, tmp, height.p, mx.p, n, s);
+      const int maxh = fetch(mx.p);
+      DBuf<unsigned> keys(npiv), keys2(npiv);
+      k_sort_keys<<<cdiv(npiv, 256), 256, 0, s>>>(prow.p, npiv, height.p, maxh, keys.p);
+      int bits = 1;
+      while ((1LL << bits) <= maxh) bits++;
+      tmp = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys.p, keys2.p, prow.p, P.p.p, npiv, 0, bits, s);
+      DBuf<char> t2(tmp);
+      cub::DeviceRadixSort::SortPairs(t2.p, tmp, keys.p, keys2.p, prow.p, P.p.p, npiv, 0, bits, s);
+      P.max_height = maxh;
+    }
+    CK(cudaGetLastError());
+  }
+  return npiv;
+}
+
+// append the normalised pivot rows p[0:npiv] of A to U (pivot entry first, the rest scaled, in
+// storage order), set Uqinv, return the pivot values (for L)
+void extract_pivot_rows(const DCsr &A, const PivotSearch &P, DCsr &U, DBuf<int> &Uqinv, const Fp &F, DBuf<uint32_t> &pivval) {
+  const int npiv = P.npiv;
+  pivval.alloc(std::max(npiv, 1));
+  if (npiv == 0) return;
+  cudaStream_t s = stream();
+  DBuf<int> len(npiv + 1);
+  DBuf<long long> pos(npiv + 1);
+  k_row_lens<<<cdiv(npiv + 1, 256), 256, 0, s>>>(A.p.p, P.p.p, npiv, len.p);
+  exclusive_scan_i32_to_i64(len.p, pos.p, npiv + 1);
+  const long long add = fetch(pos.p + npiv);
+  csr_reserve(U, U.nnz + add, U.n + npiv);
+  if (F.small)
+    k_extract<true><<<cdiv((long long)npiv * 32, 256), 256, 0, s>>>(A.p.p, A.j.p, A.x.p, P.p.p, P.pinv.p, npiv, pos.p, U.nnz, U.n, U.p.p,
+                                                                  U.j.p, U.x.p, Uqinv.p, pivval.p, F);
+  else
+    k_extract<false><<<cdiv((long long)npiv * 32, 256), 256, 0, s>>>(A.p.p, A.j.p, A.x.p, P.p.p, P.pinv.p, npiv, pos.p, U.nnz, U.n, U.p.p,
+                                                                   U.j.p, U.x.p, Uqinv.p, pivval.p, F);
+  CK(cudaGetLastError());
+  U.nnz += add;
+  U.n += npiv;
+}
+
+}  // namespace sb

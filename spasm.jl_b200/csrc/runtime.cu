@@ -1,0 +1,197 @@
+// runtime.cu — device runtime: stream, stream-ordered memory, scans, CSR up/download, transpose.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace sb {
+
+static cudaStream_t g_stream = nullptr;
+static int g_sms = 0;
+static bool g_ready = false;
+
+void require_gpu() {
+  if (g_ready) return;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error("spasm_b200: no CUDA device — this library has no CPU fallback");
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) throw Error("spasm_b200: built for sm_100a (B200) only");
+  g_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thresh = UINT64_MAX;  // keep freed blocks cached in the pool
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  g_ready = true;
+}
+cudaStream_t stream() { return g_stream; }
+int sm_count() { return g_sms; }
+void sync() { CK(cudaStreamSynchronize(g_stream)); }
+
+void *dmalloc_bytes(size_t bytes) {
+  void *p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, bytes, g_stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error("spasm_b200: device allocation of " + std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e));
+  }
+  return p;
+}
+void dfree(void *p) { cudaFreeAsync(p, g_stream); }
+size_t dev_free_bytes() {
+  size_t f = 0, t = 0;
+  cudaMemGetInfo(&f, &t);
+  return f;
+}
+
+// ------------------------------------------------------------------ scans
+void exclusive_scan_i64(const long long *in, long long *out, size_t n) {
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, g_stream);
+  DBuf<char> t(tmp);
+  cub::DeviceScan::ExclusiveSum(t.p, tmp, in, out, n, g_stream);
+}
+struct I32ToI64 {
+  __device__ long long operator()(int v) const { return (long long)v; }
+};
+void exclusive_scan_i32_to_i64(const int *in, long long *out, size_t n_plus_one) {
+  cub::TransformInputIterator<long long, I32ToI64, const int *> it(in, I32ToI64());
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, out, n_plus_one, g_stream);
+  DBuf<char> t(tmp);
+  cub::DeviceScan::ExclusiveSum(t.p, tmp, it, out, n_plus_one, g_stream);
+}
+long long reduce_sum_i32(const int *in, size_t n) {
+  cub::TransformInputIterator<long long, I32ToI64, const int *> it(in, I32ToI64());
+  DBuf<long long> out(1);
+  size_t tmp = 0;
+  cub::DeviceReduce::Sum(nullptr, tmp, it, out.p, n, g_stream);
+  DBuf<char> t(tmp);
+  cub::DeviceReduce::Sum(t.p, tmp, it, out.p, n, g_stream);
+  return fetch(out.p);
+}
+
+// ------------------------------------------------------------------ CSR transfer
+__global__ void k_to_u(const int *__restrict__ in, uint32_t *__restrict__ out, long long n, Fp F) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = to_u(in[i], F);
+}
+__global__ void k_to_bal(const uint32_t *__restrict__ in, int *__restrict__ out, long long n, Fp F) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = to_bal(in[i], F);
+}
+
+void convert_to_balanced(const uint32_t *in, int *out, long long n, const Fp &F) {
+  if (n) k_to_bal<<<cdiv(n, 256), 256, 0, g_stream>>>(in, out, n, F);
+  CK(cudaGetLastError());
+}
+void convert_to_residues(const int *in, uint32_t *out, long long n, const Fp &F) {
+  if (n) k_to_u<<<cdiv(n, 256), 256, 0, g_stream>>>(in, out, n, F);
+  CK(cudaGetLastError());
+}
+
+void upload_csr(const spasm_csr *A, DCsr &D, const Fp &F) {
+  D.n = A->n, D.m = A->m, D.nnz = A->p[A->n];
+  D.p.alloc(A->n + 1);
+  D.j.alloc(D.nnz);
+  D.x.alloc(D.nnz);
+  D.p.upload((const long long *)A->p, A->n + 1);
+  if (D.nnz) {
+    D.j.upload(A->j, D.nnz);
+    DBuf<int> tmp(D.nnz);
+    tmp.upload(A->x, D.nnz);
+    k_to_u<<<cdiv(D.nnz, 256), 256, 0, g_stream>>>(tmp.p, D.x.p, D.nnz, F);
+    CK(cudaGetLastError());
+  }
+}
+
+spasm_csr *download_csr(const DCsr &D, int64_t prime, const Fp &F) {
+  spasm_csr *A = spasm_csr_alloc(D.n, D.m, D.nnz, prime, true);
+  D.p.download((long long *)A->p, D.n + 1);
+  if (D.nnz) {
+    D.j.download(A->j, D.nnz);
+    DBuf<int> tmp(D.nnz);
+    k_to_bal<<<cdiv(D.nnz, 256), 256, 0, g_stream>>>(D.x.p, tmp.p, D.nnz, F);
+    CK(cudaGetLastError());
+    tmp.download(A->x, D.nnz);
+  }
+  sync();
+  return A;
+}
+
+// ------------------------------------------------------------------ transpose
+// T = A^T with every row of T sorted by original row index (the order a stable counting sort
+// produces — same as the oracle's, src/SpaSM.jl:589).  Stable LSD radix sort of the nnz entries by
+// column: keys = column (log2 m bits), payload = entry index; rows are recovered from a row-id
+// expansion.  16 B/nnz algorithmic traffic (read j,x; write row,x) + 8(n+m+2).
+__global__ void k_expand_rows(const long long *__restrict__ p, int n, int *__restrict__ rowid) {
+  // one warp per row
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  long long a = p[w], b = p[w + 1];
+  for (long long e = a + lane; e < b; e += 32) rowid[e] = w;
+}
+__global__ void k_count_cols(const int *__restrict__ j, long long nnz, int *__restrict__ cnt) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < nnz) atomicAdd(&cnt[j[i]], 1);
+}
+__global__ void k_gather_t(const long long *__restrict__ perm, const int *__restrict__ rowid,
+                           const uint32_t *__restrict__ x, long long nnz, int *__restrict__ Tj,
+                           uint32_t *__restrict__ Tx) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < nnz) {
+    long long e = perm[i];
+    Tj[i] = rowid[e];
+    Tx[i] = x[e];
+  }
+}
+__global__ void k_iota(long long *a, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
+void transpose_csr(const DCsr &A, DCsr &T) {
+  T.n = A.m, T.m = A.n, T.nnz = A.nnz;
+  T.p.alloc(A.m + 1);
+  T.j.alloc(A.nnz);
+  T.x.alloc(A.nnz);
+  DBuf<int> cnt(A.m + 1);
+  cnt.zero();
+  if (A.nnz) k_count_cols<<<cdiv(A.nnz, 256), 256, 0, g_stream>>>(A.j.p, A.nnz, cnt.p);
+  exclusive_scan_i32_to_i64(cnt.p, T.p.p, A.m + 1);
+  if (A.nnz == 0) return;
+  DBuf<int> rowid(A.nnz), keys_out(A.nnz);
+  DBuf<long long> idx(A.nnz), perm(A.nnz);
+  k_expand_rows<<<cdiv((long long)A.n * 32, 256), 256, 0, g_stream>>>(A.p.p, A.n, rowid.p);
+  k_iota<<<cdiv(A.nnz, 256), 256, 0, g_stream>>>(idx.p, A.nnz);
+  int bits = 1;
+  while ((1LL << bits) < A.m) bits++;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, A.j.p, keys_out.p, idx.p, perm.p, A.nnz, 0, bits, g_stream);
+  DBuf<char> t(tmp);
+  cub::DeviceRadixSort::SortPairs(t.p, tmp, A.j.p, keys_out.p, idx.p, perm.p, A.nnz, 0, bits, g_stream);
+  k_gather_t<<<cdiv(A.nnz, 256), 256, 0, g_stream>>>(perm.p, rowid.p, A.x.p, A.nnz, T.j.p, T.x.p);
+  CK(cudaGetLastError());
+}
+
+}  // namespace sb
+
+// src/SpaSM.jl:589 — ONE argument; values always kept (test/runtests.jl:12-15)
+extern "C" struct spasm_csr *spasm_transpose(const struct spasm_csr *A) {
+  try {
+    sb::require_gpu();
+    sb::Fp F = sb::make_field(A->field->p);
+    sb::DCsr dA, dT;
+    if (A->x == nullptr) throw sb::Error("spasm_transpose: pattern-only matrices are not supported");
+    sb::upload_csr(A, dA, F);
+    sb::transpose_csr(dA, dT);
+    return sb::download_csr(dT, A->field->p, F);
+  } catch (const std::exception &e) {
+    sb::logf("[spasm_b200] spasm_transpose failed: %s\n", e.what());
+    return nullptr;
+  }
+}

@@ -1,0 +1,819 @@
+// solve_sparse.cu — the sparse row-solve engine: x.G = B[k] for many rows k at once.
+//
+// Replaces spasm_sparse_triangular_solve + spasm_reach/spasm_dfs/spasm_scatter and the OpenMP row
+// loops of spasm_schur / spasm_kernel / spasm_rref (reference bindings src/SpaSM.jl:619-629,
+// :694-722, :761-762, :871, :876-882; algorithm SURVEY.md A.3/A.6).
+//
+// B200 design.  One warp per row (light tier) or one CTA per row (medium tier).  The row under
+// elimination lives in a SHARED-MEMORY open-addressing hash accumulator keyed by column; pivot
+// rows of G stream through L2 with coalesced 32-lane loads of (j,x).  Instead of the reference's
+// DFS (inherently sequential) the elimination order is "pending pivotal columns by increasing
+// prio": every row of G only references pivots of larger prio (U rows are appended in
+// topological order), so popping the minimum is a valid topological order, and since arithmetic
+// in F_p is exact every valid order gives bit-identical values.  Multipliers that are zero are
+// skipped (their sub-tree contributes nothing).  Output entries are emitted in increasing column
+// order (normalisation N1) after an in-place compaction + bitonic sort of the accumulator.
+// Reduction mod p: 32-bit Barrett for p < 2^16 (products < 2^32), 64-bit Barrett otherwise.
+//
+// Rows whose accumulator overflows the tier are re-run in the next tier (status 1); rows that do
+// not fit the output slab are re-run with an exactly sized slab (status 2).  The heavy tier keeps
+// the accumulator as a direct-indexed array in global memory with a bitmap priority queue.
+#include "solve_sparse.cuh"
+
+namespace sb {
+
+static constexpr int EMPTY = -1;
+static constexpr int ST_OK = 0, ST_TABLE = 1, ST_SLAB = 2;
+
+struct KArgs {
+  SolveSystem G;
+  SolveRows B;
+  const int *todo;  // [ntodo] indices k into B.rows
+  int ntodo;
+  int *work_counter;
+  // emit
+  int count_only, all_columns, structural, want_L;
+  const int *prefix_col;
+  uint32_t prefix_val;
+  int *cnt;             // [nrows]
+  unsigned long long *off;  // [nrows]  (slab id << 56 | offset)
+  int *oj;
+  uint32_t *ox;
+  unsigned long long cap, slab_id;
+  unsigned long long *cursor;
+  int *lcnt;
+  unsigned long long *loff;
+  int *lj;
+  uint32_t *lx;
+  unsigned long long lcap;
+  unsigned long long *lcursor;
+  int *status;  // [nrows]
+  unsigned long long *stats;  // [0] bytes, [1] macs, [2] #table overflow, [3] #slab overflow, [4] slab need, [5] L slab need
+  Fp F;
+  // heavy tier
+  int *gkeys;            // [groups][width]
+  uint32_t *gvals;       // [groups][width]
+  unsigned *gbitmap;     // [groups][nprio/32+1]
+  int nprio;
+};
+
+template <int T>
+struct Grp {
+  __device__ static __forceinline__ void sync() {
+    if (T == 32)
+      __syncwarp();
+    else
+      __syncthreads();
+  }
+  __device__ static __forceinline__ int tid() { return T == 32 ? (threadIdx.x & 31) : threadIdx.x; }
+  // minimum of a u64 over the group; scratch: T/32 u64 (unused for warps)
+  __device__ static __forceinline__ unsigned long long min64(unsigned long long v, unsigned long long *scratch) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+      v = w < v ? w : v;
+    }
+    if (T == 32) return v;
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) scratch[w] = v;
+    __syncthreads();
+    unsigned long long r = scratch[0];
+#pragma unroll
+    for (int i = 1; i < T / 32; i++) r = scratch[i] < r ? scratch[i] : r;
+    __syncthreads();
+    return r;
+  }
+  // exclusive rank of `pred` among the group + total; scratch: T/32 ints
+  __device__ static __forceinline__ int rank(bool pred, int &total, int *scratch) {
+    unsigned b = __ballot_sync(0xffffffffu, pred);
+    int l = threadIdx.x & 31;
+    int pre = __popc(b & ((1u << l) - 1u)), wt = __popc(b);
+    if (T == 32) {
+      total = wt;
+      return pre;
+    }
+    int w = threadIdx.x >> 5;
+    if (l == 0) scratch[w] = wt;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < T / 32; i++) {
+      int v = scratch[i];
+      if (i < w) base += v;
+      tot += v;
+    }
+    __syncthreads();
+    total = tot;
+    return base + pre;
+  }
+  __device__ static __forceinline__ int bcast(int v, int *scratch) {
+    if (T == 32) return __shfl_sync(0xffffffffu, v, 0);
+    if (threadIdx.x == 0) scratch[0] = v;
+    __syncthreads();
+    int r = scratch[0];
+    __syncthreads();
+    return r;
+  }
+};
+
+__device__ __forceinline__ unsigned hash_col(int c) { return (unsigned)c * 0x9E3779B1u; }
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory tiers.  T threads per row, H table slots, PCAP pending entries.
+template <int T, int H, int PCAP, bool SMALL>
+__global__ void __launch_bounds__(T == 32 ? 256 : T) k_solve_smem(KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int GROUPS = (T == 32) ? 8 : 1;  // row groups per block
+  constexpr int LOGH = (H == 512) ? 9 : (H == 1024) ? 10 : (H == 2048) ? 11 : (H == 4096) ? 12 : (H == 8192) ? 13 : 14;
+  static_assert((1 << LOGH) == H, "H must be a supported power of two");
+  const int g = (T == 32) ? (threadIdx.x >> 5) : 0;
+  const int tid = Grp<T>::tid();
+  // layout per group: keys[H] vals[H] pprio[PCAP] pcol[PCAP] pslot[PCAP]
+  constexpr size_t PER = (size_t)(2 * H + 3 * PCAP) * 4;
+  unsigned char *base = smem_raw + (size_t)g * PER;
+  int *keys = (int *)base;
+  uint32_t *vals = (uint32_t *)(keys + H);
+  int *pprio = (int *)(vals + H);
+  int *pcol = pprio + PCAP;
+  int *pslot = pcol + PCAP;
+  unsigned long long *red64 = (unsigned long long *)(smem_raw + (size_t)GROUPS * PER);
+  int *redi = (int *)(red64 + 32);
+  const Fp F = a.F;
+  const PDesc *__restrict__ pdesc = a.G.pdesc;
+  const int *__restrict__ Gj = a.G.Gj;
+  const uint32_t *__restrict__ Gx = a.G.Gx;
+  constexpr int LIMIT = H - H / 8 - T;  // keep the load factor below 7/8
+
+  for (;;) {
+    int t = 0;
+    if (tid == 0) t = atomicAdd(a.work_counter, 1);
+    t = Grp<T>::bcast(t, redi);
+    if (t >= a.ntodo) break;
+    const int k = a.todo ? a.todo[t] : t;
+    const int brow = a.B.rows ? a.B.rows[k] : k;
+    const int maskc = a.B.mask ? a.B.mask[k] : -1;
+    for (int s = tid; s < H; s += T) keys[s] = EMPTY;
+    Grp<T>::sync();
+    int fill = 0, np = 0;
+    bool overflow = false;
+    unsigned long long bytes = 0, macs = 0;
+
+    // one batch of <= T entries (cj, delta) is merged into the accumulator
+    auto merge = [&](bool valid, int cj, uint32_t delta) {
+      int slot = -1;
+      bool isnew = false;
+      if (valid) {
+        unsigned h = hash_col(cj) >> (32 - LOGH);
+        for (;;) {
+          int kk = ((volatile int *)keys)[h];
+          if (kk == cj) {
+            vals[h] = addmod(vals[h], delta, F);
+            break;
+          }
+          if (kk == EMPTY) {
+            int old = atomicCAS(&keys[h], EMPTY, cj);
+            if (old == EMPTY) {
+              vals[h] = delta;
+              isnew = true;
+              break;
+            }
+            if (old == cj) {
+              vals[h] = addmod(vals[h], delta, F);
+              break;
+            }
+          }
+          h = (h + 1) & (H - 1);
+        }
+        slot = (int)h;
+      }
+      int prio = -1;
+      bool push = false;
+      if (isnew && cj != maskc) {
+        PDesc d = pdesc[cj];
+        if (d.len >= 0) push = true, prio = d.prio;
+      }
+      int totnew, totpush;
+      Grp<T>::rank(isnew, totnew, redi);
+      int pos = Grp<T>::rank(push, totpush, redi);
+      if (np + totpush > PCAP) {
+        overflow = true;
+      } else if (push) {
+        pprio[np + pos] = prio;
+        pcol[np + pos] = cj;
+        pslot[np + pos] = slot;
+      }
+      np += totpush;
+      fill += totnew;
+      Grp<T>::sync();
+    };
+
+    // ---- load B[k]
+    {
+      const long long b0 = a.B.Bp[brow], b1 = a.B.Bp[brow + 1];
+      bytes += 8 * (b1 - b0) + 8;
+      for (long long e0 = b0; e0 < b1 && !overflow; e0 += T) {
+        if (fill > LIMIT) {
+          overflow = true;
+          break;
+        }
+        long long e = e0 + tid;
+        bool valid = e < b1;
+        int cj = valid ? a.B.Bj[e] : 0;
+        uint32_t v = valid ? a.B.Bx[e] : 0;
+        merge(valid, cj, v);
+      }
+    }
+    // ---- eliminate pending pivots by increasing prio
+    while (np > 0 && !overflow) {
+      unsigned long long best = ~0ULL;
+      for (int i = tid; i < np; i += T) {
+        unsigned long long key = ((unsigned long long)(unsigned)pprio[i] << 32) | (unsigned)i;
+        best = key < best ? key : best;
+      }
+      best = Grp<T>::min64(best, red64);
+      const int idx = (int)(best & 0xffffffffu);
+      const int c = pcol[idx];
+      const uint32_t mult = vals[pslot[idx]];
+      Grp<T>::sync();
+      if (tid == 0) {
+        pprio[idx] = pprio[np - 1];
+        pcol[idx] = pcol[np - 1];
+        pslot[idx] = pslot[np - 1];
+      }
+      np--;
+      Grp<T>::sync();
+      if (mult == 0 && !a.structural) continue;
+      const PDesc d = pdesc[c];
+      const uint32_t coef = negmod(mult, F);
+      bytes += 8 * (long long)d.len + 8;
+      macs += d.len;
+      for (int e0 = 0; e0 < d.len; e0 += T) {
+        if (fill > LIMIT) {
+          overflow = true;
+          break;
+        }
+        int e = e0 + tid;
+        bool valid = e < d.len;
+        int cj = 0;
+        uint32_t delta = 0;
+        if (valid) {
+          cj = Gj[d.start + e];
+          if (cj == c)
+            valid = false;  // the unit pivot entry: x[c] keeps the multiplier
+          else
+            delta = mulmod<SMALL>(coef, Gx[d.start + e], F);
+        }
+        merge(valid, cj, delta);
+      }
+    }
+    if (overflow) {
+      if (tid == 0) {
+        a.status[k] = ST_TABLE;
+        atomicAdd(&a.stats[2], 1ULL);
+      }
+      Grp<T>::sync();
+      continue;
+    }
+
+    // ---- emit.  (1) multipliers -> pend arrays (free now), (2) in-place compaction, (3) sort
+    int nl = 0;
+    if (a.want_L) {
+      for (int s0 = 0; s0 < H && !overflow; s0 += T) {
+        int s = s0 + tid;
+        int kk = keys[s];
+        uint32_t v = vals[s];
+        bool pass = false;
+        int prio = 0;
+        if (kk != EMPTY && v != 0 && kk != maskc) {
+          PDesc d = pdesc[kk];
+          if (d.len >= 0) pass = true, prio = d.prio;
+        }
+        int tot;
+        int pos = Grp<T>::rank(pass, tot, redi);
+        if (nl + tot > PCAP)
+          overflow = true;
+        else if (pass) {
+          pprio[nl + pos] = prio;
+          pcol[nl + pos] = (int)v;
+        }
+        nl += tot;
+      }
+      Grp<T>::sync();
+      if (overflow) {
+        if (tid == 0) {
+          a.status[k] = ST_TABLE;
+          atomicAdd(&a.stats[2], 1ULL);
+        }
+        Grp<T>::sync();
+        continue;
+      }
+    }
+    int nout = 0;
+    for (int s0 = 0; s0 < H; s0 += T) {
+      int s = s0 + tid;
+      int kk = keys[s];
+      uint32_t v = vals[s];
+      bool pass = kk != EMPTY && (v != 0 || a.structural);
+      if (pass && !a.all_columns && !a.structural) pass = (kk == maskc) ? false : (pdesc[kk].len < 0);
+      if (pass && a.B.mask && kk == maskc) pass = false;  // own pivot of an rref row goes to the prefix
+      int tot;
+      int pos = Grp<T>::rank(pass, tot, redi);
+      Grp<T>::sync();  // all reads of this batch precede the writes below
+      if (pass) {
+        keys[nout + pos] = kk;
+        vals[nout + pos] = v;
+      }
+      nout += tot;
+      Grp<T>::sync();
+    }
+    const int npre = a.prefix_col ? 1 : 0;
+    if (tid == 0) {
+      a.cnt[k] = nout + npre;
+      if (a.want_L) a.lcnt[k] = nl;
+      atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
+      atomicAdd(&a.stats[1], macs);
+    }
+    if (a.count_only) {
+      if (tid == 0) a.status[k] = ST_OK;
+      Grp<T>::sync();
+      continue;
+    }
+    // bitonic sort of (keys, vals)[0:nout) by key, and of (pprio, pcol)[0:nl) by prio
+    auto bitonic = [&](int *kk, uint32_t *vv, int n) {
+      int N = 1;
+      while (N < n) N <<= 1;
+      for (int i = n + tid; i < N; i += T) kk[i] = 0x7fffffff;
+      Grp<T>::sync();
+      for (int size = 2; size <= N; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = tid; i < (N >> 1); i += T) {
+            int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+            int hi = lo | stride;
+            bool up = ((lo & size) == 0);
+            int ka = kk[lo], kb = kk[hi];
+            if ((ka > kb) == up) {
+              kk[lo] = kb, kk[hi] = ka;
+              uint32_t tv = vv[lo];
+              vv[lo] = vv[hi], vv[hi] = tv;
+            }
+          }
+          Grp<T>::sync();
+        }
+    };
+    if (nout > 1) bitonic(keys, vals, nout);
+    if (nl > 1) bitonic(pprio, (uint32_t *)pcol, nl);
+    // slab allocation
+    unsigned long long o = 0, lo_ = 0;
+    int st = ST_OK;
+    if (tid == 0) {
+      o = atomicAdd(a.cursor, (unsigned long long)(nout + npre));
+      if (o + nout + npre > a.cap) st = ST_SLAB;
+      if (a.want_L) {
+        lo_ = atomicAdd(a.lcursor, (unsigned long long)nl);
+        if (lo_ + nl > a.lcap) st = ST_SLAB;
+      }
+      if (st == ST_SLAB) {
+        atomicAdd(&a.stats[3], 1ULL);
+        atomicAdd(&a.stats[4], (unsigned long long)(nout + npre));
+        atomicAdd(&a.stats[5], (unsigned long long)nl);
+      }
+      a.status[k] = st;
+      a.off[k] = (a.slab_id << 56) | o;
+      if (a.want_L) a.loff[k] = (a.slab_id << 56) | lo_;
+    }
+    if (T == 32) {
+      st = __shfl_sync(0xffffffffu, st, 0);
+      o = __shfl_sync(0xffffffffu, o, 0);
+      lo_ = __shfl_sync(0xffffffffu, lo_, 0);
+    } else {
+      __shared__ unsigned long long bc[3];
+      if (tid == 0) bc[0] = (unsigned long long)st, bc[1] = o, bc[2] = lo_;
+      __syncthreads();
+      st = (int)bc[0], o = bc[1], lo_ = bc[2];
+      __syncthreads();
+    }
+    if (st == ST_OK) {
+      if (npre && tid == 0) {
+        a.oj[o] = a.prefix_col[k];
+        a.ox[o] = a.prefix_val;
+      }
+      for (int i = tid; i < nout; i += T) {
+        a.oj[o + npre + i] = keys[i];
+        a.ox[o + npre + i] = vals[i];
+      }
+      for (int i = tid; i < nl; i += T) {
+        a.lj[lo_ + i] = pprio[i];
+        a.lx[lo_ + i] = (uint32_t)pcol[i];
+      }
+    }
+    Grp<T>::sync();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// heavy tier: CTA per row, direct-indexed accumulator in global memory (slot = column), pending
+// pivots in a bitmap over prio.  Output comes out column-sorted by scanning the slots in order.
+template <int T, bool SMALL>
+__global__ void __launch_bounds__(T) k_solve_heavy(KArgs a, const int *__restrict__ prio2col) {
+  __shared__ unsigned long long red64[32];
+  __shared__ int redi[40];
+  const int tid = threadIdx.x;
+  const Fp F = a.F;
+  const int W = a.G.width;
+  const int nwords = (a.nprio + 31) / 32 + 1;
+  int *keys = a.gkeys + (size_t)blockIdx.x * W;          // keys[c] == c when present else EMPTY (kept EMPTY between rows)
+  uint32_t *vals = a.gvals + (size_t)blockIdx.x * W;
+  unsigned *bitmap = a.gbitmap + (size_t)blockIdx.x * nwords;  // kept all-zero between rows
+  const PDesc *__restrict__ pdesc = a.G.pdesc;
+
+  for (;;) {
+    int t = 0;
+    if (tid == 0) t = atomicAdd(a.work_counter, 1);
+    t = Grp<T>::bcast(t, redi);
+    if (t >= a.ntodo) break;
+    const int k = a.todo ? a.todo[t] : t;
+    const int brow = a.B.rows ? a.B.rows[k] : k;
+    const int maskc = a.B.mask ? a.B.mask[k] : -1;
+    unsigned long long bytes = 0, macs = 0;
+
+    auto merge = [&](bool valid, int cj, uint32_t delta) {
+      if (!valid) return;
+      if (keys[cj] == cj) {
+        vals[cj] = addmod(vals[cj], delta, F);
+      } else {
+        keys[cj] = cj;
+        vals[cj] = delta;
+        if (cj != maskc) {
+          PDesc d = pdesc[cj];
+          if (d.len >= 0) atomicOr(&bitmap[d.prio >> 5], 1u << (d.prio & 31));
+        }
+      }
+    };
+    const long long b0 = a.B.Bp[brow], b1 = a.B.Bp[brow + 1];
+    bytes += 8 * (b1 - b0) + 8;
+    for (long long e = b0 + tid; e < b1; e += T) merge(true, a.B.Bj[e], a.B.Bx[e]);
+    __syncthreads();
+    int cursor = 0;  // word index
+    for (;;) {
+      // find the first set bit at or after word `cursor`
+      unsigned long long best = ~0ULL;
+      for (int w0 = cursor; w0 < nwords; w0 += T) {
+        int w = w0 + tid;
+        unsigned bits = (w < nwords) ? bitmap[w] : 0u;
+        if (bits) best = (unsigned long long)w * 32 + (__ffs(bits) - 1);
+        best = Grp<T>::min64(best, red64);
+        if (best != ~0ULL) break;
+      }
+      if (best == ~0ULL) break;
+      const int prio = (int)best;
+      cursor = prio >> 5;
+      const int c = prio2col[prio];
+      if (tid == 0) bitmap[prio >> 5] &= ~(1u << (prio & 31));
+      const uint32_t mult = vals[c];
+      __syncthreads();
+      if (mult == 0 && !a.structural) continue;
+      const PDesc d = pdesc[c];
+      const uint32_t coef = negmod(mult, F);
+      bytes += 8 * (long long)d.len + 8;
+      macs += d.len;
+      for (int e = tid; e < d.len; e += T) {
+        int cj = a.G.Gj[d.start + e];
+        if (cj != c) merge(true, cj, mulmod<SMALL>(coef, a.G.Gx[d.start + e], F));
+      }
+      __syncthreads();
+    }
+    // pass 1: count
+    int nout = 0, nl = 0;
+    for (int s0 = 0; s0 < W; s0 += T) {
+      int s = s0 + tid;
+      bool present = s < W && keys[s] == s;
+      uint32_t v = present ? vals[s] : 0;
+      bool piv = present && s != maskc && pdesc[s].len >= 0;
+      bool pass = present && (v != 0 || a.structural) && (a.all_columns || a.structural || !piv) && s != maskc;
+      bool lpass = a.want_L && present && v != 0 && piv;
+      int tot;
+      Grp<T>::rank(pass, tot, redi);
+      nout += tot;
+      if (a.want_L) {
+        Grp<T>::rank(lpass, tot, redi);
+        nl += tot;
+      }
+    }
+    const int npre = a.prefix_col ? 1 : 0;
+    unsigned long long o = 0, lo_ = 0;
+    int st = ST_OK;
+    if (tid == 0) {
+      a.cnt[k] = nout + npre;
+      if (a.want_L) a.lcnt[k] = nl;
+      atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
+      atomicAdd(&a.stats[1], macs);
+      if (!a.count_only) {
+        o = atomicAdd(a.cursor, (unsigned long long)(nout + npre));
+        if (o + nout + npre > a.cap) st = ST_SLAB;
+        if (a.want_L) {
+          lo_ = atomicAdd(a.lcursor, (unsigned long long)nl);
+          if (lo_ + nl > a.lcap) st = ST_SLAB;
+        }
+        if (st == ST_SLAB) {
+          atomicAdd(&a.stats[3], 1ULL);
+          atomicAdd(&a.stats[4], (unsigned long long)(nout + npre));
+          atomicAdd(&a.stats[5], (unsigned long long)nl);
+        }
+        a.off[k] = (a.slab_id << 56) | o;
+        if (a.want_L) a.loff[k] = (a.slab_id << 56) | lo_;
+      }
+      a.status[k] = st;
+    }
+    {
+      __shared__ unsigned long long bc[3];
+      if (tid == 0) bc[0] = (unsigned long long)st, bc[1] = o, bc[2] = lo_;
+      __syncthreads();
+      st = (int)bc[0], o = bc[1], lo_ = bc[2];
+      __syncthreads();
+    }
+    const bool write = !a.count_only && st == ST_OK;
+    if (write && npre && tid == 0) {
+      a.oj[o] = a.prefix_col[k];
+      a.ox[o] = a.prefix_val;
+    }
+    // pass 2: write (column order) + reset the accumulator.  The L stream must be by increasing
+    // prio: it is written through the prio2col map in a third pass below.
+    int w_ = 0;
+    for (int s0 = 0; s0 < W; s0 += T) {
+      int s = s0 + tid;
+      bool present = s < W && keys[s] == s;
+      uint32_t v = present ? vals[s] : 0;
+      bool piv = present && s != maskc && pdesc[s].len >= 0;
+      bool pass = present && (v != 0 || a.structural) && (a.all_columns || a.structural || !piv) && s != maskc;
+      int tot;
+      int pos = Grp<T>::rank(pass, tot, redi);
+      if (write && pass) {
+        a.oj[o + npre + w_ + pos] = s;
+        a.ox[o + npre + w_ + pos] = v;
+      }
+      w_ += tot;
+      if (present && !(a.want_L && piv)) keys[s] = EMPTY;
+    }
+    if (a.want_L) {
+      __syncthreads();
+      int lw = 0;
+      for (int q0 = 0; q0 < a.nprio; q0 += T) {
+        int q = q0 + tid;
+        int c = q < a.nprio ? prio2col[q] : -1;
+        bool present = c >= 0 && keys[c] == c;
+        uint32_t v = present ? vals[c] : 0;
+        bool lpass = present && v != 0 && c != maskc;
+        int tot;
+        int pos = Grp<T>::rank(lpass, tot, redi);
+        if (write && lpass) {
+          a.lj[lo_ + lw + pos] = q;
+          a.lx[lo_ + lw + pos] = v;
+        }
+        lw += tot;
+        if (present) keys[c] = EMPTY;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_collect_status(const int *__restrict__ status, const int *__restrict__ todo, int ntodo, int want,
+                                 int *__restrict__ out, int *__restrict__ nout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntodo) return;
+  int k = todo ? todo[i] : i;
+  if (status[k] == want) out[atomicAdd(nout, 1)] = k;
+}
+__global__ void k_fill(int *a, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+struct SlabPtrs {
+  const int *j[16];
+  const uint32_t *x[16];
+};
+__global__ void k_gather_rows(const int *__restrict__ cnt, const unsigned long long *__restrict__ off,
+                              const long long *__restrict__ p, int nrows, SlabPtrs S, int *__restrict__ oj,
+                              uint32_t *__restrict__ ox) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nrows) return;
+  int c = cnt[w];
+  unsigned long long o = off[w];
+  int sid = (int)(o >> 56);
+  o &= (1ULL << 56) - 1;
+  const int *sj = S.j[sid];
+  const uint32_t *sx = S.x[sid];
+  long long d = p[w];
+  for (int i = lane; i < c; i += 32) {
+    oj[d + i] = sj[o + i];
+    ox[d + i] = sx[o + i];
+  }
+}
+__global__ void k_prio2col(const PDesc *__restrict__ pdesc, int width, int *__restrict__ prio2col) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < width && pdesc[c].len >= 0) prio2col[pdesc[c].prio] = c;
+}
+__global__ void k_sort_check(const int *todo, int n) {}
+
+// order-preserving compaction of a todo list is not needed: rows are written by k.
+
+void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, const Fp &F, SolveResult &R) {
+  const int nrows = B.nrows;
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, stream()));
+  R.cnt.alloc(nrows + 1);
+  R.cnt.zero();
+  R.p.alloc(nrows + 1);
+  if (E.want_L) {
+    R.lcnt.alloc(nrows + 1);
+    R.lcnt.zero();
+    R.lp.alloc(nrows + 1);
+  }
+  R.nnz = R.lnnz = 0;
+  R.stats = WorkStats();
+  R.stats.rows = nrows;
+  if (nrows == 0) {
+    R.p.zero();
+    if (E.want_L) R.lp.zero();
+    R.j.alloc(0), R.x.alloc(0);
+    return;
+  }
+  DBuf<int> status(nrows);
+  DBuf<unsigned long long> off(nrows), loff(E.want_L ? nrows : 1);
+  DBuf<unsigned long long> ctrs(8);  // [0..5] stats, [6] cursor, [7] lcursor
+  DBuf<int> counter(2);
+  ctrs.zero();
+  std::vector<DBuf<int>> slabs_j, slabs_lj;
+  std::vector<DBuf<uint32_t>> slabs_x, slabs_lx;
+  SlabPtrs SP{}, LSP{};
+
+  KArgs a{};
+  a.G = G, a.B = B;
+  a.count_only = E.count_only, a.all_columns = E.all_columns, a.structural = E.structural, a.want_L = E.want_L;
+  a.prefix_col = E.prefix_col, a.prefix_val = E.prefix_val;
+  a.cnt = R.cnt.p, a.off = off.p, a.lcnt = R.lcnt.p, a.loff = loff.p;
+  a.status = status.p, a.stats = ctrs.p, a.cursor = ctrs.p + 6, a.lcursor = ctrs.p + 7;
+  a.F = F;
+  a.work_counter = counter.p;
+
+  DBuf<int> todoA, todoB, ntodo_d(1), prio2col;
+  const int *todo = nullptr;
+  int ntodo = nrows;
+  long long guess = 0;
+  {
+    // initial slab guess: 4x the source rows + 1 per row, refined exactly on overflow
+    long long src = 0;
+    if (B.rows == nullptr)
+      src = 0;  // unknown without a fetch; use a flat guess
+    guess = 64LL * nrows + 4096;
+  }
+  DBuf<int> gkeys;
+  DBuf<uint32_t> gvals;
+  DBuf<unsigned> gbitmap;
+  int nprio = 0;
+
+  for (int tier = 0; tier < 3 && ntodo > 0; tier++) {
+    long long need = guess, lneed = guess;
+    for (int attempt = 0; attempt < 4 && ntodo > 0; attempt++) {
+      // fresh slab for this launch
+      unsigned long long h_ctrs[8];
+      if (!E.count_only) {
+        if (slabs_j.size() >= 16) throw Error("solve_rows: too many slabs");
+        slabs_j.emplace_back((size_t)need);
+        slabs_x.emplace_back((size_t)need);
+        a.oj = slabs_j.back().p, a.ox = slabs_x.back().p, a.cap = need;
+        a.slab_id = slabs_j.size() - 1;
+        SP.j[a.slab_id] = a.oj, SP.x[a.slab_id] = a.ox;
+        if (E.want_L) {
+          slabs_lj.emplace_back((size_t)lneed);
+          slabs_lx.emplace_back((size_t)lneed);
+          a.lj = slabs_lj.back().p, a.lx = slabs_lx.back().p, a.lcap = lneed;
+          LSP.j[a.slab_id] = a.lj, LSP.x[a.slab_id] = a.lx;
+        }
+      }
+      CK(cudaMemsetAsync(ctrs.p + 2, 0, 6 * sizeof(unsigned long long), stream()));
+      counter.zero();
+      a.todo = todo, a.ntodo = ntodo;
+      const int sms = sm_count();
+      if (tier == 0) {
+        constexpr int H = 512, PC = 256;
+        size_t smem = 8 * (size_t)(2 * H + 3 * PC) * 4 + 32 * 8 + 64 * 4;
+        int blocks = std::min(cdiv(ntodo, 8), sms * 4);
+        if (F.small) {
+          CK(cudaFuncSetAttribute(k_solve_smem<32, H, PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_solve_smem<32, H, PC, true><<<blocks, 256, smem, stream()>>>(a);
+        } else {
+          CK(cudaFuncSetAttribute(k_solve_smem<32, H, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_solve_smem<32, H, PC, false><<<blocks, 256, smem, stream()>>>(a);
+        }
+        R.stats.light += ntodo;
+      } else if (tier == 1) {
+        constexpr int H = 16384, PC = 4096;
+        size_t smem = (size_t)(2 * H + 3 * PC) * 4 + 32 * 8 + 64 * 4;
+        int blocks = std::min(ntodo, sms);
+        if (F.small) {
+          CK(cudaFuncSetAttribute(k_solve_smem<256, H, PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_solve_smem<256, H, PC, true><<<blocks, 256, smem, stream()>>>(a);
+        } else {
+          CK(cudaFuncSetAttribute(k_solve_smem<256, H, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_solve_smem<256, H, PC, false><<<blocks, 256, smem, stream()>>>(a);
+        }
+        R.stats.medium += ntodo;
+      } else {
+        int blocks = std::min(ntodo, sms * 2);
+        if (gkeys.p == nullptr) {
+          // nprio = 1 + max prio: the number of pivotal columns
+          DBuf<int> tmp(1);
+          nprio = G.width;  // upper bound on the number of pivots
+          prio2col.alloc(nprio + 1);
+          prio2col.fill_ff();
+          k_prio2col<<<cdiv(G.width, 256), 256, 0, stream()>>>(G.pdesc, G.width, prio2col.p);
+          size_t per = (size_t)G.width;
+          size_t avail = dev_free_bytes();
+          while (blocks > 1 && (size_t)blocks * per * 8 > avail / 2) blocks /= 2;
+          gkeys.alloc((size_t)blocks * per);
+          gkeys.fill_ff();
+          gvals.alloc((size_t)blocks * per);
+          gbitmap.alloc((size_t)blocks * ((nprio + 31) / 32 + 1));
+          gbitmap.zero();
+        } else {
+          blocks = std::min<long long>(blocks, (long long)(gkeys.n / (size_t)G.width));
+        }
+        a.gkeys = gkeys.p, a.gvals = gvals.p, a.gbitmap = gbitmap.p, a.nprio = nprio;
+        if (F.small)
+          k_solve_heavy<256, true><<<blocks, 256, 0, stream()>>>(a, prio2col.p);
+        else
+          k_solve_heavy<256, false><<<blocks, 256, 0, stream()>>>(a, prio2col.p);
+        R.stats.heavy += ntodo;
+      }
+      CK(cudaGetLastError());
+      ctrs.download(h_ctrs, 8);
+      sync();
+      const long long n_tbl = (long long)h_ctrs[2], n_slab = (long long)h_ctrs[3];
+      if (n_tbl == 0 && n_slab == 0) {
+        ntodo = 0;
+        break;
+      }
+      // rows that overflowed the slab are retried in this tier with an exact slab
+      DBuf<int> &dst = (todo == todoA.p) ? todoB : todoA;
+      if (n_slab > 0) {
+        dst.alloc(ntodo);
+        ntodo_d.zero();
+        k_collect_status<<<cdiv(ntodo, 256), 256, 0, stream()>>>(status.p, todo, ntodo, ST_SLAB, dst.p, ntodo_d.p);
+        // table-overflow rows of this attempt must not be lost: collect them after the retries
+        // by re-scanning all rows at the tier boundary (status stays ST_TABLE)
+        todo = dst.p;
+        ntodo = fetch(ntodo_d.p);
+        need = (long long)h_ctrs[4] + 16;
+        lneed = (long long)h_ctrs[5] + 16;
+        continue;
+      }
+      ntodo = 0;
+      break;
+    }
+    // next tier: every row whose status is ST_TABLE
+    DBuf<int> &dst = (todo == todoA.p) ? todoB : todoA;
+    dst.alloc(nrows);
+    ntodo_d.zero();
+    k_collect_status<<<cdiv(nrows, 256), 256, 0, stream()>>>(status.p, nullptr, nrows, ST_TABLE, dst.p, ntodo_d.p);
+    todo = dst.p;
+    ntodo = fetch(ntodo_d.p);
+    if (ntodo > 0) {
+      // mark them pending so a later tier's collect does not see stale states
+      guess = std::max<long long>(guess, 1024LL * ntodo);
+    }
+  }
+  if (ntodo > 0) throw Error("solve_rows: rows left unsolved after the heavy tier");
+
+  unsigned long long h_ctrs[8];
+  ctrs.download(h_ctrs, 8);
+  exclusive_scan_i32_to_i64(R.cnt.p, R.p.p, nrows + 1);
+  if (E.want_L) exclusive_scan_i32_to_i64(R.lcnt.p, R.lp.p, nrows + 1);
+  R.nnz = fetch(R.p.p + nrows);
+  R.stats.bytes = (long long)h_ctrs[0];
+  R.stats.macs = (long long)h_ctrs[1];
+  if (!E.count_only) {
+    R.j.alloc(R.nnz);
+    R.x.alloc(R.nnz);
+    k_gather_rows<<<cdiv((long long)nrows * 32, 256), 256, 0, stream()>>>(R.cnt.p, off.p, R.p.p, nrows, SP, R.j.p, R.x.p);
+    if (E.want_L) {
+      R.lnnz = fetch(R.lp.p + nrows);
+      R.lj.alloc(R.lnnz);
+      R.lx.alloc(R.lnnz);
+      k_gather_rows<<<cdiv((long long)nrows * 32, 256), 256, 0, stream()>>>(R.lcnt.p, loff.p, R.lp.p, nrows, LSP, R.lj.p, R.lx.p);
+    }
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ev1, stream()));
+  sync();
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  R.stats.ms = ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+}
+
+}  // namespace sb

@@ -1,0 +1,176 @@
+"""GPU parity, part 2: the whole path through the C ABI — spasm_echelonize (all option paths),
+spasm_pivots_extract_structural, spasm_dense_rref, spasm_kernel, spasm_solve / spasm_gesv, SpMV —
+bit-exact against the CPU oracle on the same seeded inputs, plus the canonical invariants computed
+independently of the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import checks
+import synth
+from test_gpu_engine import make_fact
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n, m, k, prime, seed, ragged
+    (60, 60, 3, 42013, 1, False),
+    (400, 380, 3, 42013, 2, False),
+    (1500, 1500, 5, 42013, 3, False),   # goes dense after round 0 (like C1)
+    (1200, 2400, 4, 42013, 4, False),   # wide (like C5)
+    (2500, 900, 4, 65521, 5, False),    # tall
+    (700, 800, 6, 7, 6, True),          # tiny prime: cancellations; ragged incl. empty rows
+    (600, 600, 4, 3, 7, True),
+    (500, 520, 4, 4294967291, 8, False),  # largest prime allowed (src/SpaSM.jl:74): 64-bit path
+    (500, 480, 4, 2147483647, 9, True),
+]
+
+
+def _mk(api, case):
+    n, m, k, prime, seed, ragged = case
+    p, j, x = (synth.ragged_rows if ragged else synth.random_rows)(n, m, k, prime, seed)
+    return api.from_arrays(n, m, p, j, x, prime)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_structural_pivots(pkg, gpu, oracle, case):
+    """FL + FL-on-columns + greedy search + reorder + extraction == sequential oracle"""
+    A = _mk(oracle, case)
+    res = []
+    for api in (oracle, gpu):
+        lu, U, qinv = make_fact(pkg, api, A)
+        p = np.zeros(max(A.n, 1), dtype=np.int32)
+        opts = api.EchelonizeOpts()
+        npiv = api.lib.spasm_pivots_extract_structural(A.data, None, C.byref(lu), p.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(opts))
+        res.append(dict(npiv=npiv, p=p.copy(), qinv=qinv.copy(), Up=U.arrays()[0], Uj=U.arrays()[1], Ux=U.arrays()[2]))
+    checks.assert_same(res[0], res[1], "pivots: ")
+
+
+OPTS = [
+    dict(),
+    dict(enable_dense=False),                      # sparse rounds + GPLU
+    dict(enable_dense=False, enable_greedy_pivot_search=False),
+    dict(max_round=0, enable_dense=False),         # pure GPLU
+    dict(sparsity_threshold=0.0, max_round=1, dense_block_size=64),  # forced dense, several blocks
+    dict(max_round=1),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("kw", OPTS)
+def test_echelonize_bit_exact(gpu, oracle, case, kw):
+    A = _mk(oracle, case)
+    fo = oracle.echelonize(A, **kw)
+    fg = gpu.echelonize(A, **kw)
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg), f"{kw}: ")
+
+
+@pytest.mark.parametrize("case", CASES[:6])
+def test_invariants_and_kernel(gpu, oracle, case):
+    A = _mk(gpu, case)
+    fact = gpu.echelonize(A)
+    checks.check_U_structure(gpu, fact)
+    checks.check_rank_and_rowspace(gpu, A, fact)
+    K = gpu.kernel(fact)
+    checks.check_kernel(gpu, A, fact, K)
+    Ko = oracle.kernel(oracle.echelonize(A))
+    for a, b in zip(K.arrays(), Ko.arrays()):
+        assert np.array_equal(a, b)
+    Rq = np.zeros(A.m, dtype=np.int32)
+    R = gpu.rref(fact, Rq)
+    checks.check_rref(gpu, fact, R, Rq)
+
+
+def test_reference_goldens_on_gpu(gpu):
+    """test/runtests.jl:7-24 and README.md:9-48 through the CUDA library"""
+    import json
+    from pathlib import Path
+
+    import scipy.sparse as sp
+
+    G = json.loads((Path(__file__).parent / "golden" / "reference_goldens.json").read_text())
+    g = G["runtests"]
+    p = g["prime"]
+    m = sp.csc_matrix((g["V"], (np.array(g["I"]) - 1, np.array(g["J"]) - 1)))
+    sm = gpu.CSR(m)
+    assert (gpu.sparse(gpu.transpose(gpu.transpose(sm))) != gpu.sparse(sm)).nnz == 0
+    for key, mat in (("kernel", sm), ("kernel_transpose", gpu.transpose(sm))):
+        kk = g[key]
+        want = sp.csc_matrix((kk["V"], (np.array(kk["I"]) - 1, np.array(kk["J"]) - 1)), shape=tuple(kk["shape"]))
+        got = gpu.sparse(gpu.kernel(mat))
+        assert got.shape == want.shape and not ((got - want).toarray() % p).any()
+    r = G["readme"]
+    sm = gpu.CSR(sp.csc_matrix((r["V"], (np.array(r["I"]) - 1, np.array(r["J"]) - 1))))
+    lines = []
+    gpu.log(lambda s: lines.append(s) or 0)
+    try:
+        fact = gpu.echelonize(sm, verbose=True)
+        k = gpu.kernel(fact, verbose=True)
+    finally:
+        gpu.log(None)
+    assert (fact.r, fact.U.nnz(), k.nnz()) == (r["rank"], r["nz_in_basis"], r["nnz_K"])
+    text = "".join(lines)
+    for must in r["log_must_contain"]:
+        assert must in text, must
+
+
+@pytest.mark.parametrize("prime", [7, 42013, 65521, 2147483647, 4294967291])
+def test_dense_rref(gpu, oracle, prime):
+    for (n, m, rank, seed) in [(50, 80, None, 1), (200, 150, 70, 2), (130, 130, None, 3), (1, 9, None, 4)]:
+        D = synth.dense_random(n, m, prime, seed, rank)
+        a, b = D.copy(), D.copy()
+        ro, po = oracle.dense_rref(prime, a)
+        rg, pg = gpu.dense_rref(prime, b)
+        assert ro == rg and np.array_equal(po, pg)
+        assert np.array_equal(a[:ro], b[:rg])
+        if rank is not None:
+            assert rg == min(rank, n, m)
+
+
+@pytest.mark.parametrize("prime", [251, 42013, 4294967291])
+def test_solve_gesv_spmv(gpu, oracle, prime):
+    n, m, k = 300, 420, 4
+    p, j, x = synth.random_rows(n, m, k, prime, 21)
+    A = gpu.from_arrays(n, m, p, j, x, prime)
+    fo, fg = oracle.echelonize(A, L=True), gpu.echelonize(A, L=True)
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg), "L=true: ")
+    Ad = checks.dense_of(gpu, A)
+    assert np.array_equal(checks.mm(checks.dense_of(gpu, fg.L), checks.dense_of(gpu, fg.U), prime), Ad), "A != L.U"
+    rng = np.random.default_rng(3)
+    for t in range(5):
+        x0 = rng.integers(0, prime, size=n)
+        b = checks.mm(x0, Ad, prime) if t < 3 else rng.integers(0, prime, size=m)
+        bb = synth.balanced(b, prime)
+        xo, xg = oracle.solve(fo, bb), gpu.solve(fg, bb)
+        assert (xo is None) == (xg is None)
+        if xg is not None:
+            assert np.array_equal(xo, xg)
+            assert np.array_equal(checks.mm(xg % prime, Ad, prime), b % prime)
+    # SpMV
+    xv = synth.balanced(rng.integers(0, prime, size=n), prime)
+    yv = synth.balanced(rng.integers(0, prime, size=m), prime)
+    assert np.array_equal(gpu.xapy(xv, A, yv.copy()), oracle.xapy(xv, A, yv.copy()))
+    assert np.array_equal(gpu.axpy(A, yv, xv.copy()), oracle.axpy(A, yv, xv.copy()))
+    # gesv
+    import scipy.sparse as sp
+
+    Bd = np.vstack([Ad[3], (Ad[1] + 2 * Ad[2]) % prime, rng.integers(0, prime, size=m)])
+    B = gpu.CSR(sp.csc_matrix(Bd.T), prime)
+    Xo, oko = oracle.gesv(fo, B)
+    Xg, okg = gpu.gesv(fg, B)
+    assert np.array_equal(oko, okg)
+    for a, b2 in zip(Xo.arrays(), Xg.arrays()):
+        assert np.array_equal(a, b2)
+
+
+def test_medium_scale_c1_like(gpu, oracle):
+    """a down-scaled configs[0] (random 5 nnz/row, mod 42013): echelonize + kernel, bit-exact"""
+    n = m = 3000
+    p, j, x = synth.random_rows(n, m, 5, 42013, 0x5A5A0001)
+    A = gpu.from_arrays(n, m, p, j, x, 42013)
+    fo, fg = oracle.echelonize(A), gpu.echelonize(A)
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg))
+    Ko, Kg = oracle.kernel(fo), gpu.kernel(fg)
+    for a, b in zip(Ko.arrays(), Kg.arrays()):
+        assert np.array_equal(a, b)
