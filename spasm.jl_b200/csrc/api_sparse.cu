@@ -173,7 +173,7 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
     logf("Schur complement: %d * %d [%lld nz / density= %.3f], %.1fs\n", n, A->m, (long long)R.nnz, dens, spasm_wtime() - t0);
     return S;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_schur failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_schur failed: %s\n", e.what());
     return nullptr;
   }
 }
@@ -203,7 +203,7 @@ double spasm_schur_estimate_density(const struct spasm_csr *A, const int *p, int
     solve_rows(G, B, E, F, R);
     return ((double)R.nnz) / (A->m - U->n) / R_;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_schur_estimate_density failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_schur_estimate_density failed: %s\n", e.what());
     return -1;
   }
 }
@@ -256,7 +256,7 @@ int spasm_sparse_triangular_solve(const struct spasm_csr *U, const struct spasm_
     }
     return top;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_sparse_triangular_solve failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_sparse_triangular_solve failed: %s\n", e.what());
     return -1;
   }
 }
@@ -286,7 +286,7 @@ struct spasm_csr *spasm_kernel(const struct spasm_lu *fact) {
     logf("[kernel] done in %.1fs. NNZ(K) = %lld\n", spasm_wtime() - t0, (long long)R.nnz);
     return Kh;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_kernel failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_kernel failed: %s\n", e.what());
     return nullptr;
   }
 }
@@ -312,7 +312,7 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv) {
     for (int j = 0; j < m; j++) Rqinv[j] = fact->qinv[j];
     return result_to_host_csr(R, r, m, f.prime, f.F);
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_rref failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_rref failed: %s\n", e.what());
     return nullptr;
   }
 }

@@ -20,7 +20,8 @@ struct Error : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
 
-void logf(const char *fmt, ...);  // -> logcallback or stderr (host_util.cpp)
+void logf(const char *fmt, ...);  // -> logcallback or stderr (host_abi.cu)
+void errf(const char *fmt, ...);  // errors: always stderr, and the callback when installed
 
 #define CK(call)                                                                                   \
   do {                                                                                             \

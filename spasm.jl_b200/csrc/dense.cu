@@ -277,7 +277,7 @@ extern "C" int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, 
     }
     return rr;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_dense_rref failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_dense_rref failed: %s\n", e.what());
     return -1;
   }
 }

@@ -20,6 +20,11 @@ static u64 sm64(u64 &s) {
   return z ^ (z >> 31);
 }
 
+// phase timings of the last spasm_echelonize call (seconds)
+//  0 total  1 upload  2 FL  3 FL-cols  4 greedy  5 reorder+extract  6 density  7 schur  8 tail  9 download
+// 10 rounds 11 flcol rounds 12 greedy windows 13 schur bytes 14 schur macs 15 schur kernel ms
+double g_timings[16];
+
 struct Echelon {
   Fp F;
   int64_t prime;
@@ -35,15 +40,25 @@ struct Echelon {
 static int structural_round(Echelon &E, const DCsr &cur, const std::vector<int> &p_in, bool greedy, PivotSearch &P) {
   int counts[3];
   double t0 = spasm_wtime();
+  P.t_fl = P.t_flcol = P.t_greedy = P.t_reorder = 0;
+  P.flcol_rounds = P.greedy_windows = 0;
   find_structural_pivots(cur, greedy, P, counts);
   sync();
-  logf("[pivots] Faugère-Lachartre: %d pivots found [%.1fs]\n", counts[0], spasm_wtime() - t0);
-  logf("[pivots] ``Faugère-Lachartre on columns'': %d pivots found [%.1fs]\n", counts[1], 0.0);
-  if (greedy) logf("[pivots] greedy alternating cycle-free search: %d pivots found [%.1fs]\n", counts[2], 0.0);
+  (void)t0;
+  logf("[pivots] Faugère-Lachartre: %d pivots found [%.1fs]\n", counts[0], P.t_fl);
+  logf("[pivots] ``Faugère-Lachartre on columns'': %d pivots found [%.1fs]\n", counts[1], P.t_flcol);
+  if (greedy) logf("[pivots] greedy alternating cycle-free search: %d pivots found [%.1fs]\n", counts[2], P.t_greedy);
+  g_timings[2] += P.t_fl, g_timings[3] += P.t_flcol, g_timings[4] += P.t_greedy, g_timings[5] += P.t_reorder;
+  g_timings[11] += P.flcol_rounds, g_timings[12] += P.greedy_windows;
   logf("[pivots] %d pivots found\n", P.npiv);
   const int urow0 = E.U.n;
   DBuf<uint32_t> pivval;
-  extract_pivot_rows(cur, P, E.U, E.Uqinv, E.F, pivval);
+  {
+    double t1 = spasm_wtime();
+    extract_pivot_rows(cur, P, E.U, E.Uqinv, E.F, pivval);
+    sync();
+    g_timings[5] += spasm_wtime() - t1;
+  }
   if (E.L != nullptr && P.npiv > 0) {
     std::vector<int> hp(P.npiv);
     std::vector<uint32_t> hv(P.npiv);
@@ -238,6 +253,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
   const int64_t prime = A->field->p;
   g_seed_state = SEED0;
   const double start = spasm_wtime();
+  for (double &t : g_timings) t = 0;
   logf("[echelonize] Start on %d x %d matrix with %lld nnz\n", n0, m, (long long)spasm_nnz(A));
   if (opts->complete) opts->L = 1;
 
@@ -260,6 +276,8 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
 
   DCsr A0, S;
   upload_csr(A, A0, E.F);
+  sync();
+  g_timings[1] = spasm_wtime() - start;
   const DCsr *cur = &A0;
   int n = n0, npiv = 0;
   std::vector<int> p_in;  // current row -> original row (empty: identity)
@@ -267,9 +285,16 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
   bool finished = false, go_dense = false;
   PivotSearch P;
   P.p.alloc(std::max(n, 1));
+  {
+    std::vector<int> id(std::max(n, 1));
+    for (int i = 0; i < n; i++) id[i] = i;
+    P.p.upload(id.data(), n);
+    sync();
+  }
 
   for (int round = 0; round < opts->max_round; round++) {
     logf("[echelonize] round %d\n", round);
+    g_timings[10] += 1;
     double t0 = spasm_wtime();
     npiv = structural_round(E, *cur, p_in, opts->enable_greedy_pivot_search, P);
     E.t_pivots += spasm_wtime() - t0;
@@ -285,6 +310,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
     }
     t0 = spasm_wtime();
     density = estimate_density(E, *cur, P.p.p + npiv, rem_rows, 100);
+    g_timings[6] += spasm_wtime() - t0, t0 = spasm_wtime();
     logf("Schur complement is %d x %d, estimated density : %.2f (%lld byte)\n", rem_rows, rem_cols, density,
          (long long)(4.0 * density * rem_rows * rem_cols));
     if (density > opts->sparsity_threshold && opts->enable_dense) {
@@ -302,6 +328,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
     SolveResult R;
     solve_rows(G, B, Em, E.F, R);
     g_last_stats = R.stats;
+    g_timings[13] += (double)R.stats.bytes, g_timings[14] += (double)R.stats.macs, g_timings[15] += R.stats.ms;
     std::vector<int> hp(rem_rows), p_out(rem_rows);
     CK(cudaMemcpyAsync(hp.data(), P.p.p + npiv, (size_t)rem_rows * sizeof(int), cudaMemcpyDeviceToHost, stream()));
     sync();
@@ -320,6 +347,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
     density = (n > 0 && rem_cols > 0) ? (double)S.nnz / n / rem_cols : 0.0;
     logf("Schur complement: %d * %d [%lld nz / density= %.3f], %.1fs\n", n, m, (long long)S.nnz, density, spasm_wtime() - t0);
     E.t_schur += spasm_wtime() - t0;
+    g_timings[7] += spasm_wtime() - t0;
     // identity permutation for the finish stage if the loop ends here
     if (P.p.n < (size_t)n) P.p.alloc(n);
     {
@@ -352,8 +380,11 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
       echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size);
     else
       logf("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
+    sync();
     E.t_tail += spasm_wtime() - t0;
+    g_timings[8] = E.t_tail;
   }
+  const double t_dl = spasm_wtime();
 
   // ---- the factor goes back to host memory (plain malloc arrays: src/SpaSM.jl:279-304 unsafe_loads them)
   spasm_lu *fact = (spasm_lu *)spasm_malloc(sizeof(spasm_lu));
@@ -372,6 +403,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
   fact->qinv = (int *)spasm_malloc((i64)std::max(m, 1) * (i64)sizeof(int));
   CK(cudaMemcpyAsync(fact->qinv, E.Uqinv.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream()));
   sync();
+  g_timings[9] = spasm_wtime() - t_dl;
   fact->r = E.U.n;
   fact->complete = 0;
   fact->L = nullptr;
@@ -394,6 +426,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
     spasm_triplet_free(E.L);
     fact->complete = 1;
   }
+  g_timings[0] = spasm_wtime() - start;
   logf("[echelonize] Done in %.1fs. Rank %d, %lld nz in basis\n", spasm_wtime() - start, fact->r, (long long)E.U.nnz);
   return fact;
 }
@@ -408,9 +441,13 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
   try {
     return echelonize_impl(A, opts);
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_echelonize failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_echelonize failed: %s\n", e.what());
     return nullptr;
   }
+}
+
+void spasm_b200_last_timings(double *out) {
+  for (int i = 0; i < 16; i++) out[i] = g_timings[i];
 }
 
 void spasm_lu_free(struct spasm_lu *N) {
@@ -467,7 +504,7 @@ int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, 
     sync();
     return npiv;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_pivots_extract_structural failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_pivots_extract_structural failed: %s\n", e.what());
     return -1;
   }
 }

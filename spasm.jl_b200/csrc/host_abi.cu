@@ -28,6 +28,16 @@ void logf(const char *fmt, ...) {
     fputs(buf, stderr);
 }
 
+void errf(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  fputs(buf, stderr);
+  if (logcallback != nullptr) logcallback(buf);
+}
+
 Fp make_field(int64_t p) {
   Fp F;
   F.p = (uint32_t)p;

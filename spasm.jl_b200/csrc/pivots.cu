@@ -13,9 +13,13 @@
 //    (reachability is monotone in the pivot set, so the continued closure equals the sequential
 //    one; a row that failed speculatively stays failed).
 //  * reorder: heights in the pivot DAG by relaxation, then a stable sort (normalisation N2).
+#include <cooperative_groups.h>
+
 #include <cub/cub.cuh>
 
 #include "pivots.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sb {
 
@@ -126,129 +130,183 @@ struct GreedyArgs {
   int *queue;             // [W][qcap]
   int qcap;
   int *surv, *head, *tail;  // [W]
-  int *newcol;              // [W]
+  int *ctl;                 // [0] cursor  [1] new pivot column (-1: window finished)  [2] row slot of that pivot
   int *npiv;
 };
 
 __device__ __forceinline__ unsigned mark_state(unsigned short s, unsigned gen) { return ((unsigned)s >> 2) == gen ? (s & 3u) : 0u; }
 
-// expand queued pivotal columns until the queue is empty or no candidate survives
+// claim column jj for this row's closure; returns 0 (already reached), 1 (newly reached), and sets
+// `killed` when it was a surviving candidate.  16-bit CAS: two lanes of the warp may meet the same column.
+__device__ __forceinline__ int claim(unsigned short *marks, int jj, unsigned gen, unsigned newstate, int &killed) {
+  for (;;) {
+    unsigned short cur = ((volatile unsigned short *)marks)[jj];
+    unsigned st = mark_state(cur, gen);
+    if (st == ST_SEEN || st == ST_EXP) return 0;
+    unsigned short nv = (unsigned short)((gen << 2) | newstate);
+    if (atomicCAS(&marks[jj], cur, nv) == cur) {
+      killed = (st == ST_CAND);
+      return 1;
+    }
+  }
+}
+
+// Expand queued pivotal columns until the queue is empty or no candidate survives.  Up to 32 queue
+// entries are expanded together: lane l owns entry head+l, and the entries of those pivot rows are
+// walked as one flattened index space, 32 at a time (full lanes even though rows are short).
 __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *marks, int *q, int &head, int &tail, int &surviving,
                                         unsigned gen, int lane) {
   while (head < tail && surviving > 0) {
-    const int j = q[head++];
-    const int I = g.qinv[j];
-    if (I < 0) continue;
-    const long long a = g.Ap[I], b = g.Ap[I + 1];
-    for (long long e0 = a; e0 < b; e0 += 32) {
-      long long e = e0 + lane;
+    const int nb = min(32, tail - head);
+    long long a = 0;
+    int len = 0;
+    if (lane < nb) {
+      const int I = g.qinv[q[head + lane]];
+      if (I >= 0) {
+        a = g.Ap[I];
+        len = (int)(g.Ap[I + 1] - a);
+      }
+    }
+    head += nb;
+    // inclusive prefix of len over lanes
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    for (int f0 = 0; f0 < total; f0 += 32) {
+      const int f = f0 + lane;
+      const int fc = min(f, total - 1);
       int push = 0, killed = 0, jj = 0;
-      if (e < b) {
-        jj = g.Aj[e];
-        unsigned st = mark_state(marks[jj], gen);
-        if (st == 0 || st == ST_CAND) {
-          killed = (st == ST_CAND);
-          if (g.qinv[jj] >= 0) {
-            marks[jj] = (unsigned short)((gen << 2) | ST_EXP);
-            push = 1;
-          } else
-            marks[jj] = (unsigned short)((gen << 2) | ST_SEEN);
-        }
+      // owner lane = number of lanes whose inclusive prefix is <= fc (all lanes take part)
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        int v = __shfl_sync(0xffffffffu, inc, lo + step - 1);
+        if (v <= fc) lo += step;
+      }
+      const int excl = __shfl_sync(0xffffffffu, inc - len, lo);
+      const long long base = __shfl_sync(0xffffffffu, a, lo);
+      if (f < total) {
+        jj = g.Aj[base + (f - excl)];
+        const bool piv = g.qinv[jj] >= 0;
+        if (claim(marks, jj, gen, piv ? ST_EXP : ST_SEEN, killed)) push = piv;
       }
       unsigned pm = __ballot_sync(0xffffffffu, push);
       surviving -= __popc(__ballot_sync(0xffffffffu, killed));
       if (push) q[tail + __popc(pm & ((1u << lane) - 1u))] = jj;
       tail += __popc(pm);
+      __syncwarp();
+      if (surviving <= 0) break;
     }
     __syncwarp();
   }
 }
 
-__global__ void k_greedy_speculate(GreedyArgs g, int w0, int wn, unsigned gen) {
-  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (t >= wn) return;
-  const int i = g.cand[w0 + t];
-  unsigned short *marks = g.marks + (size_t)t * g.m;
-  int *q = g.queue + (size_t)t * g.qcap;
-  int head = 0, tail = 0, surviving = 0;
-  const long long a = g.Ap[i], b = g.Ap[i + 1];
-  for (long long e0 = a; e0 < b; e0 += 32) {
-    long long e = e0 + lane;
-    int push = 0, isc = 0, j = 0;
-    if (e < b) {
-      j = g.Aj[e];
-      if (g.qinv[j] < 0) {
-        marks[j] = (unsigned short)((gen << 2) | ST_CAND);
-        isc = 1;
-      } else {
-        marks[j] = (unsigned short)((gen << 2) | ST_EXP);
-        push = 1;
-      }
-    }
-    unsigned pm = __ballot_sync(0xffffffffu, push);
-    surviving += __popc(__ballot_sync(0xffffffffu, isc));
-    if (push) q[tail + __popc(pm & ((1u << lane) - 1u))] = j;
-    tail += __popc(pm);
-  }
-  __syncwarp();
-  bfs_run(g, marks, q, head, tail, surviving, gen, lane);
-  if (lane == 0) g.surv[t] = surviving, g.head[t] = head, g.tail[t] = tail;
-}
-
-// one warp walks the window in row order
-__global__ void k_greedy_commit(GreedyArgs g, int w0, int wn, unsigned gen) {
-  const int lane = threadIdx.x;
-  int nnew = 0;
-  for (int t = 0; t < wn; t++) {
-    int surviving = g.surv[t];
-    if (surviving == 0) continue;  // failed speculatively: more pivots only reach more
+// one cooperative launch per window of rows:
+//   phase 1  every row of the window runs its BFS against the pivots known at window start;
+//   phase 2  commit loop: warp 0 of block 0 takes the first row (in row order) that still has a
+//            surviving candidate — all earlier rows are final — and makes its first surviving entry a
+//            pivot; then every later row that has touched that column continues its BFS from it.
+__global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int wn, unsigned gen) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int NW = (gridDim.x * blockDim.x) >> 5;
+  for (int t = gw; t < wn; t += NW) {
     const int i = g.cand[w0 + t];
     unsigned short *marks = g.marks + (size_t)t * g.m;
     int *q = g.queue + (size_t)t * g.qcap;
-    int head = g.head[t], tail = g.tail[t];
-    // pivots committed earlier in this window that this row has touched
-    for (int b0 = 0; b0 < nnew && surviving > 0; b0 += 32) {
-      int jn = (b0 + lane < nnew) ? g.newcol[b0 + lane] : -1;
-      unsigned st = jn >= 0 ? mark_state(marks[jn], gen) : 0u;
-      unsigned hit = __ballot_sync(0xffffffffu, st == ST_CAND || st == ST_SEEN);
-      while (hit && surviving > 0) {
-        int src = __ffs(hit) - 1;
-        hit &= hit - 1;
-        int jc = __shfl_sync(0xffffffffu, jn, src);
-        unsigned s2 = mark_state(marks[jc], gen);  // may have been expanded by a continuation just before
-        if (s2 == ST_EXP) continue;
-        if (s2 == ST_CAND) surviving--;
-        __syncwarp();
-        if (lane == 0) {
-          marks[jc] = (unsigned short)((gen << 2) | ST_EXP);
-          q[tail] = jc;
-        }
-        tail++;
-        __syncwarp();
-        bfs_run(g, marks, q, head, tail, surviving, gen, lane);
-      }
-    }
-    if (surviving <= 0) continue;
-    // first surviving candidate in storage order
+    int head = 0, tail = 0, surviving = 0;
     const long long a = g.Ap[i], b = g.Ap[i + 1];
-    int jp = -1;
-    for (long long e0 = a; e0 < b && jp < 0; e0 += 32) {
+    for (long long e0 = a; e0 < b; e0 += 32) {
       long long e = e0 + lane;
-      int j = e < b ? g.Aj[e] : -1;
-      unsigned c = __ballot_sync(0xffffffffu, j >= 0 && mark_state(marks[j], gen) == ST_CAND);
-      if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
-    }
-    if (jp >= 0) {
-      if (lane == 0) {
-        g.pinv[i] = jp;
-        g.qinv[jp] = i;
-        g.newcol[nnew] = jp;
-        atomicAdd(g.npiv, 1);
+      int push = 0, isc = 0, j = 0;
+      if (e < b) {
+        j = g.Aj[e];
+        if (g.qinv[j] < 0) {
+          marks[j] = (unsigned short)((gen << 2) | ST_CAND);
+          isc = 1;
+        } else {
+          marks[j] = (unsigned short)((gen << 2) | ST_EXP);
+          push = 1;
+        }
       }
-      nnew++;
-      __syncwarp();
-      __threadfence_block();
+      unsigned pm = __ballot_sync(0xffffffffu, push);
+      surviving += __popc(__ballot_sync(0xffffffffu, isc));
+      if (push) q[tail + __popc(pm & ((1u << lane) - 1u))] = j;
+      tail += __popc(pm);
     }
+    __syncwarp();
+    bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+    if (lane == 0) g.surv[t] = surviving, g.head[t] = head, g.tail[t] = tail;
+  }
+  if (gw == 0 && lane == 0) g.ctl[0] = 0;
+  __threadfence();
+  grid.sync();
+  for (;;) {
+    if (gw == 0) {
+      // first row at or after the cursor that still has a surviving candidate
+      int cur = g.ctl[0], found = -1;
+      for (int t0 = cur; t0 < wn && found < 0; t0 += 32) {
+        int t = t0 + lane;
+        unsigned has = __ballot_sync(0xffffffffu, t < wn && ((volatile int *)g.surv)[t] > 0);
+        if (has) found = t0 + (__ffs(has) - 1);
+      }
+      int jp = -1;
+      if (found >= 0) {
+        const int i = g.cand[w0 + found];
+        const unsigned short *marks = g.marks + (size_t)found * g.m;
+        const long long a = g.Ap[i], b = g.Ap[i + 1];
+        for (long long e0 = a; e0 < b && jp < 0; e0 += 32) {
+          long long e = e0 + lane;
+          int j = e < b ? g.Aj[e] : -1;
+          unsigned c = __ballot_sync(0xffffffffu, j >= 0 && mark_state(((volatile unsigned short *)marks)[j], gen) == ST_CAND);
+          if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
+        }
+        if (lane == 0) {
+          g.pinv[i] = jp;
+          g.qinv[jp] = i;
+          g.surv[found] = 0;
+          atomicAdd(g.npiv, 1);
+        }
+      }
+      if (lane == 0) {
+        g.ctl[0] = found >= 0 ? found + 1 : wn;
+        g.ctl[1] = jp;
+      }
+      __threadfence();
+    }
+    grid.sync();
+    const int jp = ((volatile int *)g.ctl)[1];
+    if (jp < 0) break;
+    const int cursor = ((volatile int *)g.ctl)[0];
+    // rows after the committed one that have touched column jp continue their BFS through its row
+    int t = gw;
+    if (t < cursor) t += ((cursor - t + NW - 1) / NW) * NW;
+    for (; t < wn; t += NW) {
+      int surviving = g.surv[t];
+      if (surviving <= 0) continue;
+      unsigned short *marks = g.marks + (size_t)t * g.m;
+      const unsigned st = mark_state(marks[jp], gen);
+      if (st != ST_CAND && st != ST_SEEN) continue;
+      int *q = g.queue + (size_t)t * g.qcap;
+      int head = g.head[t], tail = g.tail[t];
+      if (st == ST_CAND) surviving--;
+      __syncwarp();
+      if (lane == 0) {
+        marks[jp] = (unsigned short)((gen << 2) | ST_EXP);
+        q[tail] = jp;
+      }
+      tail++;
+      __syncwarp();
+      bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+      if (lane == 0) g.surv[t] = surviving, g.head[t] = head, g.tail[t] = tail;
+    }
+    __threadfence();
+    grid.sync();
   }
 }
 
@@ -348,6 +406,7 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
   DBuf<int> ctr(4);
   ctr.zero();
   const int rowblocks = cdiv((long long)n * 32, 256);
+  double tt = spasm_wtime();
   {  // FL
     DBuf<unsigned long long> best(m);
     best.fill_ff();
@@ -356,6 +415,7 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
     CK(cudaGetLastError());
     counts[0] = fetch(ctr.p);
   }
+  P.t_fl = spasm_wtime() - tt, tt = spasm_wtime();
   {  // FL on columns
     DBuf<unsigned char> open(m), state(n);
     DBuf<unsigned long long> res(m);
@@ -369,10 +429,12 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
       k_flc_reserve<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, P.qinv.p, open.p, state.p, res.p, round);
       k_flc_commit<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, P.qinv.p, open.p, state.p, res.p, round, ctr.p);
       CK(cudaGetLastError());
+      P.flcol_rounds = (int)round + 1;
       if (fetch(ctr.p + 1) == 0) break;
     }
     counts[1] = fetch(ctr.p);
   }
+  P.t_flcol = spasm_wtime() - tt, tt = spasm_wtime();
   if (greedy) {
     DBuf<int> flag(n + 1), cand;
     DBuf<long long> pos(n + 1);
@@ -384,20 +446,24 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
       k_compact_rows<<<cdiv(n, 256), 256, 0, s>>>(flag.p, pos.p, n, cand.p);
       const int qcap = std::min(n, m) + 1;
       const size_t per = (size_t)m * 2 + (size_t)qcap * 4;
-      size_t budget = std::min<size_t>(dev_free_bytes() / 4, (size_t)12 << 30);
-      int W = (int)std::max<size_t>(32, std::min<size_t>(4096, budget / per));
+      size_t budget = std::min<size_t>(dev_free_bytes() / 3, (size_t)24 << 30);
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy_window, 256, 0));
+      const int grid = std::max(1, occ) * sm_count();
+      int W = (int)std::max<size_t>(32, std::min<size_t>((size_t)grid * 8, budget / per));
       W = std::min(W, ncand);
       DBuf<unsigned short> marks((size_t)W * m);
-      DBuf<int> queue((size_t)W * qcap), surv(W), head(W), tail(W), newcol(W);
+      DBuf<int> queue((size_t)W * qcap), surv(W), head(W), tail(W), ctl(4);
       marks.zero();
       ctr.zero();
-      GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, queue.p, qcap, surv.p, head.p, tail.p, newcol.p, ctr.p};
+      GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, queue.p, qcap, surv.p, head.p, tail.p, ctl.p, ctr.p};
       unsigned gen = 1;
       for (int w0 = 0; w0 < ncand; w0 += W) {
         int wn = std::min(W, ncand - w0);
-        k_greedy_speculate<<<cdiv((long long)wn * 32, 256), 256, 0, s>>>(g, w0, wn, gen);
-        k_greedy_commit<<<1, 32, 0, s>>>(g, w0, wn, gen);
+        void *args[] = {&g, &w0, &wn, &gen};
+        CK(cudaLaunchCooperativeKernel((void *)k_greedy_window, dim3(grid), dim3(256), args, 0, s));
         gen++;
+        P.greedy_windows++;
         if (gen == (1u << 14)) {
           marks.zero();
           gen = 1;
@@ -409,6 +475,7 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
   }
   const int npiv = counts[0] + counts[1] + counts[2];
   P.npiv = npiv;
+  P.t_greedy = spasm_wtime() - tt, tt = spasm_wtime();
   // ---- reorder: p[0:npiv] by (height desc, row asc), p[npiv:n] the other rows increasing
   {
     DBuf<int> flag(n + 1), prow(std::max(npiv, 1));
@@ -450,6 +517,8 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
     }
     CK(cudaGetLastError());
   }
+  sync();
+  P.t_reorder = spasm_wtime() - tt;
   return npiv;
 }
 

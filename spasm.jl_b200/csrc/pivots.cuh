@@ -10,6 +10,8 @@ struct PivotSearch {
   DBuf<int> p;     // [n] pivotal rows first (topological order, N2), then the others increasing
   int npiv = 0;
   int max_height = 0;
+  double t_fl = 0, t_flcol = 0, t_greedy = 0, t_reorder = 0;  // seconds (host clock around synchronised phases)
+  int flcol_rounds = 0, greedy_windows = 0;
 };
 
 // counts = {FL, FL on columns, greedy}

@@ -191,7 +191,7 @@ extern "C" struct spasm_csr *spasm_transpose(const struct spasm_csr *A) {
     sb::transpose_csr(dA, dT);
     return sb::download_csr(dT, A->field->p, F);
   } catch (const std::exception &e) {
-    sb::logf("[spasm_b200] spasm_transpose failed: %s\n", e.what());
+    sb::errf("[spasm_b200] spasm_transpose failed: %s\n", e.what());
     return nullptr;
   }
 }

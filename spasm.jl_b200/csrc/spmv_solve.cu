@@ -176,7 +176,7 @@ void spasm_xApy(const spasm_ZZp *x, const struct spasm_csr *A, spasm_ZZp *y) {
     transpose_csr(dA, dT);
     spmv(dT, x, y, F);
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_xApy failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_xApy failed: %s\n", e.what());
   }
 }
 void spasm_Axpy(const struct spasm_csr *A, const spasm_ZZp *x, spasm_ZZp *y) {
@@ -187,7 +187,7 @@ void spasm_Axpy(const struct spasm_csr *A, const spasm_ZZp *x, spasm_ZZp *y) {
     upload_csr(A, dA, F);
     spmv(dA, x, y, F);
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_Axpy failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_Axpy failed: %s\n", e.what());
   }
 }
 
@@ -210,7 +210,7 @@ bool spasm_dense_forward_solve(const struct spasm_csr *U, spasm_ZZp *b, spasm_ZZ
     for (int i = 0; i < r; i++) x[i] = to_bal(z[i], f.F);
     return ok;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_dense_forward_solve failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_dense_forward_solve failed: %s\n", e.what());
     return false;
   }
 }
@@ -227,7 +227,7 @@ bool spasm_dense_back_solve(const struct spasm_csr *L, spasm_ZZp *b, spasm_ZZp *
     backward(S, dr, F, z, L->n, x);
     return true;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_dense_back_solve failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_dense_back_solve failed: %s\n", e.what());
     return false;
   }
 }
@@ -250,7 +250,7 @@ bool spasm_solve(const struct spasm_lu *fact, const spasm_ZZp *b, spasm_ZZp *x) 
     backward(S, dr, f.F, z, fact->L->n, x);
     return true;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_solve failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_solve failed: %s\n", e.what());
     return false;
   }
 }
@@ -289,7 +289,7 @@ struct spasm_csr *spasm_gesv(const struct spasm_lu *fact, const struct spasm_csr
     if (!Xj.empty()) memcpy(X->j, Xj.data(), Xj.size() * sizeof(int)), memcpy(X->x, Xx.data(), Xx.size() * sizeof(spasm_ZZp));
     return X;
   } catch (const std::exception &e) {
-    logf("[spasm_b200] spasm_gesv failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_gesv failed: %s\n", e.what());
     return nullptr;
   }
 }

@@ -130,9 +130,12 @@ def dense_random(n: int, m: int, prime: int, seed: int, rank: int | None = None)
         return balanced(v, prime).reshape(n, m)
     a = (stream(seed, 0, n * rank) % np.uint64(prime)).astype(np.int64).reshape(n, rank)
     b = (stream(seed + 7, 0, rank * m) % np.uint64(prime)).astype(np.int64).reshape(rank, m)
-    out = np.zeros((n, m), dtype=np.int64)
-    for k0 in range(0, rank, 64):  # keep products below 2^63
-        out = (out + a[:, k0 : k0 + 64] @ b[k0 : k0 + 64]) % prime
+    if prime < (1 << 28):
+        out = np.zeros((n, m), dtype=np.int64)
+        for k0 in range(0, rank, 64):  # keep sums of products below 2^63
+            out = (out + a[:, k0 : k0 + 64] @ b[k0 : k0 + 64]) % prime
+    else:  # exact Python integers
+        out = ((a.astype(object) @ b.astype(object)) % prime).astype(np.int64)
     return balanced(out, prime).reshape(n, m)
 
 

@@ -146,7 +146,7 @@ def test_solve_gesv_spmv(gpu, oracle, prime):
         assert (xo is None) == (xg is None)
         if xg is not None:
             assert np.array_equal(xo, xg)
-            assert np.array_equal(checks.mm(xg % prime, Ad, prime), b % prime)
+            assert np.array_equal(checks.mm(xg.astype(np.int64) % prime, Ad, prime), b % prime)
     # SpMV
     xv = synth.balanced(rng.integers(0, prime, size=n), prime)
     yv = synth.balanced(rng.integers(0, prime, size=m), prime)

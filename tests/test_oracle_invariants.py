@@ -116,7 +116,7 @@ def test_solve_and_gesv(oracle, prime):
         inside = synth.dense_rank_mod_p(np.vstack([Ad, b]), prime) == fact.r
         assert (xb is not None) == inside
         if xb is not None:
-            assert np.array_equal(checks.mm(xb % prime, Ad, prime), b % prime), "x.A != b"
+            assert np.array_equal(checks.mm(xb.astype(np.int64) % prime, Ad, prime), b % prime), "x.A != b"
     # gesv: rows of B = some rows of A and a random row
     import scipy.sparse as sp
 
@@ -154,7 +154,7 @@ def test_triangular_solve_contract(oracle, prime):
         xb[qinv[pat[piv]]] = xx[pat[piv]]
         xa = xx.copy()
         xa[pat[piv]] = 0
-        assert np.array_equal((checks.mm(xb % prime, Ud, prime) + xa) % prime, Ad[row])
+        assert np.array_equal((checks.mm(xb.astype(np.int64) % prime, Ud, prime) + xa) % prime, Ad[row])
         assert not xa.any(), "rows of A are in the row space of U"
         assert not xj[2 * m :].any(), "marks must be left zero (\"it remains OK\", src/SpaSM.jl:700)"
         xj[: 2 * m] = 0  # pattern + DFS stack scratch; the Julia driver refills with zeros too (:740)
