@@ -203,46 +203,315 @@ __global__ void k_write_rows(const uint32_t *__restrict__ S, long long ld, int m
   }
 }
 
+void make_free_columns(const int *qinv, int m, int *flag, long long *pos, int *q, int *qpos) {
+  cudaStream_t s = stream();
+  k_free_cols<<<cdiv(m + 1, 256), 256, 0, s>>>(qinv, m, flag);
+  exclusive_scan_i32_to_i64(flag, pos, m + 1);
+  k_make_q<<<cdiv(m, 256), 256, 0, s>>>(flag, pos, m, q, qpos);
+  CK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ GEMM mod p on CUDA cores
+// 64x64 output tile, K chunks of 32 through shared memory, 4x4 outputs per thread.  Products of
+// residues below 2^16 fit 32 bits and are summed in 64-bit accumulators with ONE reduction at the
+// end; larger primes reduce every product.  (The tcgen05 int8-limb kernel in dense_mma.cu takes
+// over for p < 2^16 and large shapes.)
+template <bool SMALL>
+__global__ void __launch_bounds__(256) k_gemm_nt(uint32_t *__restrict__ C, long long ldc, int M, int N, const uint32_t *__restrict__ A,
+                                                  long long lda, const uint32_t *__restrict__ B, long long ldb, int K, int subtract, Fp F) {
+  __shared__ uint32_t As[64][33], Bs[64][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  unsigned long long acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
+      const int rr = idx >> 5, kk = idx & 31;
+      const int gi = i0 + rr, gj = j0 + rr, gk = k0 + kk;
+      As[rr][kk] = (gi < M && gk < K) ? A[(long long)gi * lda + gk] : 0u;
+      Bs[rr][kk] = (gj < N && gk < K) ? B[(long long)gj * ldb + gk] : 0u;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; kk++) {
+      uint32_t av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) av[a] = As[ty + 16 * a][kk];
+#pragma unroll
+      for (int b = 0; b < 4; b++) bv[b] = Bs[tx + 16 * b][kk];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          if (SMALL)
+            acc[a][b] += (unsigned long long)(av[a] * bv[b]);
+          else
+            acc[a][b] += mulmod<false>(av[a], bv[b], F);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
+      if (gi < M && gj < N) {
+        uint32_t v = red64(acc[a][b], F);
+        uint32_t *c = C + (long long)gi * ldc + gj;
+        *c = subtract ? addmod(*c, negmod(v, F), F) : v;
+      }
+    }
+}
+
+bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
+                 bool subtract, const Fp &F);  // dense_mma.cu: returns false when the shape / prime is not handled
+
+void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
+             bool subtract, const Fp &F) {
+  if (M <= 0 || N <= 0) return;
+  if (gemm_nt_mma(C, ldc, M, N, A, lda, B, ldb, K, subtract, F)) return;
+  dim3 grid(cdiv(N, 64), cdiv(M, 64));
+  if (F.small)
+    k_gemm_nt<true><<<grid, 256, 0, stream()>>>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F);
+  else
+    k_gemm_nt<false><<<grid, 256, 0, stream()>>>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F);
+  CK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ panel factorisation
+// The panel is rows [k0, k0+Sn) of D, i.e. Dt[c][k0 + t].  T (Sn x Sn) accumulates the row
+// operations: T.Panel is in reduced row echelon form on the columns scanned so far.  Columns are
+// scanned left to right in tiles; for each tile  W = T.Panel_tile  (GEMM), one CTA runs
+// Gauss-Jordan on W among the rows that are not pivots yet (at most 32 new pivots per tile) while
+// recording the operations as the columns Gc of the update  T <- G.T.
+struct PanelCtl {
+  int npiv;      // pivots found so far in this panel
+  int found;     // pivots found in the last tile
+  int consumed;  // columns consumed by the last tile
+  int pad;
+};
+template <bool SMALL>
+__global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ W, int Sn, int wc, long long ldw, int c0,
+                                                      int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
+                                                      uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl, Fp F) {
+  __shared__ int red[32];
+  __shared__ int s_piv;
+  __shared__ uint32_t s_alpha;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int npiv = ctl->npiv, found = 0, cc = 0;
+  for (int idx = tid; idx < Sn * 32; idx += 1024) Gc[idx] = 0;
+  __syncthreads();
+  for (; cc < wc && found < 32 && npiv < Sn; cc++) {
+    // first row that is not a pivot yet and is nonzero on column cc
+    int best = 0x7fffffff;
+    for (int r = tid; r < Sn; r += 1024)
+      if (!ispiv[r] && W[(long long)r * ldw + cc] != 0) {
+        best = r;
+        break;
+      }
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) red[wid] = best;
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < 32; i++) best = min(best, red[i]);
+      s_piv = best;
+      if (best != 0x7fffffff) {
+        s_alpha = dev_inv(W[(long long)best * ldw + cc], F.p);
+        ispiv[best] = 1;
+        pivrow[npiv] = best;
+        pivcol[npiv] = c0 + cc;
+        tilepiv[found] = best;
+        Gc[best * 32 + found] = 1;
+      }
+    }
+    __syncthreads();
+    const int pr = s_piv;
+    if (pr == 0x7fffffff) continue;
+    const uint32_t alpha = s_alpha;
+    // scale the pivot row of [W | Gc]
+    uint32_t *Wp = W + (long long)pr * ldw;
+    for (int k = cc + tid; k < wc; k += 1024) Wp[k] = mulmod<SMALL>(alpha, Wp[k], F);
+    if (tid <= found) Gc[pr * 32 + tid] = mulmod<SMALL>(alpha, Gc[pr * 32 + tid], F);
+    __syncthreads();
+    // eliminate column cc from every other row: warp per row
+    for (int r = wid; r < Sn; r += 32) {
+      if (r == pr) continue;
+      uint32_t *Wr = W + (long long)r * ldw;
+      const uint32_t f = Wr[cc];
+      if (f == 0) continue;
+      const uint32_t nf = negmod(f, F);
+      __syncwarp();
+      for (int k = cc + lane; k < wc; k += 32) Wr[k] = addmod(Wr[k], mulmod<SMALL>(nf, Wp[k], F), F);
+      if (lane <= found) Gc[r * 32 + lane] = addmod(Gc[r * 32 + lane], mulmod<SMALL>(nf, Gc[pr * 32 + lane], F), F);
+    }
+    found++;
+    npiv++;
+    __syncthreads();
+  }
+  if (tid == 0) ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc;
+}
+__global__ void k_set_identity(uint32_t *T, int n) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx < (long long)n * n) T[idx] = (idx / n == idx % n) ? 1u : 0u;
+}
+__global__ void k_gather_T_rows(const uint32_t *__restrict__ T, int Sn, const int *__restrict__ rowsel, const int *__restrict__ count_ptr,
+                                int count_fixed, uint32_t *__restrict__ out) {
+  const int cnt = count_ptr ? *count_ptr : count_fixed;
+  const int s = blockIdx.y;
+  if (s >= cnt) return;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < Sn) out[(long long)s * Sn + col] = T[(long long)rowsel[s] * Sn + col];
+}
+// T[r][:] = (r is a pivot of this tile ? 0 : T[r][:]) + sum_s Gc[r][s] * Tp[s][:]
+template <bool SMALL>
+__global__ void k_update_T(uint32_t *__restrict__ T, int Sn, const uint32_t *__restrict__ Gc, const uint32_t *__restrict__ Tp,
+                           const int *__restrict__ tilepiv, const PanelCtl *__restrict__ ctl, Fp F) {
+  const int found = ctl->found;
+  if (found == 0) return;
+  const int r = blockIdx.y, col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= Sn) return;
+  bool isp = false;
+  for (int s = 0; s < found; s++) isp |= (tilepiv[s] == r);
+  unsigned long long acc = isp ? 0ull : T[(long long)r * Sn + col];
+  for (int s = 0; s < found; s++) {
+    const uint32_t g = Gc[r * 32 + s];
+    if (g == 0) continue;
+    if (SMALL)
+      acc += (unsigned long long)(g * Tp[(long long)s * Sn + col]);
+    else
+      acc += mulmod<false>(g, Tp[(long long)s * Sn + col], F);
+  }
+  T[(long long)r * Sn + col] = red64(acc, F);
+}
+__global__ void k_transpose_u32(const uint32_t *__restrict__ in, long long ldi, int rows, int cols, uint32_t *__restrict__ out, long long ldo) {
+  // out[c][r] = in[r][c]
+  __shared__ uint32_t tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int r = r0 + y, c = c0 + threadIdx.x;
+    tile[y][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * ldi + c] : 0u;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int c = c0 + y, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(long long)c * ldo + r] = tile[threadIdx.x][y];
+  }
+}
+// Pt[k][s] = Dt[pivcol[s]][kbase + k]
+__global__ void k_gather_pivot_cols_T(const uint32_t *__restrict__ Dt, long long ld, const int *__restrict__ pivcol, int rr, long long kbase,
+                                      int nk, uint32_t *__restrict__ Pt, long long ldp) {
+  __shared__ uint32_t tile[32][33];
+  const int k0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int s = s0 + y, k = k0 + threadIdx.x;
+    tile[y][threadIdx.x] = (s < rr && k < nk) ? Dt[(long long)pivcol[s] * ld + kbase + k] : 0u;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int k = k0 + y, s = s0 + threadIdx.x;
+    if (k < nk && s < rr) Pt[(long long)k * ldp + s] = tile[threadIdx.x][y];
+  }
+}
+__global__ void k_iota2(int *a, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
+// returns rr; T final, pivrow/pivcol filled (pivcol increasing)
+static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0, int Sn, uint32_t *T, DBuf<int> &ispiv, DBuf<int> &pivrow,
+                        DBuf<int> &pivcol, const Fp &F) {
+  cudaStream_t s = stream();
+  const int WMAX = 2048;
+  DBuf<uint32_t> W((size_t)Sn * WMAX), Gc((size_t)Sn * 32), Tp((size_t)32 * Sn);
+  DBuf<int> tilepiv(32);
+  DBuf<PanelCtl> ctl(1);
+  ctl.zero();
+  ispiv.alloc(Sn);
+  ispiv.zero();
+  pivrow.alloc(Sn);
+  pivcol.alloc(Sn);
+  k_set_identity<<<cdiv((long long)Sn * Sn, 256), 256, 0, s>>>(T, Sn);
+  int w = 32, npiv = 0;
+  for (int c0 = 0; c0 < Sm0 && npiv < Sn;) {
+    const int wc = std::min(w, Sm0 - c0);
+    // W = T . Panel_tile
+    gemm_nt(W.p, wc, Sn, wc, T, Sn, Dt + (long long)c0 * ld + k0, ld, Sn, false, F);
+    if (F.small)
+      k_tile_gauss<true><<<1, 1024, 0, s>>>(W.p, Sn, wc, wc, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
+    else
+      k_tile_gauss<false><<<1, 1024, 0, s>>>(W.p, Sn, wc, wc, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
+    k_gather_T_rows<<<dim3(cdiv(Sn, 256), 32), 256, 0, s>>>(T, Sn, tilepiv.p, &ctl.p->found, 0, Tp.p);
+    if (F.small)
+      k_update_T<true><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, Tp.p, tilepiv.p, ctl.p, F);
+    else
+      k_update_T<false><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, Tp.p, tilepiv.p, ctl.p, F);
+    CK(cudaGetLastError());
+    PanelCtl h = fetch(ctl.p);
+    npiv = h.npiv;
+    c0 += h.consumed;
+    // adapt the tile width to the pivot density just seen
+    if (h.found >= 16)
+      w = 32;
+    else if (h.found == 0)
+      w = std::min(WMAX, w * 4);
+    else
+      w = std::min(WMAX, std::max(32, (int)(32.0 * h.consumed / h.found)));
+  }
+  return npiv;
+}
+
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size) {
   cudaStream_t s = stream();
-  const int m = A.m;
   if (block_size <= 0) block_size = 1000;
-  DBuf<int> flag(m + 1), q(m), qpos(m), pivcol, pivrow;
-  DBuf<long long> pos(m + 1);
-  DBuf<PDesc> pdesc;
-  for (int processed = 0; processed < nrows;) {
-    const int Sm = m - U.n;
-    if (Sm == 0) break;
-    const int Sn = std::min(block_size, nrows - processed);
-    logf("[echelonize/dense] processing dense schur complement of dimension %d x %d; block size=%d\n", nrows - processed, Sm, block_size);
-    k_free_cols<<<cdiv(m + 1, 256), 256, 0, s>>>(Uqinv.p, m, flag.p);
-    exclusive_scan_i32_to_i64(flag.p, pos.p, m + 1);
-    k_make_q<<<cdiv(m, 256), 256, 0, s>>>(flag.p, pos.p, m, q.p, qpos.p);
-    build_pdesc_U(U, Uqinv.p, pdesc);
-    SolveSystem G{U.j.p, U.x.p, pdesc.p, m};
-    SolveRows B{A.p.p, A.j.p, A.x.p, rows + processed, Sn, nullptr};
-    SolveEmit E;
-    SolveResult R;
-    solve_rows(G, B, E, F, R);
-    DBuf<uint32_t> S((size_t)Sn * Sm);
-    S.zero();
-    k_scatter_dense<<<cdiv((long long)Sn * 32, 256), 256, 0, s>>>(R.p.p, R.j.p, R.x.p, Sn, qpos.p, S.p, Sm);
-    CK(cudaGetLastError());
-    const int rr = dense_rref_device(S.p, Sn, Sm, Sm, F, pivcol, pivrow);
+  if (nrows == 0 || A.m == U.n) return;
+  double t0 = spasm_wtime();
+  DenseSchur D;
+  build_dense_schur(A, rows, nrows, U, Uqinv.p, F, D);
+  const int Sm0 = D.Sm0;
+  const long long ld = D.ld;
+  logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)\n", nrows, Sm0, spasm_wtime() - t0, D.levels);
+  const int Bmax = std::min(block_size, nrows);
+  DBuf<uint32_t> T((size_t)Bmax * Bmax), Tsel((size_t)Bmax * Bmax), R((size_t)Bmax * Sm0), Rt, Pt;
+  DBuf<int> ispiv, pivrow, pivcol, ident(Bmax);
+  k_iota2<<<cdiv(Bmax, 256), 256, 0, s>>>(ident.p, Bmax);
+  for (long long k0 = 0; k0 < nrows; k0 += block_size) {
+    const int Sn = (int)std::min<long long>(block_size, nrows - k0);
+    logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - k0, A.m - U.n,
+         block_size);
+    const int rr = panel_factor(D.Dt.p, ld, Sm0, k0, Sn, T.p, ispiv, pivrow, pivcol, F);
     if (rr > 0) {
+      // reduced rows  R[s][c] = sum_t T[pivrow[s]][t] * Dt[c][k0+t]
+      k_gather_T_rows<<<dim3(cdiv(Sn, 256), rr), 256, 0, s>>>(T.p, Sn, pivrow.p, nullptr, rr, Tsel.p);
+      gemm_nt(R.p, Sm0, rr, Sm0, Tsel.p, Sn, D.Dt.p + k0, ld, Sn, false, F);
+      // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
       DBuf<int> cnt(rr + 1);
       DBuf<long long> rpos(rr + 1);
-      k_count_rows<<<rr, 256, 0, s>>>(S.p, Sm, Sm, pivrow.p, rr, cnt.p);
+      k_count_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, rr, cnt.p);
       exclusive_scan_i32_to_i64(cnt.p, rpos.p, rr + 1);
       const long long add = fetch(rpos.p + rr);
       csr_reserve(U, U.nnz + add, U.n + rr);
-      k_write_rows<<<rr, 256, 0, s>>>(S.p, Sm, Sm, pivrow.p, pivcol.p, q.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
+      k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pivcol.p, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
       CK(cudaGetLastError());
       U.nnz += add;
       U.n += rr;
+      // trailing update of the later rows:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
+      const long long kb = k0 + Sn;
+      const int nk = (int)(nrows - kb);
+      if (nk > 0) {
+        const long long ldk = ((long long)rr + 15) / 16 * 16;
+        Rt.alloc((size_t)Sm0 * ldk);
+        Pt.alloc((size_t)nk * ldk);
+        k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
+        k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt.p, ldk);
+        gemm_nt(D.Dt.p + kb, ld, Sm0, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F);
+      }
     }
-    processed += Sn;
     logf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U.n);
+    if (U.n == A.m) break;
   }
 }
 

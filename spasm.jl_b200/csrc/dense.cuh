@@ -10,6 +10,20 @@ namespace sb {
 // row pivrow[s].  Returns the rank.
 int dense_rref_device(uint32_t *S, int n, int m, long long ld, const Fp &F, DBuf<int> &pivcol, DBuf<int> &pivrow);
 
+// dense Schur complement of the rows `rows` of A w.r.t. U, stored transposed (dense_engine.cu):
+// Dt[c][k] = entry of remaining row k on free column q0[c]; leading dimension ld (k contiguous)
+struct DenseSchur {
+  int n_rem = 0, Sm0 = 0, levels = 0;
+  long long ld = 0;
+  DBuf<int> q0;
+  DBuf<uint32_t> Dt;
+};
+void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U, const int *Uqinv, const Fp &F, DenseSchur &D);
+
+// C (M x N, row-major, ldc) = [C -] A (M x K, row-major lda) . B^T (B is N x K, row-major ldb)   (mod p)
+void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
+             bool subtract, const Fp &F);
+
 // eliminate the rows `rows` of A against U block by block, RREF each block, append to U
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);
 
