@@ -1,5 +1,344 @@
-// dense_mma.cu — tcgen05 int8-limb GEMM mod p (placeholder until the kernel lands: declines every shape)
+// dense_mma.cu — the one real dense contraction of the hot path on the 5th-gen tensor cores:
+//     C (M x N) = [C -] A (M x K) . B^T (N x K)   mod p,     p < 2^16
+// as tcgen05.mma.kind::i8 tiles (SASS: UTCIMMA) fed by TMA, int32 accumulators in TMEM, reduction
+// mod p in the epilogue.  This is the trailing update / row transformation of the dense Schur tail
+// (replaces FFLAS fgemm behind spasm_ffpack_rref, prototype src/SpaSM.jl:805).
+//
+// Limbs.  Residues in [0,p) are split as a = a1*256 + a0 with a0,a1 unsigned bytes, so
+//     a*b = a1*b1 * 2^16 + (a1*b0 + a0*b1) * 2^8 + a0*b0.
+// Four u8 x u8 MMAs per K-step feed THREE int32 accumulators (hi, mid, lo) in TMEM
+// (3 x 128 columns of the 512): |lo|,|hi| <= 255^2 K and |mid| <= 2*255^2 K stay below 2^31 for
+// K <= 16512, which covers every K this library produces (dense_block_size, default 1000).
+// The epilogue recombines hi*2^16 + mid*2^8 + lo in 64 bits and Barrett-reduces once.
+//
+// Kernel shape.  One CTA per 128x128 output tile, 6 warps: warp 0 = TMA producer (4 boxes of
+// 128 rows x 128 B per stage, SWIZZLE_128B), warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = epilogue (tcgen05.ld 32x32b, one output row per thread).  3-stage smem ring of
+// 64 KB stages, full/empty mbarriers, tcgen05.commit releases a stage / publishes the accumulator.
+#include <cuda.h>
+
 #include "dense.cuh"
+
 namespace sb {
-bool gemm_nt_mma(uint32_t *, long long, int, int, const uint32_t *, long long, const uint32_t *, long long, int, bool, const Fp &) { return false; }
+
+static constexpr int TILE = 128;   // output tile M = N = 128
+static constexpr int BK = 128;     // bytes (= int8 elements) of K per stage: one 128B swizzle row
+static constexpr int STAGES = 3;
+static constexpr int STAGE_BYTES = 4 * TILE * BK;  // A0 A1 B0 B1
+static constexpr int MMA_THREADS = 192;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// K-major, SWIZZLE_128B operand tile: 8-row atoms of 1024 B (SBO = 1024), LBO unused (1), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::i8, D = s32, A = B = u8, both K-major, M = 128, N = 128
+static constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+
+struct __align__(8) MmaShared {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+template <bool SUB>
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+              const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, uint32_t *__restrict__ C, long long ldc,
+              int M, int N, int nkb, Fp F) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *tiles = (uint8_t *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  MmaShared *sh = (MmaShared *)(tiles + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], 1);
+    }
+    mbar_init(&sh->tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB1) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sh->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&sh->empty[s], ph ^ 1);
+        uint8_t *st = tiles + s * STAGE_BYTES;
+        mbar_expect_tx(&sh->full[s], STAGE_BYTES);
+        tma_load_2d(st + 0 * TILE * BK, &mapA0, kb * BK, m0, &sh->full[s]);
+        tma_load_2d(st + 1 * TILE * BK, &mapA1, kb * BK, m0, &sh->full[s]);
+        tma_load_2d(st + 2 * TILE * BK, &mapB0, kb * BK, n0, &sh->full[s]);
+        tma_load_2d(st + 3 * TILE * BK, &mapB1, kb * BK, n0, &sh->full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&sh->full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = smem_u32(tiles + s * STAGE_BYTES);
+        const uint64_t a0 = make_desc(base), a1 = make_desc(base + TILE * BK), b0 = make_desc(base + 2 * TILE * BK),
+                       b1 = make_desc(base + 3 * TILE * BK);
+#pragma unroll
+        for (int ks = 0; ks < BK / 32; ks++) {
+          const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 32 bytes of K per instruction
+          const uint32_t acc = (kb | ks) ? 1u : 0u;
+          umma_i8(tmem + 0 * TILE, a0 + adv, b0 + adv, IDESC, acc);    // lo
+          umma_i8(tmem + 1 * TILE, a1 + adv, b0 + adv, IDESC, acc);    // mid
+          umma_i8(tmem + 1 * TILE, a0 + adv, b1 + adv, IDESC, 1u);     // mid
+          umma_i8(tmem + 2 * TILE, a1 + adv, b1 + adv, IDESC, acc);    // hi
+        }
+        umma_commit(&sh->empty[s]);  // frees the stage when these MMAs have read it
+      }
+      umma_commit(&sh->tmem_full);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    mbar_wait(&sh->tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t *crow = C + (long long)row * ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TILE; c0 += 16) {
+      uint32_t lo[16], mid[16], hi[16];
+      tmem_ld16(lane_base + 0 * TILE + c0, lo);
+      tmem_ld16(lane_base + 1 * TILE + c0, mid);
+      tmem_ld16(lane_base + 2 * TILE + c0, hi);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int col = n0 + c0 + j;
+          if (col < N) {
+            unsigned long long v = ((unsigned long long)hi[j] << 16) + ((unsigned long long)mid[j] << 8) + lo[j];
+            uint32_t r = red64(v, F);
+            if (SUB) {
+              uint32_t c = crow[col];
+              crow[col] = addmod(c, negmod(r, F), F);
+            } else
+              crow[col] = r;
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ limb split (u32 residues -> two K-major u8 planes, zero padded)
+__global__ void k_split_limbs(const uint32_t *__restrict__ in, long long ld, int rows, int K, uint8_t *__restrict__ lo, uint8_t *__restrict__ hi,
+                              int rows_pad, int Kpad) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one thread per 4 k
+  const int kq = Kpad >> 2;
+  if (idx >= (long long)rows_pad * kq) return;
+  const int r = (int)(idx / kq), k = (int)(idx % kq) * 4;
+  uchar4 l = make_uchar4(0, 0, 0, 0), h = make_uchar4(0, 0, 0, 0);
+  if (r < rows) {
+    const uint32_t *src = in + (long long)r * ld + k;
+    uint32_t v0 = k + 0 < K ? src[0] : 0u, v1 = k + 1 < K ? src[1] : 0u, v2 = k + 2 < K ? src[2] : 0u, v3 = k + 3 < K ? src[3] : 0u;
+    l = make_uchar4(v0 & 255, v1 & 255, v2 & 255, v3 & 255);
+    h = make_uchar4(v0 >> 8, v1 >> 8, v2 >> 8, v3 >> 8);
+  }
+  *(uchar4 *)(lo + (long long)r * Kpad + k) = l;
+  *(uchar4 *)(hi + (long long)r * Kpad + k) = h;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || p == nullptr) throw Error("cuTensorMapEncodeTiled is not available");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static CUtensorMap make_map(uint8_t *base, int rows_pad, int Kpad) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad};
+  cuuint32_t box[2] = {BK, TILE};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+// statistics for the roofline (bench.py): int8 MACs issued and device time spent in the MMA kernel
+double g_mma_ms = 0;
+double g_mma_macs = 0;  // modular MACs (x4 int8 MACs)
+long long g_mma_calls = 0;
+static bool g_mma_disabled = false;
+
+bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
+                 bool subtract, const Fp &F) {
+  if (g_mma_disabled || !F.small) return false;
+  if (K < 64 || K > 16384 || (long long)M * N < 4LL * TILE * TILE) return false;
+  static bool env_checked = false;
+  if (!env_checked) {
+    env_checked = true;
+    if (getenv("SPASM_B200_NO_MMA")) {
+      g_mma_disabled = true;
+      return false;
+    }
+  }
+  cudaStream_t s = stream();
+  const int Mp = (M + TILE - 1) / TILE * TILE, Np = (N + TILE - 1) / TILE * TILE, Kp = (K + BK - 1) / BK * BK;
+  DBuf<uint8_t> a0((size_t)Mp * Kp), a1((size_t)Mp * Kp), b0((size_t)Np * Kp), b1((size_t)Np * Kp);
+  k_split_limbs<<<cdiv((long long)Mp * (Kp >> 2), 256), 256, 0, s>>>(A, lda, M, K, a0.p, a1.p, Mp, Kp);
+  k_split_limbs<<<cdiv((long long)Np * (Kp >> 2), 256), 256, 0, s>>>(B, ldb, N, K, b0.p, b1.p, Np, Kp);
+  CUtensorMap mA0 = make_map(a0.p, Mp, Kp), mA1 = make_map(a1.p, Mp, Kp), mB0 = make_map(b0.p, Np, Kp), mB1 = make_map(b1.p, Np, Kp);
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + sizeof(MmaShared) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_gemm_i8limb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_gemm_i8limb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(Np / TILE, Mp / TILE);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, s));
+  if (subtract)
+    k_gemm_i8limb<true><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, F);
+  else
+    k_gemm_i8limb<false><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, F);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, s));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  g_mma_ms += ms;
+  g_mma_macs += (double)Mp * Np * Kp;
+  g_mma_calls++;
+  return true;
+}
+
 }  // namespace sb
+
+extern "C" void spasm_b200_mma_stats(double *out, int reset) {
+  out[0] = sb::g_mma_ms, out[1] = sb::g_mma_macs, out[2] = (double)sb::g_mma_calls;
+  if (reset) sb::g_mma_ms = sb::g_mma_macs = 0, sb::g_mma_calls = 0;
+}
+
+// test / bench hook: C = [C -] A . B^T mod p on host arrays of residues in [0,p).
+// path 0: as the library would choose; 1: CUDA-core kernel only.  Returns 1 if the tcgen05 kernel ran.
+extern "C" int spasm_b200_gemm_nt_host(long long prime, int M, int N, int K, const unsigned *A, const unsigned *B, unsigned *C, int subtract,
+                                       int path, double *ms_out) {
+  using namespace sb;
+  try {
+    require_gpu();
+    Fp F = make_field(prime);
+    DBuf<uint32_t> dA((size_t)M * K), dB((size_t)N * K), dC((size_t)M * N);
+    dA.upload(A, (size_t)M * K);
+    dB.upload(B, (size_t)N * K);
+    dC.upload(C, (size_t)M * N);
+    const long long calls0 = g_mma_calls;
+    const bool saved = g_mma_disabled;
+    if (path == 1) g_mma_disabled = true;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, stream()));
+    gemm_nt(dC.p, N, M, N, dA.p, K, dB.p, K, K, subtract != 0, F);
+    CK(cudaEventRecord(e1, stream()));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_out) *ms_out = ms;
+    g_mma_disabled = saved;
+    dC.download(C, (size_t)M * N);
+    sync();
+    return g_mma_calls > calls0 ? 1 : 0;
+  } catch (const std::exception &e) {
+    errf("[spasm_b200] gemm test failed: %s\n", e.what());
+    return -1;
+  }
+}

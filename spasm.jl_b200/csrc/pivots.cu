@@ -13,13 +13,9 @@
 //    (reachability is monotone in the pivot set, so the continued closure equals the sequential
 //    one; a row that failed speculatively stays failed).
 //  * reorder: heights in the pivot DAG by relaxation, then a stable sort (normalisation N2).
-#include <cooperative_groups.h>
-
 #include <cub/cub.cuh>
 
 #include "pivots.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace sb {
 
@@ -130,8 +126,10 @@ struct GreedyArgs {
   int *queue;             // [W][qcap]
   int qcap;
   int *surv, *head, *tail;  // [W]
-  int *ctl;                 // [0] cursor  [1] new pivot column (-1: window finished)  [2] row slot of that pivot
+  int *ctl;                 // [0] cursor (rows decided)  [1] pivots published in this window
+  int *newcol;              // [W] columns of the pivots published in this window
   int *npiv;
+  unsigned long long *prof;  // [0] max end-of-speculation time [1] min  [2] commit ns [3] spec ns [4] iterations
 };
 
 __device__ __forceinline__ unsigned mark_state(unsigned short s, unsigned gen) { return ((unsigned)s >> 2) == gen ? (s & 3u) : 0u; }
@@ -161,7 +159,7 @@ __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *mar
     long long a = 0;
     int len = 0;
     if (lane < nb) {
-      const int I = g.qinv[q[head + lane]];
+      const int I = __ldcg(&g.qinv[q[head + lane]]);
       if (I >= 0) {
         a = g.Ap[I];
         len = (int)(g.Ap[I + 1] - a);
@@ -191,7 +189,7 @@ __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *mar
       const long long base = __shfl_sync(0xffffffffu, a, lo);
       if (f < total) {
         jj = g.Aj[base + (f - excl)];
-        const bool piv = g.qinv[jj] >= 0;
+        const bool piv = __ldcg(&g.qinv[jj]) >= 0;
         if (claim(marks, jj, gen, piv ? ST_EXP : ST_SEEN, killed)) push = piv;
       }
       unsigned pm = __ballot_sync(0xffffffffu, push);
@@ -205,28 +203,31 @@ __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *mar
   }
 }
 
-// one cooperative launch per window of rows:
-//   phase 1  every row of the window runs its BFS against the pivots known at window start;
-//   phase 2  commit loop: warp 0 of block 0 takes the first row (in row order) that still has a
-//            surviving candidate — all earlier rows are final — and makes its first surviving entry a
-//            pivot; then every later row that has touched that column continues its BFS from it.
+// one cooperative launch per window, ONE WARP PER ROW, all rows of the window co-resident:
+//   1. every row runs its BFS against the pivots known at window start;
+//   2. rows are then decided strictly in row order.  Pivots committed in this window are published in
+//      an append-only list; every waiting row keeps applying them to its own closure as they appear
+//      (continuing its BFS), so when its turn comes only the last few remain.  A row whose candidates
+//      are all reached is final at once (reachability only grows) and is skipped by the cursor.
+// ctl: [0] cursor (rows decided)   [1] number of pivots published   done[]: row is final
 __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int wn, unsigned gen) {
-  cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int NW = (gridDim.x * blockDim.x) >> 5;
-  for (int t = gw; t < wn; t += NW) {
-    const int i = g.cand[w0 + t];
-    unsigned short *marks = g.marks + (size_t)t * g.m;
-    int *q = g.queue + (size_t)t * g.qcap;
-    int head = 0, tail = 0, surviving = 0;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= wn) return;
+  volatile int *ctl = g.ctl;
+  volatile int *done = g.head;  // reuse: head[] is not needed across warps any more
+  const int i = g.cand[w0 + t];
+  unsigned short *marks = g.marks + (size_t)t * g.m;
+  int *q = g.queue + (size_t)t * g.qcap;
+  int head = 0, tail = 0, surviving = 0;
+  {
     const long long a = g.Ap[i], b = g.Ap[i + 1];
     for (long long e0 = a; e0 < b; e0 += 32) {
       long long e = e0 + lane;
       int push = 0, isc = 0, j = 0;
       if (e < b) {
         j = g.Aj[e];
-        if (g.qinv[j] < 0) {
+        if (__ldcg(&g.qinv[j]) < 0) {
           marks[j] = (unsigned short)((gen << 2) | ST_CAND);
           isc = 1;
         } else {
@@ -241,72 +242,109 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
     }
     __syncwarp();
     bfs_run(g, marks, q, head, tail, surviving, gen, lane);
-    if (lane == 0) g.surv[t] = surviving, g.head[t] = head, g.tail[t] = tail;
   }
-  if (gw == 0 && lane == 0) g.ctl[0] = 0;
-  __threadfence();
-  grid.sync();
+  int applied = 0;
+  unsigned backoff = 32;
   for (;;) {
-    if (gw == 0) {
-      // first row at or after the cursor that still has a surviving candidate
-      int cur = g.ctl[0], found = -1;
-      for (int t0 = cur; t0 < wn && found < 0; t0 += 32) {
-        int t = t0 + lane;
-        unsigned has = __ballot_sync(0xffffffffu, t < wn && ((volatile int *)g.surv)[t] > 0);
-        if (has) found = t0 + (__ffs(has) - 1);
+    if (surviving <= 0) {  // final: no pivot on this row
+      if (lane == 0) {
+        done[t] = 1;
+        __threadfence();
       }
-      int jp = -1;
-      if (found >= 0) {
-        const int i = g.cand[w0 + found];
-        const unsigned short *marks = g.marks + (size_t)found * g.m;
-        const long long a = g.Ap[i], b = g.Ap[i + 1];
-        for (long long e0 = a; e0 < b && jp < 0; e0 += 32) {
-          long long e = e0 + lane;
-          int j = e < b ? g.Aj[e] : -1;
-          unsigned c = __ballot_sync(0xffffffffu, j >= 0 && mark_state(((volatile unsigned short *)marks)[j], gen) == ST_CAND);
-          if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
-        }
+      // the cursor may be waiting on us
+      int cur = 0;
+      if (lane == 0) cur = ctl[0];
+      cur = __shfl_sync(0xffffffffu, cur, 0);
+      if (cur != t) return;
+      // fall through to advance the cursor below
+    }
+    int cur = 0, nn = 0;
+    if (lane == 0) {
+      cur = ctl[0];
+      __threadfence();  // the pivot count is read AFTER the cursor: if it is our turn the count is final
+      nn = ctl[1];
+    }
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    nn = __shfl_sync(0xffffffffu, nn, 0);
+    if (surviving > 0 && applied < nn) {
+      // apply the pivots published since last time
+      for (; applied < nn && surviving > 0; applied++) {
+        const int jc = __ldcg(&g.newcol[applied]);
+        const unsigned st = mark_state(marks[jc], gen);
+        if (st != ST_CAND && st != ST_SEEN) continue;
+        if (st == ST_CAND) surviving--;
+        __syncwarp();
         if (lane == 0) {
-          g.pinv[i] = jp;
-          g.qinv[jp] = i;
-          g.surv[found] = 0;
-          atomicAdd(g.npiv, 1);
+          marks[jc] = (unsigned short)((gen << 2) | ST_EXP);
+          q[tail] = jc;
         }
+        tail++;
+        __syncwarp();
+        bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+      }
+      backoff = 32;
+      continue;  // re-read the control words
+    }
+    if (cur != t) {
+      __nanosleep(backoff);
+      if (backoff < 1024) backoff <<= 1;
+      continue;
+    }
+    // ---- my turn: every earlier row is final and all their pivots are applied (nn is final too,
+    // because only the row at the cursor can publish)
+    int nn_now = nn;
+    if (surviving > 0) {
+      const long long a = g.Ap[i], b = g.Ap[i + 1];
+      int jp = -1;
+      for (long long e0 = a; e0 < b && jp < 0; e0 += 32) {
+        long long e = e0 + lane;
+        int j = e < b ? g.Aj[e] : -1;
+        unsigned c = __ballot_sync(0xffffffffu, j >= 0 && mark_state(marks[j], gen) == ST_CAND);
+        if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
       }
       if (lane == 0) {
-        g.ctl[0] = found >= 0 ? found + 1 : wn;
-        g.ctl[1] = jp;
+        g.pinv[i] = jp;
+        g.qinv[jp] = i;
+        g.newcol[nn] = jp;
+        atomicAdd(g.npiv, 1);
+        __threadfence();
+        ctl[1] = nn + 1;
+        done[t] = 1;
+        __threadfence();
       }
-      __threadfence();
+      nn_now = nn + 1;
     }
-    grid.sync();
-    const int jp = ((volatile int *)g.ctl)[1];
-    if (jp < 0) break;
-    const int cursor = ((volatile int *)g.ctl)[0];
-    // rows after the committed one that have touched column jp continue their BFS through its row
-    int t = gw;
-    if (t < cursor) t += ((cursor - t + NW - 1) / NW) * NW;
-    for (; t < wn; t += NW) {
-      int surviving = g.surv[t];
-      if (surviving <= 0) continue;
-      unsigned short *marks = g.marks + (size_t)t * g.m;
-      const unsigned st = mark_state(marks[jp], gen);
-      if (st != ST_CAND && st != ST_SEEN) continue;
-      int *q = g.queue + (size_t)t * g.qcap;
-      int head = g.head[t], tail = g.tail[t];
-      if (st == ST_CAND) surviving--;
-      __syncwarp();
+    (void)nn_now;
+    // advance the cursor over every following row that is already final.  atomicMax keeps it
+    // monotone when a row that just became final advances it concurrently; the re-check after the
+    // fence closes the missed-wakeup window (that row does store-done / fence / load-cursor).
+    int nxt = t + 1;
+    for (;;) {
+      for (;;) {
+        int tt = nxt + lane;
+        unsigned fin = __ballot_sync(0xffffffffu, tt < wn && done[tt] != 0);
+        int run = (fin == 0xffffffffu) ? 32 : __ffs(~fin) - 1;
+        nxt += run;
+        if (run < 32 || nxt >= wn) break;
+      }
+      if (nxt > wn) nxt = wn;
+      int cur2 = 0;
       if (lane == 0) {
-        marks[jp] = (unsigned short)((gen << 2) | ST_EXP);
-        q[tail] = jp;
+        __threadfence();
+        int old = atomicMax(g.ctl, nxt);
+        cur2 = old > nxt ? old : nxt;
+        __threadfence();
       }
-      tail++;
-      __syncwarp();
-      bfs_run(g, marks, q, head, tail, surviving, gen, lane);
-      if (lane == 0) g.surv[t] = surviving, g.head[t] = head, g.tail[t] = tail;
+      cur2 = __shfl_sync(0xffffffffu, cur2, 0);
+      if (cur2 >= wn) break;
+      int d = 0;
+      if (lane == 0) d = done[cur2];
+      d = __shfl_sync(0xffffffffu, d, 0);
+      if (!d) break;
+      nxt = cur2;
     }
-    __threadfence();
-    grid.sync();
+    // a row that became final between our scan and the store re-checks the cursor itself (top of loop)
+    return;
   }
 }
 
@@ -453,15 +491,20 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
       int W = (int)std::max<size_t>(32, std::min<size_t>((size_t)grid * 8, budget / per));
       W = std::min(W, ncand);
       DBuf<unsigned short> marks((size_t)W * m);
-      DBuf<int> queue((size_t)W * qcap), surv(W), head(W), tail(W), ctl(4);
+      DBuf<int> queue((size_t)W * qcap), surv(W), head(W), tail(W), ctl(4), newcol(W);
       marks.zero();
       ctr.zero();
-      GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, queue.p, qcap, surv.p, head.p, tail.p, ctl.p, ctr.p};
+      DBuf<unsigned long long> prof(8);
+      prof.zero();
+      CK(cudaMemsetAsync(prof.p + 1, 0xff, 8, s));
+      GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, queue.p, qcap, surv.p, head.p, tail.p, ctl.p, newcol.p, ctr.p, prof.p};
       unsigned gen = 1;
       for (int w0 = 0; w0 < ncand; w0 += W) {
         int wn = std::min(W, ncand - w0);
+        ctl.zero();
+        head.zero();
         void *args[] = {&g, &w0, &wn, &gen};
-        CK(cudaLaunchCooperativeKernel((void *)k_greedy_window, dim3(grid), dim3(256), args, 0, s));
+        CK(cudaLaunchCooperativeKernel((void *)k_greedy_window, dim3(cdiv((long long)wn * 32, 256)), dim3(256), args, 0, s));
         gen++;
         P.greedy_windows++;
         if (gen == (1u << 14)) {
@@ -470,6 +513,14 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
         }
       }
       CK(cudaGetLastError());
+      {
+        unsigned long long hp[8];
+        prof.download(hp, 8);
+        sync();
+        if (getenv("SPASM_B200_PROFILE"))
+          fprintf(stderr, "[greedy] windows=%d W=%d grid=%d spec(warp0+wait)=%.3fs spec spread(last window)=%.3fs commit=%.3fs iterations=%llu\n",
+                  P.greedy_windows, W, grid, hp[3] * 1e-9, (hp[0] - hp[1]) * 1e-9, hp[2] * 1e-9, hp[4]);
+      }
       counts[2] = fetch(ctr.p);
     }
   }
