@@ -138,7 +138,7 @@ struct DBuf {
   void download(T *h, size_t cnt) const { CK(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, stream())); }
   void grow(size_t need) {  // keep contents
     if (need <= n) return;
-    size_t nn = need + need / 2 + 1024;
+    size_t nn = (need > ((size_t)1 << 28)) ? need + need / 8 : need + need / 2 + 1024;
     T *q = (T *)dmalloc_bytes(nn * sizeof(T));
     if (p) {
       CK(cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, stream()));
@@ -168,6 +168,8 @@ struct DCsr {
 void upload_csr(const spasm_csr *A, DCsr &D, const Fp &F);          // balanced -> u32
 spasm_csr *download_csr(const DCsr &D, int64_t prime, const Fp &F); // u32 -> balanced, malloc'd host CSR
 void convert_to_balanced(const uint32_t *in, int *out, long long n, const Fp &F);
+// device -> pageable host through pinned bounce buffers, pages touched by all host threads
+void download_large(void *dst, const void *src_dev, size_t bytes);
 void convert_to_residues(const int *in, uint32_t *out, long long n, const Fp &F);
 
 // exclusive scan helpers (cub underneath; scan.cu)

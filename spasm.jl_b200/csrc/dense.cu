@@ -288,28 +288,34 @@ void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long l
 // scanned left to right in tiles; for each tile  W = T.Panel_tile  (GEMM), one CTA runs
 // Gauss-Jordan on W among the rows that are not pivots yet (at most 32 new pivots per tile) while
 // recording the operations as the columns Gc of the update  T <- G.T.
+static constexpr int PB = 32;   // pivots per tile call (number of recorded operation columns Gc)
+static constexpr int WMAX = 2048;
 struct PanelCtl {
   int npiv;      // pivots found so far in this panel
   int found;     // pivots found in the last tile
   int consumed;  // columns consumed by the last tile
   int pad;
 };
+// Gauss-Jordan on one tile.  The tile is stored COLUMN-major (Wt[c][r], r contiguous) and every
+// thread owns rows r = tid, tid+1024, ...: finding the pivot is one coalesced pass over a column,
+// eliminating it is wc-cc independent coalesced read-modify-writes per thread (no dependent chains).
+// The recorded operations Gc[s][r] (column s = s-th pivot of this call) define T <- G.T.
 template <bool SMALL>
-__global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ W, int Sn, int wc, long long ldw, int c0,
+__global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, int Sn, int wc, long long ldw, int c0,
                                                       int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
                                                       uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl, Fp F) {
   __shared__ int red[32];
   __shared__ int s_piv;
-  __shared__ uint32_t s_alpha;
+  __shared__ uint32_t prow[WMAX], gprow[PB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int npiv = ctl->npiv, found = 0, cc = 0;
-  for (int idx = tid; idx < Sn * 32; idx += 1024) Gc[idx] = 0;
+  for (long long idx = tid; idx < (long long)PB * ldw; idx += 1024) Gc[idx] = 0;
   __syncthreads();
-  for (; cc < wc && found < 32 && npiv < Sn; cc++) {
-    // first row that is not a pivot yet and is nonzero on column cc
+  for (; cc < wc && found < PB && npiv < Sn; cc++) {
     int best = 0x7fffffff;
+    const uint32_t *col = Wt + (long long)cc * ldw;
     for (int r = tid; r < Sn; r += 1024)
-      if (!ispiv[r] && W[(long long)r * ldw + cc] != 0) {
+      if (!ispiv[r] && col[r] != 0) {
         best = r;
         break;
       }
@@ -320,33 +326,42 @@ __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ W, i
       for (int i = 1; i < 32; i++) best = min(best, red[i]);
       s_piv = best;
       if (best != 0x7fffffff) {
-        s_alpha = dev_inv(W[(long long)best * ldw + cc], F.p);
         ispiv[best] = 1;
         pivrow[npiv] = best;
         pivcol[npiv] = c0 + cc;
         tilepiv[found] = best;
-        Gc[best * 32 + found] = 1;
+        Gc[(long long)found * ldw + best] = 1;
       }
     }
     __syncthreads();
     const int pr = s_piv;
     if (pr == 0x7fffffff) continue;
-    const uint32_t alpha = s_alpha;
-    // scale the pivot row of [W | Gc]
-    uint32_t *Wp = W + (long long)pr * ldw;
-    for (int k = cc + tid; k < wc; k += 1024) Wp[k] = mulmod<SMALL>(alpha, Wp[k], F);
-    if (tid <= found) Gc[pr * 32 + tid] = mulmod<SMALL>(alpha, Gc[pr * 32 + tid], F);
+    // the scaled pivot row goes to shared memory (and back to the tile)
+    const uint32_t alpha = dev_inv(Wt[(long long)cc * ldw + pr], F.p);
+    for (int k = cc + tid; k < wc; k += 1024) {
+      uint32_t v = mulmod<SMALL>(alpha, Wt[(long long)k * ldw + pr], F);
+      prow[k] = v;
+      Wt[(long long)k * ldw + pr] = v;
+    }
+    if (tid <= found) {
+      uint32_t v = mulmod<SMALL>(alpha, Gc[(long long)tid * ldw + pr], F);
+      gprow[tid] = v;
+      Gc[(long long)tid * ldw + pr] = v;
+    }
     __syncthreads();
-    // eliminate column cc from every other row: warp per row
-    for (int r = wid; r < Sn; r += 32) {
+    for (int r = tid; r < Sn; r += 1024) {
       if (r == pr) continue;
-      uint32_t *Wr = W + (long long)r * ldw;
-      const uint32_t f = Wr[cc];
+      const uint32_t f = Wt[(long long)cc * ldw + r];
       if (f == 0) continue;
       const uint32_t nf = negmod(f, F);
-      __syncwarp();
-      for (int k = cc + lane; k < wc; k += 32) Wr[k] = addmod(Wr[k], mulmod<SMALL>(nf, Wp[k], F), F);
-      if (lane <= found) Gc[r * 32 + lane] = addmod(Gc[r * 32 + lane], mulmod<SMALL>(nf, Gc[pr * 32 + lane], F), F);
+      for (int k = cc; k < wc; k++) {
+        uint32_t *w = Wt + (long long)k * ldw + r;
+        *w = addmod(*w, mulmod<SMALL>(nf, prow[k], F), F);
+      }
+      for (int c = 0; c <= found; c++) {
+        uint32_t *gp = Gc + (long long)c * ldw + r;
+        *gp = addmod(*gp, mulmod<SMALL>(nf, gprow[c], F), F);
+      }
     }
     found++;
     npiv++;
@@ -368,17 +383,22 @@ __global__ void k_gather_T_rows(const uint32_t *__restrict__ T, int Sn, const in
 }
 // T[r][:] = (r is a pivot of this tile ? 0 : T[r][:]) + sum_s Gc[r][s] * Tp[s][:]
 template <bool SMALL>
-__global__ void k_update_T(uint32_t *__restrict__ T, int Sn, const uint32_t *__restrict__ Gc, const uint32_t *__restrict__ Tp,
+__global__ void k_update_T(uint32_t *__restrict__ T, int Sn, const uint32_t *__restrict__ Gc, long long ldg, const uint32_t *__restrict__ Tp,
                            const int *__restrict__ tilepiv, const PanelCtl *__restrict__ ctl, Fp F) {
   const int found = ctl->found;
   if (found == 0) return;
   const int r = blockIdx.y, col = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_isp;
+  if (threadIdx.x == 0) {
+    int f = 0;
+    for (int s = 0; s < found; s++) f |= (tilepiv[s] == r);
+    s_isp = f;
+  }
+  __syncthreads();
   if (col >= Sn) return;
-  bool isp = false;
-  for (int s = 0; s < found; s++) isp |= (tilepiv[s] == r);
-  unsigned long long acc = isp ? 0ull : T[(long long)r * Sn + col];
+  unsigned long long acc = s_isp ? 0ull : T[(long long)r * Sn + col];
   for (int s = 0; s < found; s++) {
-    const uint32_t g = Gc[r * 32 + s];
+    const uint32_t g = Gc[(long long)s * ldg + r];
     if (g == 0) continue;
     if (SMALL)
       acc += (unsigned long long)(g * Tp[(long long)s * Sn + col]);
@@ -425,9 +445,9 @@ __global__ void k_iota2(int *a, int n) {
 static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0, int Sn, uint32_t *T, DBuf<int> &ispiv, DBuf<int> &pivrow,
                         DBuf<int> &pivcol, const Fp &F) {
   cudaStream_t s = stream();
-  const int WMAX = 2048;
-  DBuf<uint32_t> W((size_t)Sn * WMAX), Gc((size_t)Sn * 32), Tp((size_t)32 * Sn);
-  DBuf<int> tilepiv(32);
+  const long long ldw = ((long long)Sn + 31) / 32 * 32;
+  DBuf<uint32_t> Wt((size_t)WMAX * ldw), Gc((size_t)PB * ldw), Tp((size_t)PB * Sn);
+  DBuf<int> tilepiv(PB);
   DBuf<PanelCtl> ctl(1);
   ctl.zero();
   ispiv.alloc(Sn);
@@ -438,28 +458,28 @@ static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0,
   int w = 32, npiv = 0;
   for (int c0 = 0; c0 < Sm0 && npiv < Sn;) {
     const int wc = std::min(w, Sm0 - c0);
-    // W = T . Panel_tile
-    gemm_nt(W.p, wc, Sn, wc, T, Sn, Dt + (long long)c0 * ld + k0, ld, Sn, false, F);
+    // Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]     (the tile of T.Panel, transposed)
+    gemm_nt(Wt.p, ldw, wc, Sn, Dt + (long long)c0 * ld + k0, ld, T, Sn, Sn, false, F);
     if (F.small)
-      k_tile_gauss<true><<<1, 1024, 0, s>>>(W.p, Sn, wc, wc, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
+      k_tile_gauss<true><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
     else
-      k_tile_gauss<false><<<1, 1024, 0, s>>>(W.p, Sn, wc, wc, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
-    k_gather_T_rows<<<dim3(cdiv(Sn, 256), 32), 256, 0, s>>>(T, Sn, tilepiv.p, &ctl.p->found, 0, Tp.p);
+      k_tile_gauss<false><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
+    k_gather_T_rows<<<dim3(cdiv(Sn, 256), PB), 256, 0, s>>>(T, Sn, tilepiv.p, &ctl.p->found, 0, Tp.p);
     if (F.small)
-      k_update_T<true><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, Tp.p, tilepiv.p, ctl.p, F);
+      k_update_T<true><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, ldw, Tp.p, tilepiv.p, ctl.p, F);
     else
-      k_update_T<false><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, Tp.p, tilepiv.p, ctl.p, F);
+      k_update_T<false><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, ldw, Tp.p, tilepiv.p, ctl.p, F);
     CK(cudaGetLastError());
     PanelCtl h = fetch(ctl.p);
     npiv = h.npiv;
     c0 += h.consumed;
     // adapt the tile width to the pivot density just seen
-    if (h.found >= 16)
+    if (h.found >= PB / 2)
       w = 32;
     else if (h.found == 0)
       w = std::min(WMAX, w * 4);
     else
-      w = std::min(WMAX, std::max(32, (int)(32.0 * h.consumed / h.found)));
+      w = std::min(WMAX, std::max(32, (int)((double)PB * h.consumed / h.found)));
   }
   return npiv;
 }
@@ -474,6 +494,25 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
   const int Sm0 = D.Sm0;
   const long long ld = D.ld;
   logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)\n", nrows, Sm0, spasm_wtime() - t0, D.levels);
+  const bool prof = getenv("SPASM_B200_PROFILE") != nullptr;
+  double tp[6] = {0, 0, 0, 0, 0, 0};  // panel, R gemm, emit, gather/transposes, trailing gemm, blocks
+  auto tick = [&](int slot, double &t1) {
+    if (!prof) return;
+    sync();
+    double now = spasm_wtime();
+    tp[slot] += now - t1;
+    t1 = now;
+  };
+  {
+    // upper bound of what the dense rows add to U (every block full rank): reserve once, no regrowth copies
+    long long ub = 0, left = Sm0;
+    for (long long k0 = 0; k0 < nrows && left > 0; k0 += block_size) {
+      long long sn = std::min<long long>(block_size, nrows - k0), rr = std::min(sn, left);
+      ub += rr * left;
+      left -= rr;
+    }
+    if ((size_t)ub * 8 < dev_free_bytes() / 2) csr_reserve(U, U.nnz + ub, U.n + std::min(nrows, Sm0));
+  }
   const int Bmax = std::min(block_size, nrows);
   DBuf<uint32_t> T((size_t)Bmax * Bmax), Tsel((size_t)Bmax * Bmax), R((size_t)Bmax * Sm0), Rt, Pt;
   DBuf<int> ispiv, pivrow, pivcol, ident(Bmax);
@@ -482,11 +521,15 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
     const int Sn = (int)std::min<long long>(block_size, nrows - k0);
     logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - k0, A.m - U.n,
          block_size);
+    double t1 = spasm_wtime();
     const int rr = panel_factor(D.Dt.p, ld, Sm0, k0, Sn, T.p, ispiv, pivrow, pivcol, F);
+    tick(0, t1);
+    tp[5] += 1;
     if (rr > 0) {
       // reduced rows  R[s][c] = sum_t T[pivrow[s]][t] * Dt[c][k0+t]
       k_gather_T_rows<<<dim3(cdiv(Sn, 256), rr), 256, 0, s>>>(T.p, Sn, pivrow.p, nullptr, rr, Tsel.p);
       gemm_nt(R.p, Sm0, rr, Sm0, Tsel.p, Sn, D.Dt.p + k0, ld, Sn, false, F);
+      tick(1, t1);
       // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
       DBuf<int> cnt(rr + 1);
       DBuf<long long> rpos(rr + 1);
@@ -498,6 +541,7 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
       CK(cudaGetLastError());
       U.nnz += add;
       U.n += rr;
+      tick(2, t1);
       // trailing update of the later rows:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
       const long long kb = k0 + Sn;
       const int nk = (int)(nrows - kb);
@@ -507,12 +551,16 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
         Pt.alloc((size_t)nk * ldk);
         k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
         k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt.p, ldk);
+        tick(3, t1);
         gemm_nt(D.Dt.p + kb, ld, Sm0, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F);
+        tick(4, t1);
       }
     }
     logf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U.n);
     if (U.n == A.m) break;
   }
+  if (prof)
+    fprintf(stderr, "[dense] blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs trailing=%.3fs\n", (int)tp[5], tp[0], tp[1], tp[2], tp[3], tp[4]);
 }
 
 }  // namespace sb

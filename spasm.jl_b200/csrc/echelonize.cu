@@ -79,6 +79,13 @@ __global__ void k_gather_idx(const int *__restrict__ src, const int *__restrict_
   if (i < n) out[i] = src[idx[i]];
 }
 
+__global__ void k_count_nonzero(const uint32_t *__restrict__ a, long long n, unsigned long long *__restrict__ out) {
+  unsigned long long c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += (a[i] != 0);
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 static double estimate_density(Echelon &E, const DCsr &cur, const int *rows_dev, int nrows, int R_) {
   if (nrows == 0 || E.m == E.U.n) return 0;
   std::vector<int> idx(R_);
@@ -86,15 +93,17 @@ static double estimate_density(Echelon &E, const DCsr &cur, const int *rows_dev,
   DBuf<int> didx(R_), sample(R_);
   didx.upload(idx.data(), R_);
   k_gather_idx<<<cdiv(R_, 128), 128, 0, stream()>>>(rows_dev, didx.p, R_, sample.p);
-  DBuf<PDesc> pdesc;
-  build_pdesc_U(E.U, E.Uqinv.p, pdesc);
-  SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, E.m};
-  SolveRows B{cur.p.p, cur.j.p, cur.x.p, sample.p, R_, nullptr};
-  SolveEmit Em;
-  Em.count_only = true;
-  SolveResult R;
-  solve_rows(G, B, Em, E.F, R);
-  return ((double)R.nnz) / (E.m - E.U.n) / R_;
+  // the sampled rows go through the dense engine (R_ right-hand sides at once): in the dense regime
+  // each of them reaches most pivots, which is the worst case of the row-at-a-time engine
+  DenseSchur D;
+  build_dense_schur(cur, sample.p, R_, E.U, E.Uqinv.p, E.F, D);
+  DBuf<unsigned long long> cnt(1);
+  cnt.zero();
+  const long long tot = (long long)D.Sm0 * D.ld;
+  k_count_nonzero<<<std::min<long long>(cdiv(tot, 256), 4096), 256, 0, stream()>>>(D.Dt.p, tot, cnt.p);
+  CK(cudaGetLastError());
+  const unsigned long long nz = fetch(cnt.p);
+  return ((double)nz) / (E.m - E.U.n) / R_;
 }
 
 static void add_L_entries(Echelon &E, const SolveResult &R, const std::vector<int> &orig_rows) {
@@ -393,10 +402,10 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
     spasm_csr *Uh = spasm_csr_alloc(E.U.n, m, E.U.nnz, prime, true);
     CK(cudaMemcpyAsync(Uh->p, E.U.p.p, (size_t)(E.U.n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream()));
     if (E.U.nnz) {
-      CK(cudaMemcpyAsync(Uh->j, E.U.j.p, (size_t)E.U.nnz * sizeof(int), cudaMemcpyDeviceToHost, stream()));
-      DBuf<int> bal(E.U.nnz);
-      convert_to_balanced(E.U.x.p, bal.p, E.U.nnz, E.F);
-      CK(cudaMemcpyAsync(Uh->x, bal.p, (size_t)E.U.nnz * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+      download_large(Uh->j, E.U.j.p, (size_t)E.U.nnz * sizeof(int));
+      // balanced representatives are produced in place (the device copy of U is dropped afterwards)
+      convert_to_balanced(E.U.x.p, (int *)E.U.x.p, E.U.nnz, E.F);
+      download_large(Uh->x, E.U.x.p, (size_t)E.U.nnz * sizeof(int));
     }
     fact->U = Uh;
   }

@@ -1,4 +1,7 @@
 // runtime.cu — device runtime: stream, stream-ordered memory, scans, CSR up/download, transpose.
+#include <omp.h>
+
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -75,12 +78,52 @@ long long reduce_sum_i32(const int *in, size_t n) {
   return fetch(out.p);
 }
 
+// ------------------------------------------------------------------ large device -> host copies
+// malloc'd destinations are pageable and mostly untouched: a plain cudaMemcpy runs at ~2 GB/s
+// (page faults on one thread).  Bounce through two pinned buffers and let every host thread fault
+// and fill its slice of the destination.
+void download_large(void *dst, const void *src_dev, size_t bytes) {
+  const size_t CH = (size_t)128 << 20;
+  if (bytes < CH / 2) {
+    CK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, g_stream));
+    sync();
+    return;
+  }
+  static void *pin[2] = {nullptr, nullptr};
+  static cudaEvent_t ev[2];
+  if (!pin[0]) {
+    for (int i = 0; i < 2; i++) {
+      CK(cudaHostAlloc(&pin[i], CH, cudaHostAllocDefault));
+      CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t nch = (bytes + CH - 1) / CH;
+  auto issue = [&](size_t c) {
+    size_t off = c * CH, len = std::min(CH, bytes - off);
+    CK(cudaMemcpyAsync(pin[c & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaEventRecord(ev[c & 1], g_stream));
+  };
+  issue(0);
+  for (size_t c = 0; c < nch; c++) {
+    if (c + 1 < nch) issue(c + 1);
+    CK(cudaEventSynchronize(ev[c & 1]));
+    const size_t off = c * CH, len = std::min(CH, bytes - off);
+    char *d = (char *)dst + off;
+    const char *srcp = (const char *)pin[c & 1];
+#pragma omp parallel for schedule(static)
+    for (long long b = 0; b < (long long)((len + (1 << 20) - 1) >> 20); b++) {
+      size_t o = (size_t)b << 20, l = std::min((size_t)1 << 20, len - o);
+      memcpy(d + o, srcp + o, l);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ CSR transfer
 __global__ void k_to_u(const int *__restrict__ in, uint32_t *__restrict__ out, long long n, Fp F) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) out[i] = to_u(in[i], F);
 }
-__global__ void k_to_bal(const uint32_t *__restrict__ in, int *__restrict__ out, long long n, Fp F) {
+__global__ void k_to_bal(const uint32_t *in, int *out, long long n, Fp F) {  // in == out allowed
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) out[i] = to_bal(in[i], F);
 }

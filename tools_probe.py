@@ -33,6 +33,8 @@ def run(tag, n, m, p, j, x, prime=42013, kernel=False, **kw):
 
 for arg in sys.argv[1:]:
     kind, _, size = arg.partition(":")
+    if kind == "gemm":
+        continue
     s = int(size)
     if kind == "c1":
         run(arg, s, s, *synth.random_rows(s, s, 5, 42013, 0x5A5A0001), kernel=True)
@@ -46,3 +48,31 @@ for arg in sys.argv[1:]:
     elif kind == "c5":
         n, m = 500000 // s, 1000000 // s
         run(arg, n, m, *synth.random_rows(n, m, 8, 42013, 0x5A5A0005), kernel=(s >= 50))
+
+def gemm_bench(M, N, K, prime=42013):
+    f = g.lib.spasm_b200_gemm_nt_host
+    f.restype = C.c_int
+    f.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    rng = np.random.default_rng(1)
+    A = rng.integers(0, prime, size=(M, K), dtype=np.uint32)
+    B = rng.integers(0, prime, size=(N, K), dtype=np.uint32)
+    Cm = rng.integers(0, prime, size=(M, N), dtype=np.uint32)
+    st = (C.c_double * 3)()
+    g.lib.spasm_b200_mma_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
+    for path in (0, 1):
+        best = 1e9
+        for rep in range(3):
+            ms = C.c_double(0)
+            g.lib.spasm_b200_mma_stats(st, 1)
+            used = f(prime, M, N, K, A.ctypes.data, B.ctypes.data, Cm.ctypes.data, 1, path, C.byref(ms))
+            g.lib.spasm_b200_mma_stats(st, 0)
+            kms = st[0] if used else ms.value
+            best = min(best, kms)
+        macs = M * N * K
+        print(f"== gemm {M}x{N}x{K} path={'tcgen05' if used else 'cuda-core'}: kernel {best:.3f} ms  {macs/best/1e9:.1f} G modular MAC/s"
+              + (f"  = {8*macs/best/1e9:.0f} T int8 OP/s" if used else ""), flush=True)
+
+
+for arg in sys.argv[1:]:
+    if arg.startswith("gemm:"):
+        gemm_bench(*map(int, arg[5:].split(",")))
