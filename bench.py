@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — echelonize time-to-rank (s) on BASELINE.json configs[1]:
+synthetic 200 000 x 200 000, 10 nnz/row, echelonize + rank mod 42013, on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # CPU oracle restatement of libspasm, all host threads
+
+One "step" is one complete echelonization of the matrix (structural pivots -> dense Schur
+complement -> blocked RREF on the tcgen05 tensor cores).  `value` is the time with the input CSR
+already resident in HBM and the factor left on the device; `e2e` is the same call through the
+reference-facing C ABI (`spasm_echelonize` on host structs: CSR upload and the whole factor U
+downloaded into malloc'd host arrays inside the timed region).
+
+The real reference (SpaSM.jl -> libspasm) cannot run here or on the GPU box (no Julia, no libspasm
+sources): the CPU arm is the oracle restatement in oracle/, on a bounded sample of the same
+generator (the full 200k case needs ~1e15 scalar modular operations on a CPU).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
+
+PRIME = 42013
+FULL_N = 200_000
+NNZ_ROW = 10
+SEED = 0x5A5A0002
+CPU_SAMPLE_N = 3000  # ~10 s of oracle work with 8 threads
+TIMING_NAMES = "total upload FL FLcol greedy reorder_extract density schur tail download rounds flcol_rounds greedy_windows schur_bytes schur_macs schur_ms".split()
+
+
+def measured_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_input(n):
+    import synth
+
+    return synth.random_rows(n, n, NNZ_ROW, PRIME, SEED)
+
+
+def csr_bytes(n, nnz):
+    return 8 * (n + 1) + 8 * nnz
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement of libspasm (oracle/), all host threads, bounded sample."""
+    import __graft_entry__ as entry
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = entry.load_package()
+    ora = pkg.SpaSM(entry.build_oracle())
+    n = args.rows or CPU_SAMPLE_N
+    p, j, x = make_input(n)
+    A = ora.from_arrays(n, n, p, j, x, PRIME)
+    cores = ora.lib.spasm_get_num_threads()
+    for _ in range(args.warmup if args.warmup is not None else 0):
+        ora.echelonize(A)
+    times = []
+    K = args.steps or 1
+    r = None
+    for _ in range(K):
+        t = time.perf_counter()
+        f = ora.echelonize(A)
+        times.append(time.perf_counter() - t)
+        r = f.r
+        del f
+    val = sum(times) / len(times)
+    line = {
+        "impl": "reference",
+        "metric": "echelonize_time_to_rank", "value": val, "unit": "s", "n_gpus": 0, "steps": K, "warmup": args.warmup or 0,
+        "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "int32 residues mod p (i64 products)",
+        "data": "synthetic",
+        "config": {"workload": f"random sparse {FULL_N}x{FULL_N}, {NNZ_ROW} nnz/row, echelonize+rank mod {PRIME} (BASELINE configs[1])",
+                   "sample": f"same generator at n={n} ({n}x{n}); the value is the time of this SAMPLE, not of the full matrix"},
+        "cpu_baseline": {"value": val, "unit": "s", "cores": int(cores), "kind": "port",
+                         "sample": f"oracle restatement of libspasm, {cores} cores, {n}x{n} instance of the same generator (rank {r})"},
+        "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import __graft_entry__ as entry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = entry.load_package()
+    gpu = pkg.SpaSM()
+    if not os.environ.get("SPASM_B200_VERBOSE"):
+        gpu.log(False)  # progress text off (errors still reach stderr)
+    lib = gpu.lib
+    lib.spasm_b200_upload.restype = C.c_void_p
+    lib.spasm_b200_upload.argtypes = [C.c_void_p]
+    lib.spasm_b200_echelonize_resident.restype = C.c_int
+    lib.spasm_b200_echelonize_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    lib.spasm_b200_release.argtypes = [C.c_void_p]
+    lib.spasm_b200_last_timings.argtypes = [C.POINTER(C.c_double)]
+    lib.spasm_b200_mma_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
+
+    n = args.rows or FULL_N
+    p, j, x = make_input(n)
+    A = gpu.from_arrays(n, n, p, j, x, PRIME)
+    nnz = int(p[-1])
+    opts = gpu.EchelonizeOpts()
+    handle = lib.spasm_b200_upload(C.cast(A.data, C.c_void_p))
+    assert handle, "upload failed"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        flush.zero_()
+        torch.cuda.synchronize()
+        ms = C.c_double(0)
+        r = lib.spasm_b200_echelonize_resident(handle, C.byref(opts), C.byref(ms))
+        assert r >= 0, "echelonize failed (see stderr)"
+        return r, ms.value
+
+    W = 3 if args.warmup is None else args.warmup
+    K = args.steps or 3
+    for _ in range(W):
+        resident_step()
+    st = (C.c_double * 4)()
+    lib.spasm_b200_mma_stats(st, 1)
+    barrier()
+    t_wall = time.perf_counter()
+    dev_ms, ranks_seen = [], set()
+    with ClockSampler(local) as clk:
+        for _ in range(K):
+            r, ms = resident_step()
+            dev_ms.append(ms)
+            ranks_seen.add(r)
+        barrier()
+    wall = time.perf_counter() - t_wall
+    lib.spasm_b200_mma_stats(st, 0)
+    mma_ms, mma_macs, mma_calls, launches = st[0], st[1], st[2], st[3]
+    T = (C.c_double * 16)()
+    lib.spasm_b200_last_timings(T)
+    phases = {k: round(v, 6) for k, v in zip(TIMING_NAMES, T)}
+    my = sum(dev_ms) / len(dev_ms) / 1e3
+    if dist is not None:
+        t = torch.tensor([my], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        my = float(t.item())
+    assert len(ranks_seen) == 1
+    rank_found = ranks_seen.pop()
+
+    # ---- end to end through the C ABI on host structs (upload + download of the factor inside)
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    lu = gpu.echelonize(A)  # warm-up (page cache of the host allocator, pinned bounce buffers)
+    u_nnz = lu.U.nnz()
+    assert lu.r == rank_found
+    del lu
+    barrier()
+    e2e_t = []
+    for _ in range(e2e_steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        lu = gpu.echelonize(A)
+        rk = lu.r  # the device->host read of the step's result
+        e2e_t.append(time.perf_counter() - t)
+        assert rk == rank_found
+        del lu
+    e2e = sum(e2e_t) / len(e2e_t)
+    if dist is not None:
+        t = torch.tensor([e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = float(t.item())
+    lib.spasm_b200_release(handle)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    hbm_gbs, bf16_sust, src = measured_peaks()
+    # dominant kernel of this workload: k_gemm_i8limb (tcgen05.mma.kind::i8 -> SASS UTCIMMA), timed with
+    # CUDA events on the launching stream inside the library.  4 int8 MACs per modular MAC, 2 ops per MAC.
+    achieved = (8.0 * mma_macs / (mma_ms * 1e-3) / 1e12) if mma_ms > 0 else None
+    peak = 2.0 * bf16_sust  # dense int8 = 2x bf16 on sm_100; no measured int8 figure on this pool
+    roofline = {
+        "kernel": "k_gemm_i8limb (tcgen05.mma.kind::i8, SASS UTCIMMA; TMA-fed, TMEM accumulators)",
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "peak_source": f"2 x bf16_tflops_sustained of {src} (int8 dense = 2x bf16 nominal; proxy, no int8 figure is measured)",
+        "algorithmic": "8 int8 ops per modular multiply-add (4 limb MMAs x 2), M*N*K per launch (unpadded)",
+        "kernel_ms_per_step": mma_ms / K, "launches_per_step": mma_calls / K,
+        "share_of_step": (mma_ms / K / 1e3) / my if my > 0 else None,
+    }
+
+    # ---- CPU baseline: the oracle on a bounded sample, rank 0 only
+    cpu = None
+    if not args.no_cpu:
+        ora = pkg.SpaSM(entry.build_oracle())
+        ns = CPU_SAMPLE_N if n >= CPU_SAMPLE_N else n
+        ps, js, xs = make_input(ns)
+        As = ora.from_arrays(ns, ns, ps, js, xs, PRIME)
+        t = time.perf_counter()
+        fo = ora.echelonize(As)
+        tc = time.perf_counter() - t
+        cores = int(ora.lib.spasm_get_num_threads())
+        # the same sample through the GPU library, for a like-for-like ratio
+        Ag = gpu.from_arrays(ns, ns, ps, js, xs, PRIME)
+        gpu.echelonize(Ag)
+        t = time.perf_counter()
+        fg = gpu.echelonize(Ag)
+        tg = time.perf_counter() - t
+        assert fg.r == fo.r
+        cpu = {"value": tc, "unit": "s", "cores": cores, "kind": "port",
+               "sample": f"oracle restatement of libspasm (oracle/), {cores} cores, {ns}x{ns} instance of the same generator; "
+                         f"the CUDA library takes {tg:.3f} s end to end on that sample"}
+
+    line = {
+        "metric": "echelonize_time_to_rank", "value": my, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * my, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 residues mod p; dense tail on u8 limbs with int32 tensor-core accumulation", "data": "synthetic",
+        "config": {"workload": f"random sparse {n}x{n}, {NNZ_ROW} nnz/row, echelonize+rank mod {PRIME} (BASELINE configs[1])",
+                   "rank": rank_found, "nnz": nnz, "U_nnz": int(u_nnz), "l2": "flushed between iterations (256 MiB write)",
+                   "parallelism": "single GPU" if world == 1 else f"{world} replicas (no collective on this path yet)"},
+        "e2e": {"value": e2e, "unit": "s", "steps": e2e_steps, "h2d_bytes_per_step": csr_bytes(n, nnz),
+                "d2h_bytes_per_step": int(8 * (rank_found + 1) + 8 * u_nnz + 4 * n)},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "phases_last_step_s": phases,
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=None, help="debug: override the matrix size (the bench value is only valid at the default)")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -180,6 +180,8 @@ long long reduce_sum_i32(const int *in, size_t n);
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // work counters (algorithmic bytes / MACs per SURVEY.md §8d) of the last solve-type call
+extern long long g_launches;  // kernels launched by this library (counted at the call sites of the hot phases)
+
 struct WorkStats {
   long long bytes = 0, macs = 0, rows = 0, light = 0, medium = 0, heavy = 0;
   double ms = 0;

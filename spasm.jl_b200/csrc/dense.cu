@@ -273,7 +273,11 @@ bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, lo
 void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
              bool subtract, const Fp &F) {
   if (M <= 0 || N <= 0) return;
-  if (gemm_nt_mma(C, ldc, M, N, A, lda, B, ldb, K, subtract, F)) return;
+  if (gemm_nt_mma(C, ldc, M, N, A, lda, B, ldb, K, subtract, F)) {
+    g_launches += 3;  // two limb splits + the tcgen05 kernel
+    return;
+  }
+  g_launches += 1;
   dim3 grid(cdiv(N, 64), cdiv(M, 64));
   if (F.small)
     k_gemm_nt<true><<<grid, 256, 0, stream()>>>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F);
@@ -470,6 +474,7 @@ static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0,
     else
       k_update_T<false><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, ldw, Tp.p, tilepiv.p, ctl.p, F);
     CK(cudaGetLastError());
+    g_launches += 3;
     PanelCtl h = fetch(ctl.p);
     npiv = h.npiv;
     c0 += h.consumed;
@@ -541,6 +546,7 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
       CK(cudaGetLastError());
       U.nnz += add;
       U.n += rr;
+      g_launches += 6;
       tick(2, t1);
       // trailing update of the later rows:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
       const long long kb = k0 + Sn;

@@ -179,6 +179,7 @@ void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U,
       else
         k_sptrsm<false, true><<<grid, 256, 0, s>>>(Ut.p.p, Ut.j.p, Ut.x.p, order2.p + off, pivcol.p, Vp.p, kc_max, D.Dt.p, D.ld, (int)k0, kc, F);
       off += cnt;
+      g_launches += 1;
     }
     if (r > 0) {
       dim3 grid(D.Sm0, ktiles);

@@ -296,16 +296,17 @@ bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, lo
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   g_mma_ms += ms;
-  g_mma_macs += (double)Mp * Np * Kp;
+  g_mma_macs += (double)M * N * K;  // algorithmic (unpadded) modular MACs
   g_mma_calls++;
   return true;
 }
 
 }  // namespace sb
 
+// {ms in the tcgen05 kernel, modular MACs it computed, calls, kernels launched by the library}
 extern "C" void spasm_b200_mma_stats(double *out, int reset) {
-  out[0] = sb::g_mma_ms, out[1] = sb::g_mma_macs, out[2] = (double)sb::g_mma_calls;
-  if (reset) sb::g_mma_ms = sb::g_mma_macs = 0, sb::g_mma_calls = 0;
+  out[0] = sb::g_mma_ms, out[1] = sb::g_mma_macs, out[2] = (double)sb::g_mma_calls, out[3] = (double)sb::g_launches;
+  if (reset) sb::g_mma_ms = sb::g_mma_macs = 0, sb::g_mma_calls = 0, sb::g_launches = 0;
 }
 
 // test / bench hook: C = [C -] A . B^T mod p on host arrays of residues in [0,p).

@@ -251,7 +251,8 @@ static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, in
 }
 
 // ------------------------------------------------------------------ the driver
-static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
+static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, const DCsr *resident = nullptr, bool download = true,
+                                 int *rank_out = nullptr) {
   require_gpu();
   echelonize_opts defaults;
   if (opts == nullptr) {
@@ -284,10 +285,12 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
   }
 
   DCsr A0, S;
-  upload_csr(A, A0, E.F);
-  sync();
+  if (resident == nullptr) {
+    upload_csr(A, A0, E.F);
+    sync();
+  }
   g_timings[1] = spasm_wtime() - start;
-  const DCsr *cur = &A0;
+  const DCsr *cur = resident ? resident : &A0;
   int n = n0, npiv = 0;
   std::vector<int> p_in;  // current row -> original row (empty: identity)
   double density = (n0 > 0 && m > 0) ? (double)spasm_nnz(A) / n0 / m : 0.0;
@@ -394,6 +397,14 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts) {
     g_timings[8] = E.t_tail;
   }
   const double t_dl = spasm_wtime();
+  if (rank_out) *rank_out = E.U.n;
+  if (!download) {  // device-resident timing mode (bench.py `value`): the factor is dropped on the device
+    g_timings[0] = spasm_wtime() - start;
+    logf("[echelonize] Done in %.1fs. Rank %d, %lld nz in basis\n", spasm_wtime() - start, E.U.n, (long long)E.U.nnz);
+    if (E.L) spasm_triplet_free(E.L);
+    free(E.Lp);
+    return nullptr;
+  }
 
   // ---- the factor goes back to host memory (plain malloc arrays: src/SpaSM.jl:279-304 unsafe_loads them)
   spasm_lu *fact = (spasm_lu *)spasm_malloc(sizeof(spasm_lu));
@@ -454,6 +465,49 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
     return nullptr;
   }
 }
+
+// ---- device-resident entry points used by bench.py for the kernel-only number: the input CSR is
+// uploaded once, each call runs the whole echelonization from HBM and returns the rank only.
+struct ResidentMatrix {
+  const spasm_csr *host;
+  DCsr dev;
+};
+void *spasm_b200_upload(const struct spasm_csr *A) {
+  try {
+    require_gpu();
+    auto *h = new ResidentMatrix{A, {}};
+    upload_csr(A, h->dev, make_field(A->field->p));
+    sync();
+    return h;
+  } catch (const std::exception &e) {
+    errf("[spasm_b200] spasm_b200_upload failed: %s\n", e.what());
+    return nullptr;
+  }
+}
+int spasm_b200_echelonize_resident(void *handle, struct echelonize_opts *opts, double *ms) {
+  try {
+    require_gpu();
+    auto *h = (ResidentMatrix *)handle;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, stream()));
+    int rank = -1;
+    echelonize_impl(h->host, opts, &h->dev, false, &rank);
+    CK(cudaEventRecord(e1, stream()));
+    CK(cudaEventSynchronize(e1));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = t;
+    return rank;
+  } catch (const std::exception &e) {
+    errf("[spasm_b200] spasm_b200_echelonize_resident failed: %s\n", e.what());
+    return -1;
+  }
+}
+void spasm_b200_release(void *handle) { delete (ResidentMatrix *)handle; }
 
 void spasm_b200_last_timings(double *out) {
   for (int i = 0; i < 16; i++) out[i] = g_timings[i];

@@ -468,6 +468,7 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
       k_flc_commit<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, P.qinv.p, open.p, state.p, res.p, round, ctr.p);
       CK(cudaGetLastError());
       P.flcol_rounds = (int)round + 1;
+      g_launches += 2;
       if (fetch(ctr.p + 1) == 0) break;
     }
     counts[1] = fetch(ctr.p);
@@ -506,6 +507,7 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
         void *args[] = {&g, &w0, &wn, &gen};
         CK(cudaLaunchCooperativeKernel((void *)k_greedy_window, dim3(cdiv((long long)wn * 32, 256)), dim3(256), args, 0, s));
         gen++;
+        g_launches += 1;
         P.greedy_windows++;
         if (gen == (1u << 14)) {
           marks.zero();

@@ -8,6 +8,7 @@
 
 namespace sb {
 
+long long g_launches = 0;
 static cudaStream_t g_stream = nullptr;
 static int g_sms = 0;
 static bool g_ready = false;

@@ -750,6 +750,7 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
         R.stats.heavy += ntodo;
       }
       CK(cudaGetLastError());
+      g_launches += 1;
       ctrs.download(h_ctrs, 8);
       sync();
       const long long n_tbl = (long long)h_ctrs[2], n_slab = (long long)h_ctrs[3];

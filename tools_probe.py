@@ -57,7 +57,7 @@ def gemm_bench(M, N, K, prime=42013):
     A = rng.integers(0, prime, size=(M, K), dtype=np.uint32)
     B = rng.integers(0, prime, size=(N, K), dtype=np.uint32)
     Cm = rng.integers(0, prime, size=(M, N), dtype=np.uint32)
-    st = (C.c_double * 3)()
+    st = (C.c_double * 4)()
     g.lib.spasm_b200_mma_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
     for path in (0, 1):
         best = 1e9
