@@ -1,6 +1,7 @@
 // dense.cu — dense tail, first version: Gauss-Jordan by pivot steps on CUDA cores.
 // (The blocked tcgen05 path that replaces the elimination step lives in dense_mma.cu.)
 #include "dense.cuh"
+#include "dist.cuh"
 
 namespace sb {
 
@@ -489,18 +490,56 @@ static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0,
   return npiv;
 }
 
+__global__ void k_gather_int(const int *__restrict__ src, const int *__restrict__ idx, int n, int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+// ranks that do not materialise the factor still keep U.n / qinv consistent: empty rows
+__global__ void k_register_pivots_only(const int *__restrict__ pivcol, const int *__restrict__ q, int rr, int urow0, long long unz,
+                                       long long *__restrict__ Up, int *__restrict__ Uqinv) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= rr) return;
+  Uqinv[q[pivcol[s]]] = urow0 + s;
+  Up[urow0 + s + 1] = unz;
+}
+
+// Dense tail.  With N ranks the remaining rows are dealt to the ranks panel by panel
+// (block-cyclic, panel_owner): every rank builds and keeps only ITS rows of the dense Schur
+// complement; the owner of panel b factors it and broadcasts the reduced rows R_b (NCCL over
+// NVLink); every rank then updates its own later rows with the tensor-core GEMM.  Rank 0
+// materialises the rows of U; the other ranks only track the pivots.
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size) {
   cudaStream_t s = stream();
   if (block_size <= 0) block_size = 1000;
   if (nrows == 0 || A.m == U.n) return;
+  const Dist &dd = dist();
+  const int me = dd.rank, NR = dd.nranks;
+  const bool emit_rows = (me == 0);
   double t0 = spasm_wtime();
+  // ---- my rows
+  DBuf<int> rows_local;
+  int n_local = nrows;
+  const int *my_rows = rows;
+  if (NR > 1) {
+    std::vector<int> pos = local_positions(nrows, block_size, NR, me);
+    n_local = (int)pos.size();
+    DBuf<int> dpos(std::max(n_local, 1));
+    rows_local.alloc(std::max(n_local, 1));
+    if (n_local) {
+      dpos.upload(pos.data(), n_local);
+      k_gather_int<<<cdiv(n_local, 256), 256, 0, s>>>(rows, dpos.p, n_local, rows_local.p);
+      sync();
+    }
+    my_rows = rows_local.p;
+  }
   DenseSchur D;
-  build_dense_schur(A, rows, nrows, U, Uqinv.p, F, D);
+  build_dense_schur(A, my_rows, n_local, U, Uqinv.p, F, D);
   const int Sm0 = D.Sm0;
   const long long ld = D.ld;
-  logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)\n", nrows, Sm0, spasm_wtime() - t0, D.levels);
+  logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)%s\n", nrows, Sm0, spasm_wtime() - t0, D.levels,
+       NR > 1 ? " [sharded]" : "");
   const bool prof = getenv("SPASM_B200_PROFILE") != nullptr;
-  double tp[6] = {0, 0, 0, 0, 0, 0};  // panel, R gemm, emit, gather/transposes, trailing gemm, blocks
+  double tp[7] = {0, 0, 0, 0, 0, 0, 0};  // panel, R gemm, emit, gather/transposes, trailing gemm, blocks, broadcast
   auto tick = [&](int slot, double &t1) {
     if (!prof) return;
     sync();
@@ -508,7 +547,7 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
     tp[slot] += now - t1;
     t1 = now;
   };
-  {
+  if (emit_rows) {
     // upper bound of what the dense rows add to U (every block full rank): reserve once, no regrowth copies
     long long ub = 0, left = Sm0;
     for (long long k0 = 0; k0 < nrows && left > 0; k0 += block_size) {
@@ -517,40 +556,69 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
       left -= rr;
     }
     if ((size_t)ub * 8 < dev_free_bytes() / 2) csr_reserve(U, U.nnz + ub, U.n + std::min(nrows, Sm0));
+  } else {
+    csr_reserve(U, U.nnz, U.n + std::min(nrows, Sm0));
   }
   const int Bmax = std::min(block_size, nrows);
   DBuf<uint32_t> T((size_t)Bmax * Bmax), Tsel((size_t)Bmax * Bmax), R((size_t)Bmax * Sm0), Rt, Pt;
-  DBuf<int> ispiv, pivrow, pivcol, ident(Bmax);
+  DBuf<int> ispiv, pivrow, pivcol(Bmax), ident(Bmax), hdr(1);
   k_iota2<<<cdiv(Bmax, 256), 256, 0, s>>>(ident.p, Bmax);
-  for (long long k0 = 0; k0 < nrows; k0 += block_size) {
-    const int Sn = (int)std::min<long long>(block_size, nrows - k0);
-    logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - k0, A.m - U.n,
+  const long long nb = ((long long)nrows + block_size - 1) / block_size;
+  long long lb = 0;  // my panels already factored
+  for (long long b = 0; b < nb; b++) {
+    const long long kg = b * block_size;
+    const int Sn = (int)std::min<long long>(block_size, nrows - kg);
+    const int owner = panel_owner(b, NR);
+    logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - kg, A.m - U.n,
          block_size);
     double t1 = spasm_wtime();
-    const int rr = panel_factor(D.Dt.p, ld, Sm0, k0, Sn, T.p, ispiv, pivrow, pivcol, F);
-    tick(0, t1);
-    tp[5] += 1;
-    if (rr > 0) {
-      // reduced rows  R[s][c] = sum_t T[pivrow[s]][t] * Dt[c][k0+t]
-      k_gather_T_rows<<<dim3(cdiv(Sn, 256), rr), 256, 0, s>>>(T.p, Sn, pivrow.p, nullptr, rr, Tsel.p);
-      gemm_nt(R.p, Sm0, rr, Sm0, Tsel.p, Sn, D.Dt.p + k0, ld, Sn, false, F);
+    int rr = 0;
+    if (owner == me) {
+      const long long k0 = lb * block_size;
+      DBuf<int> pc_tmp;
+      rr = panel_factor(D.Dt.p, ld, Sm0, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F);
+      if (rr > 0) CK(cudaMemcpyAsync(pivcol.p, pc_tmp.p, (size_t)rr * sizeof(int), cudaMemcpyDeviceToDevice, s));
+      tick(0, t1);
+      if (rr > 0) {
+        // reduced rows  R[s][c] = sum_t T[pivrow[s]][t] * Dt[c][k0+t]
+        k_gather_T_rows<<<dim3(cdiv(Sn, 256), rr), 256, 0, s>>>(T.p, Sn, pivrow.p, nullptr, rr, Tsel.p);
+        gemm_nt(R.p, Sm0, rr, Sm0, Tsel.p, Sn, D.Dt.p + k0, ld, Sn, false, F);
+      }
       tick(1, t1);
-      // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
-      DBuf<int> cnt(rr + 1);
-      DBuf<long long> rpos(rr + 1);
-      k_count_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, rr, cnt.p);
-      exclusive_scan_i32_to_i64(cnt.p, rpos.p, rr + 1);
-      const long long add = fetch(rpos.p + rr);
-      csr_reserve(U, U.nnz + add, U.n + rr);
-      k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pivcol.p, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
-      CK(cudaGetLastError());
-      U.nnz += add;
+      lb++;
+    }
+    tp[5] += 1;
+    if (NR > 1) {
+      if (owner == me) CK(cudaMemcpyAsync(hdr.p, &rr, sizeof(int), cudaMemcpyHostToDevice, s));
+      dist_broadcast(hdr.p, sizeof(int), owner);
+      rr = fetch(hdr.p);
+      if (rr > 0) {
+        dist_broadcast(pivcol.p, (size_t)rr * sizeof(int), owner);
+        dist_broadcast(R.p, (size_t)rr * Sm0 * sizeof(uint32_t), owner);
+      }
+      tick(6, t1);
+    }
+    if (rr > 0) {
+      if (emit_rows) {
+        // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
+        DBuf<int> cnt(rr + 1);
+        DBuf<long long> rpos(rr + 1);
+        k_count_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, rr, cnt.p);
+        exclusive_scan_i32_to_i64(cnt.p, rpos.p, rr + 1);
+        const long long add = fetch(rpos.p + rr);
+        csr_reserve(U, U.nnz + add, U.n + rr);
+        k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pivcol.p, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
+        CK(cudaGetLastError());
+        U.nnz += add;
+      } else {
+        k_register_pivots_only<<<cdiv(rr, 256), 256, 0, s>>>(pivcol.p, D.q0.p, rr, U.n, U.nnz, U.p.p, Uqinv.p);
+      }
       U.n += rr;
       g_launches += 6;
       tick(2, t1);
-      // trailing update of the later rows:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
-      const long long kb = k0 + Sn;
-      const int nk = (int)(nrows - kb);
+      // trailing update of MY later rows:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
+      const long long kb = lb * block_size;
+      const int nk = (int)std::max<long long>(0, n_local - kb);
       if (nk > 0) {
         const long long ldk = ((long long)rr + 15) / 16 * 16;
         Rt.alloc((size_t)Sm0 * ldk);
@@ -566,7 +634,8 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
     if (U.n == A.m) break;
   }
   if (prof)
-    fprintf(stderr, "[dense] blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs trailing=%.3fs\n", (int)tp[5], tp[0], tp[1], tp[2], tp[3], tp[4]);
+    fprintf(stderr, "[dense] rank %d/%d blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs trailing=%.3fs bcast=%.3fs\n", me, NR, (int)tp[5],
+            tp[0], tp[1], tp[2], tp[3], tp[4], tp[6]);
 }
 
 }  // namespace sb

@@ -1,0 +1,20 @@
+// dist.cuh — one process per GPU; NCCL (loaded with dlopen, never linked) for the one real exchange
+// step of the path: the broadcast of each factored dense panel to the ranks that hold later rows.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+struct Dist {
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;  // ncclComm_t
+};
+Dist &dist();
+void dist_broadcast(void *dev_buf, size_t bytes, int root);  // on the library stream
+
+// block-cyclic ownership of the dense panels (pure host logic, also exported for the CPU tests)
+inline int panel_owner(long long b, int nranks) { return (int)(b % nranks); }
+// positions (into the remaining-row list) owned by `rank`: panels b = rank, rank+nranks, ...
+std::vector<int> local_positions(long long n_rem, int block, int nranks, int rank);
+
+}  // namespace sb

@@ -1,0 +1,51 @@
+"""Run under torchrun with N>=2 GPUs: the sharded dense tail must give rank 0 the SAME factor, bit for
+bit, as the single-GPU library gave (file written by rank 0 before the communicator exists) and as
+the CPU oracle gives.   torchrun --nproc-per-node 2 tests/dist_gpu_check.py"""
+import ctypes as C
+import os
+import sys
+
+sys.path[:0] = [".", "tests"]
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import __graft_entry__ as e
+import bench
+import checks
+import synth
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+pkg = e.load_package()
+gpu = pkg.SpaSM()
+gpu.log(False)
+cases = [(1500, 1500, 5, 42013, 3, {}), (2600, 2400, 6, 65521, 4, dict(dense_block_size=300)), (900, 1000, 4, 4294967291, 5, dict(dense_block_size=128)),
+         (5000, 5000, 10, 42013, 6, {})]
+single = []
+for (n, m, k, prime, seed, kw) in cases:  # single-GPU results first (no communicator yet)
+    p, j, x = synth.random_rows(n, m, k, prime, seed)
+    A = gpu.from_arrays(n, m, p, j, x, prime)
+    single.append(checks.lu_arrays(gpu.echelonize(A, **kw)))
+bench.dist_init(gpu.lib, dist, rank, world)
+ok = True
+for idx, (n, m, k, prime, seed, kw) in enumerate(cases):
+    p, j, x = synth.random_rows(n, m, k, prime, seed)
+    A = gpu.from_arrays(n, m, p, j, x, prime)
+    f = gpu.echelonize(A, **kw)
+    got = checks.lu_arrays(f)
+    assert got["r"] == single[idx]["r"], (rank, got["r"], single[idx]["r"])
+    assert np.array_equal(got["qinv"], single[idx]["qinv"])
+    if rank == 0:
+        checks.assert_same(single[idx], got, f"case {idx}: ")
+        ora = pkg.SpaSM(e.build_oracle())
+        checks.assert_same(checks.lu_arrays(ora.echelonize(A, **kw)), got, f"case {idx} vs oracle: ")
+        K1, K2 = gpu.kernel(f), ora.kernel(ora.echelonize(A, **kw))
+        for a, b in zip(K1.arrays(), K2.arrays()):
+            assert np.array_equal(a, b)
+dist.barrier()
+gpu.lib.spasm_b200_dist_finalize()
+dist.destroy_process_group()
+if rank == 0:
+    print(f"dist check OK on {world} GPUs: {len(cases)} cases bit-exact (single GPU == sharded == oracle)")

@@ -1,0 +1,55 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes check the block-cyclic sharding of the dense
+tail (the pure host functions the CUDA library uses, exported through the C ABI) and the bootstrap
+plumbing bench.py uses to ship the 128-byte NCCL id (here a fake id, broadcast over gloo)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+WORKER = r'''
+import ctypes as C, os, sys
+sys.path[:0] = [".", "tests"]
+import numpy as np, torch, torch.distributed as dist
+import __graft_entry__ as e
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lib = C.CDLL(str(e.build_product()), mode=os.RTLD_LOCAL)
+lib.spasm_b200_local_positions.restype = C.c_longlong
+lib.spasm_b200_local_positions.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
+for (n_rem, block) in [(10, 3), (1000, 1000), (2501, 1000), (7, 100), (0, 5), (4096, 64)]:
+    buf = np.zeros(max(n_rem, 1), dtype=np.int32)
+    cnt = lib.spasm_b200_local_positions(n_rem, block, world, rank, buf.ctypes.data, len(buf))
+    mine = buf[:cnt].copy()
+    # every position belongs to the owner of its panel, in increasing order
+    assert all(lib.spasm_b200_panel_owner(int(k) // block, world) == rank for k in mine)
+    assert (np.diff(mine) > 0).all()
+    # all ranks together cover every remaining row exactly once
+    t = torch.zeros(max(n_rem, 1), dtype=torch.int64)
+    t[torch.from_numpy(mine.astype(np.int64))] += 1 if cnt else 0
+    if cnt:
+        t.zero_(); t[torch.from_numpy(mine.astype(np.int64))] = 1
+    dist.all_reduce(t)
+    assert (t[:n_rem] == 1).all(), (n_rem, block, t)
+    # load balance: sizes differ by at most one panel
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([cnt]))
+    assert max(int(s) for s in sizes) - min(int(s) for s in sizes) <= block
+# bootstrap plumbing: rank 0's 128-byte id reaches everyone unchanged
+ident = torch.arange(128, dtype=torch.uint8) if rank == 0 else torch.zeros(128, dtype=torch.uint8)
+dist.broadcast(ident, src=0)
+assert ident.tolist() == list(range(128))
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_sharding_and_bootstrap_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
