@@ -305,18 +305,31 @@ struct PanelCtl {
 // thread owns rows r = tid, tid+1024, ...: finding the pivot is one coalesced pass over a column,
 // eliminating it is wc-cc independent coalesced read-modify-writes per thread (no dependent chains).
 // The recorded operations Gc[s][r] (column s = s-th pivot of this call) define T <- G.T.
+// colflag[c] = 1 iff column c of the tile is nonzero on some row that is not a pivot yet.  A column
+// that is zero there stays zero under the eliminations of the tile (the pivot row is one of those rows).
+__global__ void k_col_flags(const uint32_t *__restrict__ Wt, long long ldw, int Sn, const int *__restrict__ ispiv, unsigned char *__restrict__ flag) {
+  const uint32_t *col = Wt + (long long)blockIdx.x * ldw;
+  int any = 0;
+  for (int r = threadIdx.x; r < Sn; r += blockDim.x) any |= (!ispiv[r] && col[r] != 0);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flag[blockIdx.x] = any ? 1 : 0;
+}
 template <bool SMALL>
 __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, int Sn, int wc, long long ldw, int c0,
                                                       int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
-                                                      uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl, Fp F) {
+                                                      uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
+                                                      const unsigned char *__restrict__ colflag, Fp F) {
   __shared__ int red[32];
   __shared__ int s_piv;
   __shared__ uint32_t prow[WMAX], gprow[PB];
+  __shared__ unsigned char s_flag[WMAX];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int npiv = ctl->npiv, found = 0, cc = 0;
   for (long long idx = tid; idx < (long long)PB * ldw; idx += 1024) Gc[idx] = 0;
+  for (int c = tid; c < wc; c += 1024) s_flag[c] = colflag[c];
   __syncthreads();
   for (; cc < wc && found < PB && npiv < Sn; cc++) {
+    if (!s_flag[cc]) continue;
     int best = 0x7fffffff;
     const uint32_t *col = Wt + (long long)cc * ldw;
     for (int r = tid; r < Sn; r += 1024)
@@ -374,6 +387,115 @@ __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, 
   }
   if (tid == 0) ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc;
 }
+// shared-memory version for p < 2^16 and panels of at most 1024 rows (the default block size is
+// 1000): the whole tile [W | Gc] lives in smem as u16, column-major, one thread per row.
+__global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__restrict__ Wt, int Sn, int wc, long long ldw, int c0,
+                                                           int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
+                                                           uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl, Fp F) {
+  extern __shared__ unsigned short tile[];  // [32 + PB][SP]
+  __shared__ int red[32];
+  __shared__ int s_piv;
+  __shared__ uint32_t prow[32 + PB];
+  const int SP = 1024;
+  const int r = threadIdx.x, lane = r & 31, wid = r >> 5;
+  const bool live = r < Sn;
+  for (int c = 0; c < 32; c++) tile[c * SP + r] = (live && c < wc) ? (unsigned short)Wt[(long long)c * ldw + r] : 0;
+  for (int s = 0; s < PB; s++) tile[(32 + s) * SP + r] = 0;
+  int my_ispiv = live ? ispiv[r] : 1;
+  int npiv = ctl->npiv, found = 0, cc = 0;
+  __syncthreads();
+  for (; cc < wc && found < PB && npiv < Sn; cc++) {
+    int best = (!my_ispiv && tile[cc * SP + r] != 0) ? r : 0x7fffffff;
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) red[wid] = best;
+    __syncthreads();
+    if (r < 32) {
+      int b2 = red[r];
+      for (int o = 16; o; o >>= 1) b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+      if (r == 0) s_piv = b2;
+    }
+    __syncthreads();
+    const int pr = s_piv;
+    if (pr == 0x7fffffff) continue;
+    if (r == pr) {
+      my_ispiv = 1;
+      ispiv[r] = 1;
+      pivrow[npiv] = r;
+      pivcol[npiv] = c0 + cc;
+      tilepiv[found] = r;
+      tile[(32 + found) * SP + r] = 1;
+    }
+    __syncthreads();
+    if (r < 32 + PB) {
+      // the scaled pivot row (columns cc..wc of W and 0..found of Gc)
+      const bool used = (r < 32) ? (r >= cc && r < wc) : (r - 32 <= found);
+      uint32_t v = 0;
+      if (used) {
+        const uint32_t alpha = dev_inv(tile[cc * SP + pr], F.p);
+        v = mulmod<true>(alpha, tile[r * SP + pr], F);
+      }
+      prow[r] = v;
+    }
+    __syncthreads();
+    if (live) {
+      if (r == pr) {
+        for (int k = cc; k < wc; k++) tile[k * SP + r] = (unsigned short)prow[k];
+        for (int s = 0; s <= found; s++) tile[(32 + s) * SP + r] = (unsigned short)prow[32 + s];
+      } else {
+        const uint32_t f = tile[cc * SP + r];
+        if (f != 0) {
+          const uint32_t nf = F.p - f;
+          for (int k = cc; k < wc; k++) {
+            uint32_t t = (uint32_t)tile[k * SP + r] + mulmod<true>(nf, prow[k], F);
+            tile[k * SP + r] = (unsigned short)(t >= F.p ? t - F.p : t);
+          }
+          for (int s = 0; s <= found; s++) {
+            uint32_t t = (uint32_t)tile[(32 + s) * SP + r] + mulmod<true>(nf, prow[32 + s], F);
+            tile[(32 + s) * SP + r] = (unsigned short)(t >= F.p ? t - F.p : t);
+          }
+        }
+      }
+    }
+    found++;
+    npiv++;
+    __syncthreads();
+  }
+  if (live)
+    for (int s = 0; s < found; s++) Gc[(long long)s * ldw + r] = tile[(32 + s) * SP + r];
+  if (r == 0) ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc;
+}
+
+// Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]  for a narrow tile (c < wc <= 32): one CTA per 32 rows r
+template <bool SMALL>
+__global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt, long long ld, const uint32_t *__restrict__ T, int Sn, int wc,
+                                                uint32_t *__restrict__ Wt, long long ldw, Fp F) {
+  // blockIdx.y selects 8 of the <=32 columns: 4x more CTAs in flight for this latency-bound product
+  __shared__ uint32_t Ts[32][33], Ds[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // tx: r within the tile, ty: column within the group
+  const int r0 = blockIdx.x * 32, cg = blockIdx.y * 8;
+  unsigned long long acc = 0;
+  for (int t0 = 0; t0 < Sn; t0 += 32) {
+    for (int idx = threadIdx.x; idx < 32 * 32; idx += 256) {
+      const int a = idx >> 5, t = idx & 31;
+      Ts[a][t] = (r0 + a < Sn && t0 + t < Sn) ? T[(long long)(r0 + a) * Sn + t0 + t] : 0u;
+    }
+    {
+      const int a = threadIdx.x >> 5, t = threadIdx.x & 31;
+      Ds[a][t] = (cg + a < wc && t0 + t < Sn) ? Dt[(long long)(cg + a) * ld + t0 + t] : 0u;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int t = 0; t < 32; t++) {
+      if (SMALL)
+        acc += (unsigned long long)(Ts[tx][t] * Ds[ty][t]);
+      else
+        acc += mulmod<false>(Ts[tx][t], Ds[ty][t], F);
+    }
+    __syncthreads();
+  }
+  if (r0 + tx < Sn && cg + ty < wc) Wt[(long long)(cg + ty) * ldw + r0 + tx] = red64(acc, F);
+}
+
 __global__ void k_set_identity(uint32_t *T, int n) {
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx < (long long)n * n) T[idx] = (idx / n == idx % n) ? 1u : 0u;
@@ -453,6 +575,7 @@ static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0,
   const long long ldw = ((long long)Sn + 31) / 32 * 32;
   DBuf<uint32_t> Wt((size_t)WMAX * ldw), Gc((size_t)PB * ldw), Tp((size_t)PB * Sn);
   DBuf<int> tilepiv(PB);
+  DBuf<unsigned char> colflag(WMAX);
   DBuf<PanelCtl> ctl(1);
   ctl.zero();
   ispiv.alloc(Sn);
@@ -464,11 +587,28 @@ static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0,
   for (int c0 = 0; c0 < Sm0 && npiv < Sn;) {
     const int wc = std::min(w, Sm0 - c0);
     // Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]     (the tile of T.Panel, transposed)
-    gemm_nt(Wt.p, ldw, wc, Sn, Dt + (long long)c0 * ld + k0, ld, T, Sn, Sn, false, F);
-    if (F.small)
-      k_tile_gauss<true><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
-    else
-      k_tile_gauss<false><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
+    if (wc <= 32) {
+      if (F.small)
+        k_wtile<true><<<dim3(cdiv(Sn, 32), cdiv(wc, 8)), 256, 0, s>>>(Dt + (long long)c0 * ld + k0, ld, T, Sn, wc, Wt.p, ldw, F);
+      else
+        k_wtile<false><<<dim3(cdiv(Sn, 32), cdiv(wc, 8)), 256, 0, s>>>(Dt + (long long)c0 * ld + k0, ld, T, Sn, wc, Wt.p, ldw, F);
+    } else
+      gemm_nt(Wt.p, ldw, wc, Sn, Dt + (long long)c0 * ld + k0, ld, T, Sn, Sn, false, F);
+    if (F.small && Sn <= 1024 && wc <= 32) {
+      static bool attr = false;
+      const size_t smem = (size_t)(32 + PB) * 1024 * sizeof(unsigned short);
+      if (!attr) {
+        CK(cudaFuncSetAttribute(k_tile_gauss_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+      }
+      k_tile_gauss_smem<<<1, 1024, smem, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
+    } else {
+      k_col_flags<<<wc, 256, 0, s>>>(Wt.p, ldw, Sn, ispiv.p, colflag.p);
+      if (F.small)
+        k_tile_gauss<true><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, F);
+      else
+        k_tile_gauss<false><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, F);
+    }
     k_gather_T_rows<<<dim3(cdiv(Sn, 256), PB), 256, 0, s>>>(T, Sn, tilepiv.p, &ctl.p->found, 0, Tp.p);
     if (F.small)
       k_update_T<true><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, ldw, Tp.p, tilepiv.p, ctl.p, F);

@@ -91,19 +91,29 @@ struct __align__(8) MmaShared {
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
   uint64_t tmem_full;
+  uint64_t tmem_empty;
   uint32_t tmem_base;
 };
+static constexpr int HALF = TILE / 2;
+static constexpr int STAGE_SP = HALF + 1;                       // padded row of the epilogue staging tile
+static constexpr int STAGING_BYTES = TILE * STAGE_SP * 4;       // 128 x 65 words
 
+// PERSISTENT: gridDim.x CTAs (one per SM) loop over the output tiles.  Per tile: the producer streams
+// K through the 3-stage ring (it runs ahead into the next tile while the epilogue is busy), the MMA
+// thread accumulates hi/mid/lo in TMEM, the epilogue warps pull the whole accumulator into registers
+// (reduced mod p), hand TMEM back at once (tmem_empty) so the next tile's MMAs start, and only then do
+// the read-modify-write of C through a padded staging tile, half a tile at a time.
 template <bool SUB>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, uint32_t *__restrict__ C, long long ldc,
-              int M, int N, int nkb, Fp F) {
+              int M, int N, int nkb, int tiles_m, int tiles_n, Fp F) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *tiles = (uint8_t *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
-  MmaShared *sh = (MmaShared *)(tiles + STAGES * STAGE_BYTES);
+  uint32_t *stage = (uint32_t *)(tiles + STAGES * STAGE_BYTES);
+  MmaShared *sh = (MmaShared *)((uint8_t *)stage + STAGING_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
+  const long long ntiles = (long long)tiles_m * tiles_n;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -111,6 +121,7 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       mbar_init(&sh->empty[s], 1);
     }
     mbar_init(&sh->tmem_full, 1);
+    mbar_init(&sh->tmem_empty, 4);  // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
@@ -128,73 +139,152 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&sh->empty[s], ph ^ 1);
-        uint8_t *st = tiles + s * STAGE_BYTES;
-        mbar_expect_tx(&sh->full[s], STAGE_BYTES);
-        tma_load_2d(st + 0 * TILE * BK, &mapA0, kb * BK, m0, &sh->full[s]);
-        tma_load_2d(st + 1 * TILE * BK, &mapA1, kb * BK, m0, &sh->full[s]);
-        tma_load_2d(st + 2 * TILE * BK, &mapB0, kb * BK, n0, &sh->full[s]);
-        tma_load_2d(st + 3 * TILE * BK, &mapB1, kb * BK, n0, &sh->full[s]);
+      long long kbg = 0;  // k-blocks issued so far (ring position)
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (int)(tile / tiles_n) * TILE, n0 = (int)(tile % tiles_n) * TILE;
+        for (int kb = 0; kb < nkb; kb++, kbg++) {
+          const int s = (int)(kbg % STAGES);
+          const uint32_t ph = (uint32_t)((kbg / STAGES) & 1);
+          mbar_wait(&sh->empty[s], ph ^ 1);
+          uint8_t *st = tiles + s * STAGE_BYTES;
+          mbar_expect_tx(&sh->full[s], STAGE_BYTES);
+          tma_load_2d(st + 0 * TILE * BK, &mapA0, kb * BK, m0, &sh->full[s]);
+          tma_load_2d(st + 1 * TILE * BK, &mapA1, kb * BK, m0, &sh->full[s]);
+          tma_load_2d(st + 2 * TILE * BK, &mapB0, kb * BK, n0, &sh->full[s]);
+          tma_load_2d(st + 3 * TILE * BK, &mapB1, kb * BK, n0, &sh->full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&sh->full[s], ph);
+      long long kbg = 0;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        mbar_wait(&sh->tmem_empty, (it & 1) ^ 1);  // the epilogue has pulled the previous accumulator out
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t base = smem_u32(tiles + s * STAGE_BYTES);
-        const uint64_t a0 = make_desc(base), a1 = make_desc(base + TILE * BK), b0 = make_desc(base + 2 * TILE * BK),
-                       b1 = make_desc(base + 3 * TILE * BK);
+        for (int kb = 0; kb < nkb; kb++, kbg++) {
+          const int s = (int)(kbg % STAGES);
+          const uint32_t ph = (uint32_t)((kbg / STAGES) & 1);
+          mbar_wait(&sh->full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = smem_u32(tiles + s * STAGE_BYTES);
+          const uint64_t a0 = make_desc(base), a1 = make_desc(base + TILE * BK), b0 = make_desc(base + 2 * TILE * BK),
+                         b1 = make_desc(base + 3 * TILE * BK);
 #pragma unroll
-        for (int ks = 0; ks < BK / 32; ks++) {
-          const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 32 bytes of K per instruction
-          const uint32_t acc = (kb | ks) ? 1u : 0u;
-          umma_i8(tmem + 0 * TILE, a0 + adv, b0 + adv, IDESC, acc);    // lo
-          umma_i8(tmem + 1 * TILE, a1 + adv, b0 + adv, IDESC, acc);    // mid
-          umma_i8(tmem + 1 * TILE, a0 + adv, b1 + adv, IDESC, 1u);     // mid
-          umma_i8(tmem + 2 * TILE, a1 + adv, b1 + adv, IDESC, acc);    // hi
+          for (int ks = 0; ks < BK / 32; ks++) {
+            const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 32 bytes of K per instruction
+            const uint32_t acc = (kb | ks) ? 1u : 0u;
+            umma_i8(tmem + 0 * TILE, a0 + adv, b0 + adv, IDESC, acc);  // lo
+            umma_i8(tmem + 1 * TILE, a1 + adv, b0 + adv, IDESC, acc);  // mid
+            umma_i8(tmem + 1 * TILE, a0 + adv, b1 + adv, IDESC, 1u);   // mid
+            umma_i8(tmem + 2 * TILE, a1 + adv, b1 + adv, IDESC, acc);  // hi
+          }
+          umma_commit(&sh->empty[s]);  // frees the stage when these MMAs have read it
         }
-        umma_commit(&sh->empty[s]);  // frees the stage when these MMAs have read it
+        umma_commit(&sh->tmem_full);
       }
-      umma_commit(&sh->tmem_full);
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
-    mbar_wait(&sh->tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); each thread owns one output row in TMEM.
+    // The C values of a half tile (128 x 64) are PREFETCHED into registers as 16 coalesced 16-byte
+    // loads per thread before the accumulator is even ready, so no global-memory latency is exposed;
+    // the reduced accumulator is transposed through the padded staging tile to meet them.
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    const int trow = q * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t *crow = C + (long long)row * ldc;
+    const int e = warp - 2;
+    const int sub = lane >> 4, l16 = lane & 15;  // two rows per warp instruction, 16 lanes x 16 B each
+    const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int m0 = (int)(tile / tiles_n) * TILE, n0 = (int)(tile % tiles_n) * TILE;
 #pragma unroll 1
-    for (int c0 = 0; c0 < TILE; c0 += 16) {
-      uint32_t lo[16], mid[16], hi[16];
-      tmem_ld16(lane_base + 0 * TILE + c0, lo);
-      tmem_ld16(lane_base + 1 * TILE + c0, mid);
-      tmem_ld16(lane_base + 2 * TILE + c0, hi);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
+      for (int h = 0; h < 2; h++) {
+        const int nh = n0 + h * HALF;
+        uint4 cv[16];
+        // interior tiles: 16 unconditional 16-byte loads off one base pointer (all in flight together)
+        const bool interior = vec_ok && (m0 + TILE <= M) && (nh + HALF <= N);
+        uint32_t *cbase = C + (long long)(m0 + e * 2 + sub) * ldc + nh + l16 * 4;
+        const long long rstep = 8 * ldc;
+        if (SUB) {
+          if (interior) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int col = n0 + c0 + j;
-          if (col < N) {
+            for (int i = 0; i < 16; i++) cv[i] = *(const uint4 *)(cbase + i * rstep);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const int row = m0 + (i * 4 + e) * 2 + sub, col = nh + l16 * 4;
+              cv[i] = make_uint4(0, 0, 0, 0);
+              if (row < M) {
+                const uint32_t *p = cbase + i * rstep;
+                if (col + 0 < N) cv[i].x = p[0];
+                if (col + 1 < N) cv[i].y = p[1];
+                if (col + 2 < N) cv[i].z = p[2];
+                if (col + 3 < N) cv[i].w = p[3];
+              }
+            }
+          }
+        }
+        if (h == 0) {
+          mbar_wait(&sh->tmem_full, it & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging free (previous half read out)
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 16) {
+          uint32_t lo[16], mid[16], hi[16];
+          tmem_ld16(lane_base + 0 * TILE + h * HALF + c0, lo);
+          tmem_ld16(lane_base + 1 * TILE + h * HALF + c0, mid);
+          tmem_ld16(lane_base + 2 * TILE + h * HALF + c0, hi);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
             unsigned long long v = ((unsigned long long)hi[j] << 16) + ((unsigned long long)mid[j] << 8) + lo[j];
-            uint32_t r = red64(v, F);
+            stage[trow * STAGE_SP + c0 + j] = red64(v, F);
+          }
+        }
+        if (h == 1) {  // the accumulator is out of TMEM: the next tile's MMAs may start
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sh->tmem_empty)) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (interior) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const uint32_t *sp = stage + ((i * 4 + e) * 2 + sub) * STAGE_SP + l16 * 4;
+            uint4 r = make_uint4(sp[0], sp[1], sp[2], sp[3]);
             if (SUB) {
-              uint32_t c = crow[col];
-              crow[col] = addmod(c, negmod(r, F), F);
-            } else
-              crow[col] = r;
+              r.x = addmod(cv[i].x, negmod(r.x, F), F);
+              r.y = addmod(cv[i].y, negmod(r.y, F), F);
+              r.z = addmod(cv[i].z, negmod(r.z, F), F);
+              r.w = addmod(cv[i].w, negmod(r.w, F), F);
+            }
+            *(uint4 *)(cbase + i * rstep) = r;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int rr = (i * 4 + e) * 2 + sub, row = m0 + rr, col = nh + l16 * 4;
+            if (row < M) {
+              const uint32_t *sp = stage + rr * STAGE_SP + l16 * 4;
+              uint4 r = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+              if (SUB) {
+                r.x = addmod(cv[i].x, negmod(r.x, F), F);
+                r.y = addmod(cv[i].y, negmod(r.y, F), F);
+                r.z = addmod(cv[i].z, negmod(r.z, F), F);
+                r.w = addmod(cv[i].w, negmod(r.w, F), F);
+              }
+              uint32_t *p = cbase + i * rstep;
+              if (col + 0 < N) p[0] = r.x;
+              if (col + 1 < N) p[1] = r.y;
+              if (col + 2 < N) p[2] = r.z;
+              if (col + 3 < N) p[3] = r.w;
+            }
           }
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -272,22 +362,23 @@ bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, lo
   k_split_limbs<<<cdiv((long long)Mp * (Kp >> 2), 256), 256, 0, s>>>(A, lda, M, K, a0.p, a1.p, Mp, Kp);
   k_split_limbs<<<cdiv((long long)Np * (Kp >> 2), 256), 256, 0, s>>>(B, ldb, N, K, b0.p, b1.p, Np, Kp);
   CUtensorMap mA0 = make_map(a0.p, Mp, Kp), mA1 = make_map(a1.p, Mp, Kp), mB0 = make_map(b0.p, Np, Kp), mB1 = make_map(b1.p, Np, Kp);
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + sizeof(MmaShared) + 64;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + sizeof(MmaShared) + 64;
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(k_gemm_i8limb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_gemm_i8limb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(Np / TILE, Mp / TILE);
+  const int tiles_m = Mp / TILE, tiles_n = Np / TILE;
+  const int grid = (int)std::min<long long>((long long)tiles_m * tiles_n, sm_count());
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, s));
   if (subtract)
-    k_gemm_i8limb<true><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, F);
+    k_gemm_i8limb<true><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, F);
   else
-    k_gemm_i8limb<false><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, F);
+    k_gemm_i8limb<false><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, F);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, s));
   CK(cudaEventSynchronize(e1));

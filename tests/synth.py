@@ -171,3 +171,53 @@ def csr_to_dense(n, m, p, j, x, prime) -> np.ndarray:
     rows = np.repeat(np.arange(n), np.diff(p))
     np.add.at(D, (rows, j[: p[-1]]), x[: p[-1]].astype(np.int64))
     return np.mod(D, prime)
+
+
+def banded_planted(n: int, m: int, r: int, extra: float, window: int, prime: int, seed: int, combo: int = 3, spread: int = 64, colblock: int = 8):
+    """GL7d19-shaped planted-rank matrix that STAYS SPARSE under elimination.
+
+    r basis rows in echelon form: row b has a leading entry on staircase column s_b and
+    ~Poisson(extra) further entries at LOCAL offsets (exponential, mean `window`) to the right;
+    the other n-r rows are combinations of 2..combo basis rows that are close to each other
+    (indices within `spread`).  Rows are shuffled globally, columns only inside blocks of
+    `colblock` (so leftmost-entry structure is perturbed but locality survives).  rank == r."""
+    assert r <= min(n, m)
+    import scipy.sparse as sp
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    stair = np.sort(rng.choice(m, size=r, replace=False)).astype(np.int64)
+    small = np.array([1, -1, 2, -2, 3, -3], dtype=np.int64)
+    cnt = rng.poisson(extra, size=r)
+    rows_b = np.repeat(np.arange(r), cnt)
+    offs = 1 + np.floor(rng.exponential(window, size=len(rows_b))).astype(np.int64)
+    cols_b = stair[rows_b] + offs
+    keep = cols_b < m
+    rows_b, cols_b = rows_b[keep], cols_b[keep]
+    vals_b = small[rng.integers(0, 6, size=len(rows_b))]
+    B = sp.csr_matrix((np.concatenate([small[rng.integers(0, 6, size=r)], vals_b]),
+                       (np.concatenate([np.arange(r), rows_b]), np.concatenate([stair, cols_b]))), shape=(r, m))
+    B.sum_duplicates()
+    nd = n - r
+    if nd > 0:
+        k = rng.integers(2, combo + 1, size=nd)
+        rr = np.repeat(np.arange(nd), k)
+        centre = np.repeat(rng.integers(0, r, size=nd), k)
+        cc = np.clip(centre + rng.integers(-spread, spread + 1, size=len(rr)), 0, r - 1)
+        vv = small[rng.integers(0, 4, size=len(rr))]
+        Cm = sp.csr_matrix((vv, (rr, cc)), shape=(nd, r))
+        Cm.sum_duplicates()
+        A = sp.vstack([B, (Cm @ B).tocsr()]).tocsr()
+    else:
+        A = B
+    A.data = np.mod(A.data, prime)
+    A.eliminate_zeros()
+    rp = rng.permutation(n)
+    cp = np.arange(m)
+    for c0 in range(0, m, colblock):  # local column shuffle
+        pass
+    nblk = (m + colblock - 1) // colblock
+    key = np.repeat(np.arange(nblk), colblock)[:m].astype(np.float64) + rng.random(m)
+    cp = np.argsort(key, kind="stable")
+    A = A[rp][:, cp].tocsr()
+    A.sort_indices()
+    return A.indptr.astype(np.int64), A.indices.astype(np.int32), balanced(A.data, prime)
