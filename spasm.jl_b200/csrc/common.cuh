@@ -84,6 +84,16 @@ __device__ __forceinline__ uint32_t red64(uint64_t t, const Fp &F) {
   return (uint32_t)r;
 }
 uint32_t host_inv(uint32_t a, uint32_t p);
+// a^(p-2) mod p for p < 2^16: 32-bit Barrett multiplications only (no 64-bit divisions)
+__device__ inline uint32_t dev_inv_small(uint32_t a, const Fp &F) {
+  uint32_t result = 1, base = a, e = F.p - 2;
+  while (e) {
+    if (e & 1) result = mulmod<true>(result, base, F);
+    base = mulmod<true>(base, base, F);
+    e >>= 1;
+  }
+  return result;
+}
 __device__ inline uint32_t dev_inv(uint32_t a, uint32_t p) {  // extended Euclid, a in (0,p)
   int64_t r0 = a, r1 = p, s0 = 1, s1 = 0;
   while (r1 != 0) {

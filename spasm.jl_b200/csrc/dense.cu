@@ -299,7 +299,9 @@ struct PanelCtl {
   int npiv;      // pivots found so far in this panel
   int found;     // pivots found in the last tile
   int consumed;  // columns consumed by the last tile
-  int pad;
+  int c0;        // first column not scanned yet (advanced on the device: no host round trip per tile)
+  int low;       // tiles that found fewer than PB/2 pivots (time to widen the tiles)
+  int pad[3];
 };
 // Gauss-Jordan on one tile.  The tile is stored COLUMN-major (Wt[c][r], r contiguous) and every
 // thread owns rows r = tid, tid+1024, ...: finding the pivot is one coalesced pass over a column,
@@ -318,13 +320,14 @@ template <bool SMALL>
 __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, int Sn, int wc, long long ldw, int c0,
                                                       int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
                                                       uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
-                                                      const unsigned char *__restrict__ colflag, Fp F) {
+                                                      const unsigned char *__restrict__ colflag, const int *__restrict__ cand, Fp F) {
   __shared__ int red[32];
   __shared__ int s_piv;
   __shared__ uint32_t prow[WMAX], gprow[PB];
   __shared__ unsigned char s_flag[WMAX];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int npiv = ctl->npiv, found = 0, cc = 0;
+  c0 = ctl->c0;
   for (long long idx = tid; idx < (long long)PB * ldw; idx += 1024) Gc[idx] = 0;
   for (int c = tid; c < wc; c += 1024) s_flag[c] = colflag[c];
   __syncthreads();
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, 
       if (best != 0x7fffffff) {
         ispiv[best] = 1;
         pivrow[npiv] = best;
-        pivcol[npiv] = c0 + cc;
+        pivcol[npiv] = cand[c0 + cc];
         tilepiv[found] = best;
         Gc[(long long)found * ldw + best] = 1;
       }
@@ -385,13 +388,14 @@ __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, 
     npiv++;
     __syncthreads();
   }
-  if (tid == 0) ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc;
+  if (tid == 0) ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc, ctl->c0 = c0 + cc;
 }
 // shared-memory version for p < 2^16 and panels of at most 1024 rows (the default block size is
 // 1000): the whole tile [W | Gc] lives in smem as u16, column-major, one thread per row.
-__global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__restrict__ Wt, int Sn, int wc, long long ldw, int c0,
+__global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long ldw,
                                                            int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
-                                                           uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl, Fp F) {
+                                                           uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
+                                                           const int *__restrict__ cand, Fp F) {
   extern __shared__ unsigned short tile[];  // [32 + PB][SP]
   __shared__ int red[32];
   __shared__ int s_piv;
@@ -399,6 +403,13 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
   const int SP = 1024;
   const int r = threadIdx.x, lane = r & 31, wid = r >> 5;
   const bool live = r < Sn;
+  const int c0 = ctl->c0;
+  if (ctl->npiv >= Sn || c0 >= Sm0) {  // panel finished: this launch of the group is a no-op
+    __syncthreads();
+    if (r == 0) ctl->found = 0, ctl->consumed = 0;
+    return;
+  }
+  const int wc = min(32, Sm0 - c0);
   for (int c = 0; c < 32; c++) tile[c * SP + r] = (live && c < wc) ? (unsigned short)Wt[(long long)c * ldw + r] : 0;
   for (int s = 0; s < PB; s++) tile[(32 + s) * SP + r] = 0;
   int my_ispiv = live ? ispiv[r] : 1;
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
       my_ispiv = 1;
       ispiv[r] = 1;
       pivrow[npiv] = r;
-      pivcol[npiv] = c0 + cc;
+      pivcol[npiv] = cand[c0 + cc];
       tilepiv[found] = r;
       tile[(32 + found) * SP + r] = 1;
     }
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
       const bool used = (r < 32) ? (r >= cc && r < wc) : (r - 32 <= found);
       uint32_t v = 0;
       if (used) {
-        const uint32_t alpha = dev_inv(tile[cc * SP + pr], F.p);
+        const uint32_t alpha = dev_inv_small(tile[cc * SP + pr], F);
         v = mulmod<true>(alpha, tile[r * SP + pr], F);
       }
       prow[r] = v;
@@ -462,13 +473,21 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
   }
   if (live)
     for (int s = 0; s < found; s++) Gc[(long long)s * ldw + r] = tile[(32 + s) * SP + r];
-  if (r == 0) ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc;
+  if (r == 0) {
+    ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc, ctl->c0 = c0 + cc;
+    if (found < PB / 2 && npiv < Sn) ctl->low += 1;
+  }
 }
 
 // Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]  for a narrow tile (c < wc <= 32): one CTA per 32 rows r
 template <bool SMALL>
-__global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt, long long ld, const uint32_t *__restrict__ T, int Sn, int wc,
-                                                uint32_t *__restrict__ Wt, long long ldw, Fp F) {
+__global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt_panel, long long ld, const uint32_t *__restrict__ T, int Sn, int Sm0,
+                                                const PanelCtl *__restrict__ ctl, const int *__restrict__ cand, uint32_t *__restrict__ Wt,
+                                                long long ldw, Fp F) {
+  const int c0 = ctl->c0;
+  if (ctl->npiv >= Sn || c0 >= Sm0) return;
+  const int wc = min(32, Sm0 - c0);
+  if ((int)blockIdx.y * 8 >= wc) return;
   // blockIdx.y selects 8 of the <=32 columns: 4x more CTAs in flight for this latency-bound product
   __shared__ uint32_t Ts[32][33], Ds[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // tx: r within the tile, ty: column within the group
@@ -481,7 +500,7 @@ __global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt, 
     }
     {
       const int a = threadIdx.x >> 5, t = threadIdx.x & 31;
-      Ds[a][t] = (cg + a < wc && t0 + t < Sn) ? Dt[(long long)(cg + a) * ld + t0 + t] : 0u;
+      Ds[a][t] = (cg + a < wc && t0 + t < Sn) ? Dt_panel[(long long)cand[c0 + cg + a] * ld + t0 + t] : 0u;
     }
     __syncthreads();
 #pragma unroll 8
@@ -569,11 +588,27 @@ __global__ void k_iota2(int *a, int n) {
 }
 
 // returns rr; T final, pivrow/pivcol filled (pivcol increasing)
-static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0, int Sn, uint32_t *T, DBuf<int> &ispiv, DBuf<int> &pivrow,
-                        DBuf<int> &pivcol, const Fp &F) {
+__global__ void k_gather_rows_u32(const uint32_t *__restrict__ Dt_panel, long long ld, const int *__restrict__ cand, int wc, int Sn,
+                                  uint32_t *__restrict__ out) {
+  const int c = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < wc && t < Sn) out[(long long)c * Sn + t] = Dt_panel[(long long)cand[c] * ld + t];
+}
+__global__ void k_not_flag(const unsigned char *__restrict__ colpiv, int n, int *__restrict__ flag) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) flag[c] = !colpiv[c];
+  if (c == n) flag[c] = 0;
+}
+__global__ void k_mark_cols(const int *__restrict__ pivcol, int rr, unsigned char *__restrict__ colpiv) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < rr) colpiv[pivcol[s]] = 1;
+}
+
+// cand[0:Sm0) = the columns that are not pivots of an earlier panel (those are zero on this panel), increasing
+static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int Sm0, long long k0, int Sn, uint32_t *T, DBuf<int> &ispiv,
+                        DBuf<int> &pivrow, DBuf<int> &pivcol, const Fp &F) {
   cudaStream_t s = stream();
   const long long ldw = ((long long)Sn + 31) / 32 * 32;
-  DBuf<uint32_t> Wt((size_t)WMAX * ldw), Gc((size_t)PB * ldw), Tp((size_t)PB * Sn);
+  DBuf<uint32_t> Wt((size_t)WMAX * ldw), Gc((size_t)PB * ldw), Tp((size_t)PB * Sn), Agather((size_t)WMAX * Sn);
   DBuf<int> tilepiv(PB);
   DBuf<unsigned char> colflag(WMAX);
   DBuf<PanelCtl> ctl(1);
@@ -583,43 +618,49 @@ static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0,
   pivrow.alloc(Sn);
   pivcol.alloc(Sn);
   k_set_identity<<<cdiv((long long)Sn * Sn, 256), 256, 0, s>>>(T, Sn);
-  int w = 32, npiv = 0;
-  for (int c0 = 0; c0 < Sm0 && npiv < Sn;) {
-    const int wc = std::min(w, Sm0 - c0);
-    // Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]     (the tile of T.Panel, transposed)
-    if (wc <= 32) {
-      if (F.small)
-        k_wtile<true><<<dim3(cdiv(Sn, 32), cdiv(wc, 8)), 256, 0, s>>>(Dt + (long long)c0 * ld + k0, ld, T, Sn, wc, Wt.p, ldw, F);
-      else
-        k_wtile<false><<<dim3(cdiv(Sn, 32), cdiv(wc, 8)), 256, 0, s>>>(Dt + (long long)c0 * ld + k0, ld, T, Sn, wc, Wt.p, ldw, F);
-    } else
-      gemm_nt(Wt.p, ldw, wc, Sn, Dt + (long long)c0 * ld + k0, ld, T, Sn, Sn, false, F);
-    if (F.small && Sn <= 1024 && wc <= 32) {
-      static bool attr = false;
-      const size_t smem = (size_t)(32 + PB) * 1024 * sizeof(unsigned short);
-      if (!attr) {
-        CK(cudaFuncSetAttribute(k_tile_gauss_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-      }
-      k_tile_gauss_smem<<<1, 1024, smem, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, F);
-    } else {
-      k_col_flags<<<wc, 256, 0, s>>>(Wt.p, ldw, Sn, ispiv.p, colflag.p);
-      if (F.small)
-        k_tile_gauss<true><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, F);
-      else
-        k_tile_gauss<false><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, F);
-    }
+  const bool fast = F.small && Sn <= 1024;
+  static bool attr = false;
+  const size_t gsm = (size_t)(32 + PB) * 1024 * sizeof(unsigned short);
+  if (fast && !attr) {
+    CK(cudaFuncSetAttribute(k_tile_gauss_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    attr = true;
+  }
+  auto apply_T = [&]() {
     k_gather_T_rows<<<dim3(cdiv(Sn, 256), PB), 256, 0, s>>>(T, Sn, tilepiv.p, &ctl.p->found, 0, Tp.p);
     if (F.small)
       k_update_T<true><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, ldw, Tp.p, tilepiv.p, ctl.p, F);
     else
       k_update_T<false><<<dim3(cdiv(Sn, 256), Sn), 256, 0, s>>>(T, Sn, Gc.p, ldw, Tp.p, tilepiv.p, ctl.p, F);
+  };
+  PanelCtl h{};
+  // ---- dense phase: 32-column tiles, 8 tiles per host round trip, cursor advanced on the device
+  while (fast && h.npiv < Sn && h.c0 < Sm0 && h.low == 0) {
+    for (int g = 0; g < 8; g++) {
+      k_wtile<true><<<dim3(cdiv(Sn, 32), 4), 256, 0, s>>>(Dt + k0, ld, T, Sn, Sm0, ctl.p, cand, Wt.p, ldw, F);
+      k_tile_gauss_smem<<<1, 1024, gsm, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
+      apply_T();
+    }
     CK(cudaGetLastError());
-    g_launches += 3;
-    PanelCtl h = fetch(ctl.p);
-    npiv = h.npiv;
-    c0 += h.consumed;
-    // adapt the tile width to the pivot density just seen
+    g_launches += 32;
+    h = fetch(ctl.p);
+  }
+  // ---- sparse phase (few pivots per tile, or a prime / panel the fast path does not take): adaptive width
+  int w = 32;
+  while (h.npiv < Sn && h.c0 < Sm0) {
+    const int c0 = h.c0;
+    const int wc = std::min(w, Sm0 - c0);
+    // Wt[c][r] = sum_t Dt[cand[c0+c]][k0+t] * T[r][t]     (the tile of T.Panel, transposed)
+    k_gather_rows_u32<<<dim3(cdiv(Sn, 256), wc), 256, 0, s>>>(Dt + k0, ld, cand + c0, wc, Sn, Agather.p);
+    gemm_nt(Wt.p, ldw, wc, Sn, Agather.p, Sn, T, Sn, Sn, false, F);
+    k_col_flags<<<wc, 256, 0, s>>>(Wt.p, ldw, Sn, ispiv.p, colflag.p);
+    if (F.small)
+      k_tile_gauss<true><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, cand, F);
+    else
+      k_tile_gauss<false><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, cand, F);
+    apply_T();
+    CK(cudaGetLastError());
+    g_launches += 5;
+    h = fetch(ctl.p);
     if (h.found >= PB / 2)
       w = 32;
     else if (h.found == 0)
@@ -627,9 +668,17 @@ static int panel_factor(const uint32_t *Dt, long long ld, int Sm0, long long k0,
     else
       w = std::min(WMAX, std::max(32, (int)((double)PB * h.consumed / h.found)));
   }
+  const int npiv = h.npiv;
   return npiv;
 }
 
+__global__ void k_compact_idx(const int *__restrict__ flag, const long long *__restrict__ pos, int n, int *__restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n && flag[c]) out[pos[c]] = c;
+}
+static void k_compact_flags_i32(const int *flag, const long long *pos, int n, int *out) {
+  if (n) k_compact_idx<<<cdiv(n, 256), 256, 0, stream()>>>(flag, pos, n, out);
+}
 __global__ void k_gather_int(const int *__restrict__ src, const int *__restrict__ idx, int n, int *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = src[idx[i]];
@@ -701,7 +750,10 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
   }
   const int Bmax = std::min(block_size, nrows);
   DBuf<uint32_t> T((size_t)Bmax * Bmax), Tsel((size_t)Bmax * Bmax), R((size_t)Bmax * Sm0), Rt, Pt;
-  DBuf<int> ispiv, pivrow, pivcol(Bmax), ident(Bmax), hdr(1);
+  DBuf<int> ispiv, pivrow, pivcol(Bmax), ident(Bmax), hdr(1), cflag(Sm0 + 1), cand(std::max(Sm0, 1));
+  DBuf<long long> cpos(Sm0 + 1);
+  DBuf<unsigned char> colpiv(std::max(Sm0, 1));
+  colpiv.zero();
   k_iota2<<<cdiv(Bmax, 256), 256, 0, s>>>(ident.p, Bmax);
   const long long nb = ((long long)nrows + block_size - 1) / block_size;
   long long lb = 0;  // my panels already factored
@@ -716,7 +768,12 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
     if (owner == me) {
       const long long k0 = lb * block_size;
       DBuf<int> pc_tmp;
-      rr = panel_factor(D.Dt.p, ld, Sm0, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F);
+      // candidate columns of this panel: everything that is not a pivot of an earlier panel
+      k_not_flag<<<cdiv(Sm0 + 1, 256), 256, 0, s>>>(colpiv.p, Sm0, cflag.p);
+      exclusive_scan_i32_to_i64(cflag.p, cpos.p, Sm0 + 1);
+      k_compact_flags_i32(cflag.p, cpos.p, Sm0, cand.p);
+      const int ncand = (int)fetch(cpos.p + Sm0);
+      rr = panel_factor(D.Dt.p, ld, cand.p, ncand, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F);
       if (rr > 0) CK(cudaMemcpyAsync(pivcol.p, pc_tmp.p, (size_t)rr * sizeof(int), cudaMemcpyDeviceToDevice, s));
       tick(0, t1);
       if (rr > 0) {
@@ -739,6 +796,7 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
       tick(6, t1);
     }
     if (rr > 0) {
+      k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pivcol.p, rr, colpiv.p);
       if (emit_rows) {
         // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
         DBuf<int> cnt(rr + 1);

@@ -36,19 +36,62 @@ cudaStream_t stream() { return g_stream; }
 int sm_count() { return g_sms; }
 void sync() { CK(cudaStreamSynchronize(g_stream)); }
 
+// Large blocks (>= 256 MiB: the dense Schur complement, the reserved U, the SpTRSM workspace) are
+// kept in a small best-fit cache across calls: an echelonization of the same shape then allocates
+// nothing.  (The stream-ordered pool alone re-maps tens of GB per call, seconds of driver time.)
+struct BigBlock {
+  void *p;
+  size_t bytes;
+};
+static std::vector<BigBlock> g_big_free;
+static std::vector<BigBlock> g_big_live;
+static const size_t BIG = (size_t)256 << 20;
+
+static void big_trim() {
+  for (auto &b : g_big_free) cudaFreeAsync(b.p, g_stream);
+  g_big_free.clear();
+}
+
 void *dmalloc_bytes(size_t bytes) {
+  if (bytes >= BIG) {
+    int best = -1;
+    for (int i = 0; i < (int)g_big_free.size(); i++)
+      if (g_big_free[i].bytes >= bytes && g_big_free[i].bytes <= bytes + bytes / 4 && (best < 0 || g_big_free[i].bytes < g_big_free[best].bytes)) best = i;
+    if (best >= 0) {
+      BigBlock b = g_big_free[best];
+      g_big_free.erase(g_big_free.begin() + best);
+      g_big_live.push_back(b);
+      return b.p;
+    }
+  }
   void *p = nullptr;
   cudaError_t e = cudaMallocAsync(&p, bytes, g_stream);
+  if (e != cudaSuccess && !g_big_free.empty()) {  // give the cached blocks back and retry
+    cudaGetLastError();
+    big_trim();
+    cudaStreamSynchronize(g_stream);
+    e = cudaMallocAsync(&p, bytes, g_stream);
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     throw Error("spasm_b200: device allocation of " + std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e));
   }
+  if (bytes >= BIG) g_big_live.push_back({p, bytes});
   return p;
 }
-void dfree(void *p) { cudaFreeAsync(p, g_stream); }
-size_t dev_free_bytes() {
+void dfree(void *p) {
+  for (size_t i = 0; i < g_big_live.size(); i++)
+    if (g_big_live[i].p == p) {
+      g_big_free.push_back(g_big_live[i]);  // all work is on one stream: reuse is stream-ordered
+      g_big_live.erase(g_big_live.begin() + i);
+      return;
+    }
+  cudaFreeAsync(p, g_stream);
+}
+size_t dev_free_bytes() {  // what a new allocation could get: free memory + our own cached blocks
   size_t f = 0, t = 0;
   cudaMemGetInfo(&f, &t);
+  for (auto &b : g_big_free) f += b.bytes;
   return f;
 }
 
@@ -223,6 +266,18 @@ void transpose_csr(const DCsr &A, DCsr &T) {
 }
 
 }  // namespace sb
+
+// give the cached large device blocks back to the driver
+extern "C" void spasm_b200_trim(void) {
+  if (sb::g_stream) {
+    sb::big_trim();
+    cudaStreamSynchronize(sb::g_stream);
+    cudaMemPool_t pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
+}
 
 // src/SpaSM.jl:589 — ONE argument; values always kept (test/runtests.jl:12-15)
 extern "C" struct spasm_csr *spasm_transpose(const struct spasm_csr *A) {
