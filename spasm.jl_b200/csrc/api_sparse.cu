@@ -145,7 +145,7 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
     build_pdesc_U(f.U, f.qinv.p, pdesc);
     DBuf<int> rows(n);
     rows.upload(p, n);
-    SolveSystem G{f.U.j.p, f.U.x.p, pdesc.p, f.U.m};
+    SolveSystem G{f.U.j.p, f.U.x.p, pdesc.p, f.U.m, &f.U, f.qinv.p};
     SolveRows B{dA.p.p, dA.j.p, dA.x.p, rows.p, n, nullptr};
     SolveEmit E;
     E.want_L = (L != nullptr);

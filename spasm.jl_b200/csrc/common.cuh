@@ -20,6 +20,7 @@ struct Error : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
 
+extern const char *g_phase;  // what the library was doing (for error messages)
 void logf(const char *fmt, ...);  // -> logcallback or stderr (host_abi.cu)
 void errf(const char *fmt, ...);  // errors: always stderr, and the callback when installed
 

@@ -101,8 +101,13 @@ __global__ void __launch_bounds__(256) k_sptrsm(const long long *__restrict__ Tp
 }
 
 void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U, const int *Uqinv, const Fp &F, DenseSchur &D) {
+  build_dense_schur_raw(A.p.p, A.j.p, A.x.p, A.m, rows, nrows, U, Uqinv, F, D, false);
+}
+
+void build_dense_schur_raw(const long long *Ap, const int *Aj, const uint32_t *Ax, int m_, const int *rows, int nrows, const DCsr &U,
+                           const int *Uqinv, const Fp &F, DenseSchur &D, bool keep_pivot_part) {
   cudaStream_t s = stream();
-  const int m = A.m, r = U.n;
+  const int m = m_, r = U.n;
   D.n_rem = nrows;
   D.Sm0 = m - r;
   D.ld = ((long long)nrows + 63) / 64 * 64;
@@ -160,6 +165,7 @@ void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U,
     fit = fit / 256 * 256;
     if (fit < 256) throw Error("dense engine: not enough device memory for the pivot part");
     kc_max = std::min<long long>(nrows, fit);
+    if (keep_pivot_part && kc_max < nrows) throw Error("dense engine: chunk too large to keep the multipliers");
   }
   DBuf<uint32_t> Vp((size_t)std::max(r, 1) * kc_max);
   DBuf<int> freelist(std::max(D.Sm0, 1));
@@ -167,7 +173,7 @@ void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U,
   for (long long k0 = 0; k0 < nrows; k0 += kc_max) {
     const int kc = (int)std::min<long long>(kc_max, nrows - k0);
     if (r > 0) CK(cudaMemsetAsync(Vp.p, 0, (size_t)r * kc_max * 4, s));
-    k_scatter_rows_T<<<cdiv((long long)kc * 32, 256), 256, 0, s>>>(A.p.p, A.j.p, A.x.p, rows, (int)k0, kc, Uqinv, qpos.p, Vp.p, kc_max, D.Dt.p, D.ld);
+    k_scatter_rows_T<<<cdiv((long long)kc * 32, 256), 256, 0, s>>>(Ap, Aj, Ax, rows, (int)k0, kc, Uqinv, qpos.p, Vp.p, kc_max, D.Dt.p, D.ld);
     const int ktiles = cdiv(kc, 256);
     int off = r > 0 ? hist_h[0] : 0;
     for (int L = 1; L <= maxlev; L++) {
@@ -191,7 +197,57 @@ void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U,
     CK(cudaGetLastError());
   }
   D.levels = maxlev + 1;
+  if (keep_pivot_part) {
+    D.ldv = kc_max;
+    D.Vp = std::move(Vp);
+  }
   sync();
+}
+
+// ---- dense rows back to sorted sparse rows (the heavy tier of the row-solve engine)
+__global__ void k_dense_count(const uint32_t *__restrict__ M, long long ld, int nvec, int nrows, const int *__restrict__ todo, int off,
+                              int *__restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  int c = 0;
+  for (int v = 0; v < nvec; v++) c += (M[(long long)v * ld + i] != 0);
+  cnt[todo[off + i]] = c;
+}
+__global__ void k_dense_write(const uint32_t *__restrict__ M, long long ld, int nvec, int nrows, const int *__restrict__ todo, int off,
+                              const int *__restrict__ label, const long long *__restrict__ pos, int *__restrict__ oj,
+                              uint32_t *__restrict__ ox, unsigned long long *__restrict__ offs, unsigned long long slab_tag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  long long w = pos[i];
+  offs[todo[off + i]] = slab_tag | (unsigned long long)w;
+  for (int v = 0; v < nvec; v++) {
+    const uint32_t x = M[(long long)v * ld + i];
+    if (x != 0) {
+      oj[w] = label ? label[v] : v;
+      ox[w] = x;
+      w++;
+    }
+  }
+}
+__global__ void k_gather_cnt(const int *__restrict__ cnt, const int *__restrict__ todo, int off, int n, int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cnt[todo[off + i]];
+  if (i == n) out[i] = 0;
+}
+
+void dense_rows_to_sparse(const uint32_t *M, long long ld, int nvec, const int *label, int nrows, const int *todo, int off, int *cnt,
+                          unsigned long long *offs, unsigned long long slab_tag, DBuf<int> &oj, DBuf<uint32_t> &ox) {
+  cudaStream_t s = stream();
+  k_dense_count<<<cdiv(nrows, 256), 256, 0, s>>>(M, ld, nvec, nrows, todo, off, cnt);
+  DBuf<int> c2(nrows + 1);
+  DBuf<long long> pos(nrows + 1);
+  k_gather_cnt<<<cdiv(nrows + 1, 256), 256, 0, s>>>(cnt, todo, off, nrows, c2.p);
+  exclusive_scan_i32_to_i64(c2.p, pos.p, nrows + 1);
+  const long long tot = fetch(pos.p + nrows);
+  oj.alloc(std::max<long long>(tot, 1));
+  ox.alloc(std::max<long long>(tot, 1));
+  k_dense_write<<<cdiv(nrows, 256), 256, 0, s>>>(M, ld, nvec, nrows, todo, off, label, pos.p, oj.p, ox.p, offs, slab_tag);
+  CK(cudaGetLastError());
 }
 
 }  // namespace sb

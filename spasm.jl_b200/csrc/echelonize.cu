@@ -194,7 +194,7 @@ static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, in
     }
     const int wn = std::min(batch, nrows - done);
     build_pdesc_U(E.U, E.Uqinv.p, pdesc);
-    SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m};
+    SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m, &E.U, E.Uqinv.p};
     SolveRows B{cur.p.p, cur.j.p, cur.x.p, rows_dev + done, wn, nullptr};
     SolveEmit Em;
     Em.want_L = (E.L != nullptr);
@@ -308,6 +308,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     logf("[echelonize] round %d\n", round);
     g_timings[10] += 1;
     double t0 = spasm_wtime();
+    g_phase = "structural pivots";
     npiv = structural_round(E, *cur, p_in, opts->enable_greedy_pivot_search, P);
     E.t_pivots += spasm_wtime() - t0;
     const int rem_rows = n - npiv, rem_cols = m - E.U.n;
@@ -321,6 +322,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
       break;
     }
     t0 = spasm_wtime();
+    g_phase = "density estimate";
     density = estimate_density(E, *cur, P.p.p + npiv, rem_rows, 100);
     g_timings[6] += spasm_wtime() - t0, t0 = spasm_wtime();
     logf("Schur complement is %d x %d, estimated density : %.2f (%lld byte)\n", rem_rows, rem_cols, density,
@@ -331,9 +333,10 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
       break;
     }
     // ---- Schur complement on the non-pivotal rows
+    g_phase = "schur complement";
     DBuf<PDesc> pdesc;
     build_pdesc_U(E.U, E.Uqinv.p, pdesc);
-    SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m};
+    SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m, &E.U, E.Uqinv.p};
     SolveRows B{cur->p.p, cur->j.p, cur->x.p, P.p.p + npiv, rem_rows, nullptr};
     SolveEmit Em;
     Em.want_L = (E.L != nullptr);
@@ -382,6 +385,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
       for (int k = 0; k < rem_rows; k++) orig[k] = p_in.empty() ? hp[k] : p_in[hp[k]];
     }
     const double t0 = spasm_wtime();
+    g_phase = "finish (GPLU / dense tail)";
     if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
       echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
     else if (opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
@@ -397,6 +401,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     g_timings[8] = E.t_tail;
   }
   const double t_dl = spasm_wtime();
+  g_phase = "download";
   if (rank_out) *rank_out = E.U.n;
   if (!download) {  // device-resident timing mode (bench.py `value`): the factor is dropped on the device
     g_timings[0] = spasm_wtime() - start;
@@ -461,7 +466,7 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
   try {
     return echelonize_impl(A, opts);
   } catch (const std::exception &e) {
-    errf("[spasm_b200] spasm_echelonize failed: %s\n", e.what());
+    errf("[spasm_b200] spasm_echelonize failed during %s: %s\n", g_phase, e.what());
     return nullptr;
   }
 }

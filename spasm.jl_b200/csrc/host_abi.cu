@@ -16,6 +16,7 @@ const char *spasm_b200_backend(void) { return "cuda-sm_100a"; }
 }
 
 namespace sb {
+const char *g_phase = "";
 void logf(const char *fmt, ...) {
   char buf[1024];
   va_list ap;

@@ -74,7 +74,10 @@ void *dmalloc_bytes(size_t bytes) {
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
-    throw Error("spasm_b200: device allocation of " + std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e));
+    size_t f = 0, t = 0;
+    cudaMemGetInfo(&f, &t);
+    throw Error("spasm_b200: device allocation of " + std::to_string(bytes >> 20) + " MiB failed (" + std::to_string(f >> 20) + " MiB free): " +
+                cudaGetErrorString(e));
   }
   if (bytes >= BIG) g_big_live.push_back({p, bytes});
   return p;

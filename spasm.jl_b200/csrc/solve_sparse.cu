@@ -20,6 +20,8 @@
 // the accumulator as a direct-indexed array in global memory with a bitmap priority queue.
 #include "solve_sparse.cuh"
 
+#include "dense.cuh"
+
 namespace sb {
 
 static constexpr int EMPTY = -1;
@@ -585,13 +587,17 @@ __global__ void k_collect_status(const int *__restrict__ status, const int *__re
   int k = todo ? todo[i] : i;
   if (status[k] == want) out[atomicAdd(nout, 1)] = k;
 }
+__global__ void k_gather_rows_sel(const int *__restrict__ rows, const int *__restrict__ todo, int n, int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = rows ? rows[todo[i]] : todo[i];
+}
 __global__ void k_fill(int *a, int n, int v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
 }
 struct SlabPtrs {
-  const int *j[16];
-  const uint32_t *x[16];
+  const int *j[64];
+  const uint32_t *x[64];
 };
 __global__ void k_gather_rows(const int *__restrict__ cnt, const unsigned long long *__restrict__ off,
                               const long long *__restrict__ p, int nrows, SlabPtrs S, int *__restrict__ oj,
@@ -675,13 +681,13 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
   DBuf<unsigned> gbitmap;
   int nprio = 0;
 
-  for (int tier = 0; tier < 3 && ntodo > 0; tier++) {
+  for (int tier = 0; tier < 4 && ntodo > 0; tier++) {
     long long need = guess, lneed = guess;
     for (int attempt = 0; attempt < 4 && ntodo > 0; attempt++) {
       // fresh slab for this launch
       unsigned long long h_ctrs[8];
       if (!E.count_only) {
-        if (slabs_j.size() >= 16) throw Error("solve_rows: too many slabs");
+        if (slabs_j.size() >= 60) throw Error("solve_rows: too many slabs");
         slabs_j.emplace_back((size_t)need);
         slabs_x.emplace_back((size_t)need);
         a.oj = slabs_j.back().p, a.ox = slabs_x.back().p, a.cap = need;
@@ -711,6 +717,20 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
         }
         R.stats.light += ntodo;
       } else if (tier == 1) {
+        // still one warp per row, 4x the table: rows with a few hundred to ~1700 distinct columns
+        constexpr int H = 2048, PC = 512;
+        size_t smem = 8 * (size_t)(2 * H + 3 * PC) * 4 + 32 * 8 + 64 * 4;
+        int blocks = std::min(cdiv(ntodo, 8), sms);
+        if (F.small) {
+          CK(cudaFuncSetAttribute(k_solve_smem<32, H, PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_solve_smem<32, H, PC, true><<<blocks, 256, smem, stream()>>>(a);
+        } else {
+          CK(cudaFuncSetAttribute(k_solve_smem<32, H, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_solve_smem<32, H, PC, false><<<blocks, 256, smem, stream()>>>(a);
+        }
+        R.stats.light += 0;
+        R.stats.medium += ntodo;
+      } else if (tier == 2) {
         constexpr int H = 16384, PC = 4096;
         size_t smem = (size_t)(2 * H + 3 * PC) * 4 + 32 * 8 + 64 * 4;
         int blocks = std::min(ntodo, sms);
@@ -785,6 +805,44 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
     if (ntodo > 0) {
       // mark them pending so a later tier's collect does not see stale states
       guess = std::max<long long>(guess, 1024LL * ntodo);
+    }
+    if (tier == 1 && ntodo >= 2048 && G.U_dense != nullptr &&  // (a small batch does not amortise the transpose + level schedule)
+        E.prefix_col == nullptr && B.mask == nullptr && !E.structural && !E.all_columns) {
+      // ---- heavy rows of an x.U = b solve: all at once through the SpTRSM engine, in chunks that fit
+      const DCsr &U = *G.U_dense;
+      const int Sm0 = G.width - U.n, r = U.n;
+      DBuf<int> rows_sel(ntodo);
+      k_gather_rows_sel<<<cdiv(ntodo, 256), 256, 0, stream()>>>(B.rows, todo, ntodo, rows_sel.p);
+      const size_t per_row = ((size_t)Sm0 + (size_t)std::max(r, 1)) * 4 + 64;
+      long long ch = (long long)(dev_free_bytes() * 2 / 5 / per_row);
+      ch = std::max<long long>(256, std::min<long long>(ch / 256 * 256, ntodo));
+      DBuf<int> ident;
+      for (int off2 = 0; off2 < ntodo; off2 += (int)ch) {
+        const int nr = (int)std::min<long long>(ch, ntodo - off2);
+        DenseSchur D;
+        build_dense_schur_raw(B.Bp, B.Bj, B.Bx, G.width, rows_sel.p + off2, nr, U, G.qinv_dense, F, D, E.want_L);
+        if (E.count_only) {
+          DBuf<int> oj0;
+          DBuf<uint32_t> ox0;
+          dense_rows_to_sparse(D.Dt.p, D.ld, D.Sm0, D.q0.p, nr, todo, off2, R.cnt.p, off.p, 0, oj0, ox0);
+        } else {
+          if (slabs_j.size() >= 60) throw Error("solve_rows: too many slabs");
+          slabs_j.emplace_back();
+          slabs_x.emplace_back();
+          const unsigned long long sid = slabs_j.size() - 1;
+          if (E.want_L) slabs_lj.emplace_back(), slabs_lx.emplace_back();
+          dense_rows_to_sparse(D.Dt.p, D.ld, D.Sm0, D.q0.p, nr, todo, off2, R.cnt.p, off.p, sid << 56, slabs_j.back(), slabs_x.back());
+          SP.j[sid] = slabs_j.back().p, SP.x[sid] = slabs_x.back().p;
+          if (E.want_L) {
+            dense_rows_to_sparse(D.Vp.p, D.ldv, r, nullptr, nr, todo, off2, R.lcnt.p, loff.p, sid << 56, slabs_lj.back(), slabs_lx.back());
+            LSP.j[sid] = slabs_lj.back().p, LSP.x[sid] = slabs_lx.back().p;
+          }
+        }
+        R.stats.heavy += nr;
+        g_launches += 8;
+      }
+      ntodo = 0;
+      break;
     }
   }
   if (ntodo > 0) throw Error("solve_rows: rows left unsolved after the heavy tier");

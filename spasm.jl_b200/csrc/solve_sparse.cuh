@@ -21,6 +21,10 @@ struct SolveSystem {
   const uint32_t *Gx = nullptr;
   const PDesc *pdesc = nullptr;
   int width = 0;  // number of columns of the solution vector x
+  // when the system is x.U = b, rows that overflow the warp tiers are eliminated all at once by the
+  // column-major SpTRSM engine (dense_engine.cu) and converted back to sorted sparse rows
+  const DCsr *U_dense = nullptr;
+  const int *qinv_dense = nullptr;
 };
 
 struct SolveRows {

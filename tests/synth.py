@@ -221,3 +221,57 @@ def banded_planted(n: int, m: int, r: int, extra: float, window: int, prime: int
     A = A[rp][:, cp].tocsr()
     A.sort_indices()
     return A.indptr.astype(np.int64), A.indices.astype(np.int32), balanced(A.data, prime)
+
+
+def sparse_chain_planted(n: int, m: int, r: int, extra: float, link: float, window: int, prime: int, seed: int, combo: int = 3, spread: int = 64):
+    """GL7d19-shaped planted-rank matrix with SHORT elimination chains (stays sparse at any scale).
+
+    Columns are split into r staircase columns (one per basis row) and m-r free columns.  Basis row b
+    has its leading entry on its staircase column, ~Poisson(extra) entries on FREE columns within a
+    local window and ~Poisson(link) < 1 entries on later staircase columns, so the pivot graph is
+    sub-critical: every row reaches O(1/(1-link)) pivot rows whatever the size.  The other n-r rows are
+    combinations of 2..combo nearby basis rows.  Rows are shuffled globally.  rank == r."""
+    assert r <= min(n, m) and link < 1.0
+    import scipy.sparse as sp
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    is_stair = np.zeros(m, dtype=bool)
+    stair = np.sort(rng.choice(m, size=r, replace=False)).astype(np.int64)
+    is_stair[stair] = True
+    free = np.nonzero(~is_stair)[0].astype(np.int64)
+    nf = len(free)
+    # position of each staircase column among the free columns (for local windows)
+    fpos = np.searchsorted(free, stair)
+    small = np.array([1, -1, 2, -2, 3, -3], dtype=np.int64)
+    cnt = rng.poisson(extra, size=r)
+    rows_f = np.repeat(np.arange(r), cnt)
+    idx = np.clip(fpos[rows_f] + rng.integers(-window, window + 1, size=len(rows_f)), 0, max(nf - 1, 0))
+    cols_f = free[idx] if nf else np.zeros(0, dtype=np.int64)
+    lk = rng.poisson(link, size=r)
+    rows_l = np.repeat(np.arange(r), lk)
+    tgt = rows_l + 1 + rng.integers(0, window, size=len(rows_l))
+    ok = tgt < r
+    rows_l, cols_l = rows_l[ok], stair[tgt[ok]]
+    rows_all = np.concatenate([np.arange(r), rows_f, rows_l])
+    cols_all = np.concatenate([stair, cols_f, cols_l])
+    vals_all = small[rng.integers(0, 6, size=len(rows_all))]
+    B = sp.csr_matrix((vals_all, (rows_all, cols_all)), shape=(r, m))
+    B.sum_duplicates()
+    B.data[B.data == 0] = 1
+    nd = n - r
+    if nd > 0:
+        k = rng.integers(2, combo + 1, size=nd)
+        rr = np.repeat(np.arange(nd), k)
+        centre = np.repeat(rng.integers(0, r, size=nd), k)
+        cc = np.clip(centre + rng.integers(-spread, spread + 1, size=len(rr)), 0, r - 1)
+        vv = small[rng.integers(0, 4, size=len(rr))]
+        Cm = sp.csr_matrix((vv, (rr, cc)), shape=(nd, r))
+        Cm.sum_duplicates()
+        A = sp.vstack([B, (Cm @ B).tocsr()]).tocsr()
+    else:
+        A = B
+    A.data = np.mod(A.data, prime)
+    A.eliminate_zeros()
+    A = A[rng.permutation(n)].tocsr()
+    A.sort_indices()
+    return A.indptr.astype(np.int64), A.indices.astype(np.int32), balanced(A.data, prime)

@@ -174,3 +174,19 @@ def test_medium_scale_c1_like(gpu, oracle):
     Ko, Kg = oracle.kernel(fo), gpu.kernel(fg)
     for a, b in zip(Ko.arrays(), Kg.arrays()):
         assert np.array_equal(a, b)
+
+
+def test_gl7d19_shaped_sparse_regime(gpu, oracle):
+    """configs[2] at 1/128 scale (banded planted-rank generator): stays sparse, so the rounds of
+    structural pivots + sparse Schur complement + GPLU tail all run; rank known by construction;
+    every array bit-exact against the oracle"""
+    s = 128
+    n, m, r = 1911130 // s, 1955309 // s, 1033568 // s
+    p, j, x = synth.banded_planted(n, m, r, 12.0, 40, 42013, 0x5A5A0003, spread=16, colblock=8)
+    A = gpu.from_arrays(n, m, p, j, x, 42013)
+    fo, fg = oracle.echelonize(A), gpu.echelonize(A)
+    assert fg.r == r
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg))
+    checks.check_U_structure(gpu, fg)
+    fo2, fg2 = oracle.echelonize(A, L=True), gpu.echelonize(A, L=True)
+    checks.assert_same(checks.lu_arrays(fo2), checks.lu_arrays(fg2), "L: ")

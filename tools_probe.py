@@ -33,7 +33,7 @@ def run(tag, n, m, p, j, x, prime=42013, kernel=False, **kw):
 
 for arg in sys.argv[1:]:
     kind, _, size = arg.partition(":")
-    if kind == "gemm":
+    if kind in ("gemm", "c3b", "dense"):
         continue
     s = int(size)
     if kind == "c1":
@@ -76,3 +76,32 @@ def gemm_bench(M, N, K, prime=42013):
 for arg in sys.argv[1:]:
     if arg.startswith("gemm:"):
         gemm_bench(*map(int, arg[5:].split(",")))
+
+for arg in sys.argv[1:]:
+    kind, _, size = arg.partition(":")
+    if kind == "c3b":  # banded planted-rank GL7d19-shaped, scale 1/size
+        s_ = int(size)
+        n, m, r = 1911130 // s_, 1955309 // s_, 1033568 // s_
+        t = time.time()
+        pjx = synth.banded_planted(n, m, r, 12.0, 40, 42013, 0x5A5A0003, spread=16, colblock=8)
+        print(f"   generated in {time.time()-t:.1f}s nnz/row={pjx[0][-1]/n:.1f} expected rank {r}", flush=True)
+        f = run(arg, n, m, *pjx)
+        assert f.r == r, (f.r, r)
+        L = (C.c_longlong * 7)()
+        g.lib.spasm_b200_last_stats.argtypes = [C.POINTER(C.c_longlong)]
+        g.lib.spasm_b200_last_stats(L)
+        if L[6] > 0:
+            print(f"   last Schur: bytes={L[0]/1e9:.3f} GB macs={L[1]/1e9:.3f} G rows={L[2]} light={L[3]} medium={L[4]} heavy={L[5]} "
+                  f"time={L[6]/1e3:.1f} ms -> {L[0]/(L[6]*1e-6)/1e9:.1f} GB/s algorithmic", flush=True)
+    elif kind == "dense":
+        n = int(size)
+        D = synth.dense_random(n, n, 65521, 0x5A5A0004)
+        import scipy.sparse as sp
+        A = g.CSR(sp.csc_matrix(D.T.astype(np.int64)), 65521)
+        t = time.time()
+        f = g.echelonize(A)
+        dt = time.time() - t
+        T = (C.c_double * 16)()
+        g.lib.spasm_b200_last_timings(T)
+        print(f"== dense {n}x{n} mod 65521: rank={f.r} wall={dt:.3f}s  LU-equivalent {2*n**3/3/dt/1e12:.2f} T mod-p OP/s", flush=True)
+        print("   " + " ".join(f"{k}={v:.4g}" for k, v in zip(NAMES, T)), flush=True)
