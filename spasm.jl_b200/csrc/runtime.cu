@@ -129,6 +129,7 @@ long long reduce_sum_i32(const int *in, size_t n) {
 // malloc'd destinations are pageable and mostly untouched: a plain cudaMemcpy runs at ~2 GB/s
 // (page faults on one thread).  Bounce through two pinned buffers and let every host thread fault
 // and fill its slice of the destination.
+static int g_copy_threads = std::max(1, std::min(16, omp_get_num_procs()));
 void download_large(void *dst, const void *src_dev, size_t bytes) {
   const size_t CH = (size_t)128 << 20;
   if (bytes < CH / 2) {
@@ -157,7 +158,8 @@ void download_large(void *dst, const void *src_dev, size_t bytes) {
     const size_t off = c * CH, len = std::min(CH, bytes - off);
     char *d = (char *)dst + off;
     const char *srcp = (const char *)pin[c & 1];
-#pragma omp parallel for schedule(static)
+    // explicit thread count: launchers such as torchrun export OMP_NUM_THREADS=1
+#pragma omp parallel for schedule(static) num_threads(g_copy_threads)
     for (long long b = 0; b < (long long)((len + (1 << 20) - 1) >> 20); b++) {
       size_t o = (size_t)b << 20, l = std::min((size_t)1 << 20, len - o);
       memcpy(d + o, srcp + o, l);
