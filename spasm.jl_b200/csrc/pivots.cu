@@ -151,7 +151,10 @@ __device__ __forceinline__ int claim(unsigned short *marks, int jj, unsigned gen
 
 // Expand queued pivotal columns until the queue is empty or no candidate survives.  Up to 32 queue
 // entries are expanded together: lane l owns entry head+l, and the entries of those pivot rows are
-// walked as one flattened index space, 32 at a time (full lanes even though rows are short).
+// walked as one flattened index space, 32 at a time (full lanes even though rows are short).  The
+// column index of the NEXT chunk is fetched while the current one is resolved, and duplicates inside
+// a chunk are settled with __match_any (no atomics: the marks are private to the row), so the
+// dependent chain per chunk is one round trip (mark + qinv loads issue together).
 __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *marks, int *q, int &head, int &tail, int &surviving,
                                         unsigned gen, int lane) {
   while (head < tail && surviving > 0) {
@@ -174,11 +177,9 @@ __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *mar
       if (lane >= o) inc += v;
     }
     const int total = __shfl_sync(0xffffffffu, inc, 31);
-    for (int f0 = 0; f0 < total; f0 += 32) {
+    auto fetch_col = [&](int f0) -> int {
       const int f = f0 + lane;
       const int fc = min(f, total - 1);
-      int push = 0, killed = 0, jj = 0;
-      // owner lane = number of lanes whose inclusive prefix is <= fc (all lanes take part)
       int lo = 0;
 #pragma unroll
       for (int step = 16; step >= 1; step >>= 1) {
@@ -187,10 +188,24 @@ __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *mar
       }
       const int excl = __shfl_sync(0xffffffffu, inc - len, lo);
       const long long base = __shfl_sync(0xffffffffu, a, lo);
-      if (f < total) {
-        jj = g.Aj[base + (f - excl)];
+      return (f < total) ? g.Aj[base + (f - excl)] : -1;
+    };
+    int jj_next = total > 0 ? fetch_col(0) : -1;
+    for (int f0 = 0; f0 < total; f0 += 32) {
+      const int jj = jj_next;
+      if (f0 + 32 < total) jj_next = fetch_col(f0 + 32);  // in flight while this chunk is resolved
+      int push = 0, killed = 0;
+      if (jj >= 0) {
+        const unsigned short cur = marks[jj];
         const bool piv = __ldcg(&g.qinv[jj]) >= 0;
-        if (claim(marks, jj, gen, piv ? ST_EXP : ST_SEEN, killed)) push = piv;
+        const unsigned st = mark_state(cur, gen);
+        // one lane per distinct column acts
+        const unsigned same = __match_any_sync(__activemask(), jj);
+        if ((st == 0 || st == ST_CAND) && lane == __ffs(same) - 1) {
+          killed = (st == ST_CAND);
+          marks[jj] = (unsigned short)((gen << 2) | (piv ? ST_EXP : ST_SEEN));
+          push = piv;
+        }
       }
       unsigned pm = __ballot_sync(0xffffffffu, push);
       surviving -= __popc(__ballot_sync(0xffffffffu, killed));
@@ -241,7 +256,16 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
       tail += __popc(pm);
     }
     __syncwarp();
+    unsigned long long tb = 0, te = 0;
+    if (g.prof && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
     bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+    if (g.prof && lane == 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te));
+      atomicMax(g.prof + 0, te - tb);                 // longest speculative BFS (ns)
+      atomicAdd(g.prof + 1, te - tb);                 // sum over rows
+      atomicAdd(g.prof + 2, (unsigned long long)tail);  // pivot rows expanded
+      if (surviving > 0) atomicAdd(g.prof + 3, 1ULL);   // rows alive after speculation
+    }
   }
   int applied = 0;
   unsigned backoff = 32;
@@ -825,7 +849,6 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
       ctr.zero();
       DBuf<unsigned long long> prof(8);
       prof.zero();
-      CK(cudaMemsetAsync(prof.p + 1, 0xff, 8, s));
       GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, queue.p, qcap, surv.p, head.p, tail.p, ctl.p, newcol.p, ctr.p, prof.p};
       unsigned gen = 1;
       for (int w0 = 0; w0 < ncand; w0 += W) {
@@ -848,8 +871,8 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
         prof.download(hp, 8);
         sync();
         if (getenv("SPASM_B200_PROFILE"))
-          fprintf(stderr, "[greedy] windows=%d W=%d grid=%d spec(warp0+wait)=%.3fs spec spread(last window)=%.3fs commit=%.3fs iterations=%llu\n",
-                  P.greedy_windows, W, grid, hp[3] * 1e-9, (hp[0] - hp[1]) * 1e-9, hp[2] * 1e-9, hp[4]);
+          fprintf(stderr, "[greedy] windows=%d W=%d rows=%d  longest speculative BFS %.1f ms, mean %.3f ms, pivot rows expanded %.3g, alive after speculation %llu\n",
+                  P.greedy_windows, W, ncand, hp[0] * 1e-6, hp[1] * 1e-6 / std::max(ncand, 1), (double)hp[2], hp[3]);
       }
       }
       counts[2] = fetch(ctr.p);
