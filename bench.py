@@ -126,13 +126,15 @@ def run_reference(args):
     val = sum(times) / len(times)
     line = {
         "impl": "reference",
-        "metric": "echelonize_time_to_rank", "value": val, "unit": "s", "n_gpus": 0, "steps": K, "warmup": args.warmup or 0,
+        "metric": "echelonize_time_to_rank", "value": val, "unit": "s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup or 0,
         "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "int32 residues mod p (i64 products)",
         "data": "synthetic",
         "config": {"workload": f"random sparse {FULL_N}x{FULL_N}, {NNZ_ROW} nnz/row, echelonize+rank mod {PRIME} (BASELINE configs[1])",
                    "sample": f"same generator at n={n} ({n}x{n}); the value is the time of this SAMPLE, not of the full matrix"},
         "cpu_baseline": {"value": val, "unit": "s", "cores": int(cores), "kind": "port",
-                         "sample": f"oracle restatement of libspasm, {cores} cores, {n}x{n} instance of the same generator (rank {r})"},
+                         "sample": f"oracle restatement of libspasm, {cores} cores, {n}x{n} instance of the same generator (rank {r})",
+                         "extrapolated_full_s": val * (FULL_N / n) ** 3,
+                         "extrapolation": "cubic in the number of rows (the dense tail dominates); an estimate, not a measurement"},
         "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

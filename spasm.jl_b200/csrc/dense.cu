@@ -204,6 +204,8 @@ __global__ void k_write_rows(const uint32_t *__restrict__ S, long long ld, int m
   }
 }
 
+void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);
+
 void make_free_columns(const int *qinv, int m, int *flag, long long *pos, int *q, int *qpos) {
   cudaStream_t s = stream();
   k_free_cols<<<cdiv(m + 1, 256), 256, 0, s>>>(qinv, m, flag);
@@ -723,10 +725,19 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
   }
   DenseSchur D;
   build_dense_schur(A, my_rows, n_local, U, Uqinv.p, F, D);
+  logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)%s\n", nrows, D.Sm0, spasm_wtime() - t0, D.levels,
+       NR > 1 ? " [sharded]" : "");
+  dense_tail_core(D, nrows, n_local, A.m, U, Uqinv, F, block_size);
+}
+
+// the blocked elimination itself, on a dense Schur complement that is already in HBM (D holds MY rows)
+void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size) {
+  cudaStream_t s = stream();
+  const Dist &dd = dist();
+  const int me = dd.rank, NR = dd.nranks;
+  const bool emit_rows = (me == 0);
   const int Sm0 = D.Sm0;
   const long long ld = D.ld;
-  logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)%s\n", nrows, Sm0, spasm_wtime() - t0, D.levels,
-       NR > 1 ? " [sharded]" : "");
   const bool prof = getenv("SPASM_B200_PROFILE") != nullptr;
   double tp[7] = {0, 0, 0, 0, 0, 0, 0};  // panel, R gemm, emit, gather/transposes, trailing gemm, blocks, broadcast
   auto tick = [&](int slot, double &t1) {
@@ -761,7 +772,7 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
     const long long kg = b * block_size;
     const int Sn = (int)std::min<long long>(block_size, nrows - kg);
     const int owner = panel_owner(b, NR);
-    logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - kg, A.m - U.n,
+    logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - kg, m_total - U.n,
          block_size);
     double t1 = spasm_wtime();
     int rr = 0;
@@ -829,7 +840,7 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
       }
     }
     logf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U.n);
-    if (U.n == A.m) break;
+    if (U.n == m_total) break;
   }
   if (prof)
     fprintf(stderr, "[dense] rank %d/%d blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs trailing=%.3fs bcast=%.3fs\n", me, NR, (int)tp[5],
@@ -839,6 +850,57 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
 }  // namespace sb
 
 using namespace sb;
+
+namespace sb {
+__global__ void k_fill_random(uint32_t *__restrict__ a, long long n, uint32_t p, unsigned long long seed) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + (unsigned long long)i * 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  z ^= z >> 31;
+  a[i] = (uint32_t)(z % p);
+}
+}  // namespace sb
+
+// BASELINE configs[3]: dense n x m Schur complement mod `prime`, generated on the device, through the
+// blocked elimination of the dense tail (panel factorisation + tcgen05 trailing updates).
+// Returns the rank; ms = CUDA-event time of the elimination (generation excluded).
+extern "C" int spasm_b200_dense_tail_bench(long long prime, int n, int m, int block_size, unsigned long long seed, double *ms) {
+  try {
+    require_gpu();
+    Fp F = make_field(prime);
+    DenseSchur D;
+    D.n_rem = n, D.Sm0 = m, D.levels = 0;
+    D.ld = ((long long)n + 63) / 64 * 64;
+    D.Dt.alloc((size_t)m * D.ld);
+    k_fill_random<<<cdiv((long long)m * D.ld, 256), 256, 0, stream()>>>(D.Dt.p, (long long)m * D.ld, F.p, seed);
+    D.q0.alloc(m);
+    k_iota2<<<cdiv(m, 256), 256, 0, stream()>>>(D.q0.p, m);
+    DCsr U;
+    U.n = 0, U.m = m, U.nnz = 0;
+    U.p.alloc(n + 2);
+    U.p.zero();
+    U.j.alloc(16), U.x.alloc(16);
+    DBuf<int> Uqinv(m);
+    Uqinv.fill_ff();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, stream()));
+    dense_tail_core(D, n, n, m, U, Uqinv, F, block_size);
+    CK(cudaEventRecord(e1, stream()));
+    CK(cudaEventSynchronize(e1));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    if (ms) *ms = t;
+    return U.n;
+  } catch (const std::exception &e) {
+    errf("[spasm_b200] spasm_b200_dense_tail_bench failed: %s\n", e.what());
+    return -1;
+  }
+}
 
 // the dense-tail entry point of the ABI (replaces spasm_ffpack_rref, src/SpaSM.jl:805)
 extern "C" int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, int *pivcol_out) {

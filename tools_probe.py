@@ -33,7 +33,7 @@ def run(tag, n, m, p, j, x, prime=42013, kernel=False, **kw):
 
 for arg in sys.argv[1:]:
     kind, _, size = arg.partition(":")
-    if kind in ("gemm", "c3b", "dense"):
+    if kind in ("gemm", "c3b", "dense", "dtail"):
         continue
     s = int(size)
     if kind == "c1":
@@ -105,3 +105,20 @@ for arg in sys.argv[1:]:
         g.lib.spasm_b200_last_timings(T)
         print(f"== dense {n}x{n} mod 65521: rank={f.r} wall={dt:.3f}s  LU-equivalent {2*n**3/3/dt/1e12:.2f} T mod-p OP/s", flush=True)
         print("   " + " ".join(f"{k}={v:.4g}" for k, v in zip(NAMES, T)), flush=True)
+
+for arg in sys.argv[1:]:
+    kind, _, size = arg.partition(":")
+    if kind == "dtail":  # BASELINE configs[3]: dense n x n mod 65521 through the blocked dense tail
+        n = int(size)
+        f = g.lib.spasm_b200_dense_tail_bench
+        f.restype = C.c_int
+        f.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(C.c_double)]
+        st = (C.c_double * 4)()
+        g.lib.spasm_b200_mma_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
+        for rep in range(3):
+            ms = C.c_double(0)
+            g.lib.spasm_b200_mma_stats(st, 1)
+            r = f(65521, n, n, 1000, 0x5A5A0004, C.byref(ms))
+            g.lib.spasm_b200_mma_stats(st, 0)
+            print(f"== dense tail {n}x{n} mod 65521 (block 1000): rank={r} {ms.value:.1f} ms  -> {2*n**3/3/(ms.value*1e-3)/1e9:.0f} G mod-p OP/s (2n^3/3 / t);"
+                  f" tcgen05 kernel {st[0]:.1f} ms for {st[1]:.3g} modular MACs = {8*st[1]/max(st[0],1e-9)/1e9:.0f} T int8 OP/s", flush=True)
