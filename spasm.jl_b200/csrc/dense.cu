@@ -2,6 +2,7 @@
 // (The blocked tcgen05 path that replaces the elimination step lives in dense_mma.cu.)
 #include "dense.cuh"
 #include "dist.cuh"
+#include "sink.cuh"
 
 namespace sb {
 
@@ -759,6 +760,13 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   } else {
     csr_reserve(U, U.nnz, U.n + std::min(nrows, Sm0));
   }
+  HostSink *sink = emit_rows ? g_sink : nullptr;
+  if (sink) {
+    // nothing on the device reads U's rows any more (the tail only appends): stream them out now
+    sink->ensure((long long)U.j.n);
+    convert_to_balanced(U.x.p + sink->submitted, (int *)U.x.p + sink->submitted, U.nnz - sink->submitted, F);
+    sink->submit(U.j.p, (const int *)U.x.p, sink->submitted, U.nnz - sink->submitted);
+  }
   const int Bmax = std::min(block_size, nrows);
   DBuf<uint32_t> T((size_t)Bmax * Bmax), Tsel((size_t)Bmax * Bmax), R((size_t)Bmax * Sm0), Rt, Pt;
   DBuf<int> ispiv, pivrow, pivcol(Bmax), ident(Bmax), hdr(1), cflag(Sm0 + 1), cand(std::max(Sm0, 1));
@@ -815,9 +823,14 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         k_count_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, rr, cnt.p);
         exclusive_scan_i32_to_i64(cnt.p, rpos.p, rr + 1);
         const long long add = fetch(rpos.p + rr);
+        if (sink && (size_t)(U.nnz + add) > U.j.n) sink->wait_all();  // the arrays are about to move
         csr_reserve(U, U.nnz + add, U.n + rr);
         k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pivcol.p, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
         CK(cudaGetLastError());
+        if (sink) {
+          convert_to_balanced(U.x.p + U.nnz, (int *)U.x.p + U.nnz, add, F);
+          sink->submit(U.j.p, (const int *)U.x.p, U.nnz, add);
+        }
         U.nnz += add;
       } else {
         k_register_pivots_only<<<cdiv(rr, 256), 256, 0, s>>>(pivcol.p, D.q0.p, rr, U.n, U.nnz, U.p.p, Uqinv.p);

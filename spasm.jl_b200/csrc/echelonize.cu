@@ -3,9 +3,11 @@
 // dense or GPLU tail (README.md:19-38).  All matrices stay resident in HBM
 // between phases; only scalars (counts, densities) and the final factor cross PCIe.
 #include <algorithm>
+#include <memory>
 
 #include "dense.cuh"
 #include "pivots.cuh"
+#include "sink.cuh"
 
 namespace sb {
 
@@ -295,6 +297,8 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
   std::vector<int> p_in;  // current row -> original row (empty: identity)
   double density = (n0 > 0 && m > 0) ? (double)spasm_nnz(A) / n0 / m : 0.0;
   bool finished = false, go_dense = false;
+  int *sink_arrays_j = nullptr, *sink_arrays_x = nullptr;
+  long long sink_done = 0, sink_cap = 0;
   PivotSearch P;
   P.p.alloc(std::max(n, 1));
   {
@@ -386,6 +390,14 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     }
     const double t0 = spasm_wtime();
     g_phase = "finish (GPLU / dense tail)";
+    std::unique_ptr<HostSink> sink_holder;
+    if (download && !opts->L && getenv("SPASM_B200_NO_STREAMING") == nullptr) {
+      sink_holder.reset(new HostSink());
+      g_sink = sink_holder.get();
+    }
+    struct SinkGuard {
+      ~SinkGuard() { g_sink = nullptr; }
+    } sink_guard;
     if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
       echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
     else if (opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
@@ -399,6 +411,11 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     sync();
     E.t_tail += spasm_wtime() - t0;
     g_timings[8] = E.t_tail;
+    if (sink_holder && sink_holder->submitted > 0) {
+      sink_done = sink_holder->submitted;
+      sink_cap = sink_holder->cap;
+      sink_holder->release(&sink_arrays_j, &sink_arrays_x);  // waits for the copies in flight
+    }
   }
   const double t_dl = spasm_wtime();
   g_phase = "download";
@@ -415,14 +432,30 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
   spasm_lu *fact = (spasm_lu *)spasm_malloc(sizeof(spasm_lu));
   E.U.m = m;
   {
-    spasm_csr *Uh = spasm_csr_alloc(E.U.n, m, E.U.nnz, prime, true);
-    CK(cudaMemcpyAsync(Uh->p, E.U.p.p, (size_t)(E.U.n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream()));
-    if (E.U.nnz) {
-      download_large(Uh->j, E.U.j.p, (size_t)E.U.nnz * sizeof(int));
-      // balanced representatives are produced in place (the device copy of U is dropped afterwards)
-      convert_to_balanced(E.U.x.p, (int *)E.U.x.p, E.U.nnz, E.F);
-      download_large(Uh->x, E.U.x.p, (size_t)E.U.nnz * sizeof(int));
+    spasm_csr *Uh = nullptr;
+    if (sink_arrays_j != nullptr) {
+      // the dense tail streamed [0, sink_done) already; fetch what came after (nothing, normally)
+      Uh = spasm_csr_alloc(E.U.n, m, 0, prime, true);
+      free(Uh->j), free(Uh->x);
+      Uh->j = sink_arrays_j, Uh->x = sink_arrays_x;
+      Uh->nzmax = sink_cap;
+      if (E.U.nnz > sink_done) {
+        if (E.U.nnz > Uh->nzmax) spasm_csr_realloc(Uh, E.U.nnz);
+        download_large(Uh->j + sink_done, E.U.j.p + sink_done, (size_t)(E.U.nnz - sink_done) * sizeof(int));
+        convert_to_balanced(E.U.x.p + sink_done, (int *)E.U.x.p + sink_done, E.U.nnz - sink_done, E.F);
+        download_large(Uh->x + sink_done, E.U.x.p + sink_done, (size_t)(E.U.nnz - sink_done) * sizeof(int));
+      }
+      spasm_csr_realloc(Uh, E.U.nnz);
+    } else {
+      Uh = spasm_csr_alloc(E.U.n, m, E.U.nnz, prime, true);
+      if (E.U.nnz) {
+        download_large(Uh->j, E.U.j.p, (size_t)E.U.nnz * sizeof(int));
+        // balanced representatives are produced in place (the device copy of U is dropped afterwards)
+        convert_to_balanced(E.U.x.p, (int *)E.U.x.p, E.U.nnz, E.F);
+        download_large(Uh->x, E.U.x.p, (size_t)E.U.nnz * sizeof(int));
+      }
     }
+    CK(cudaMemcpyAsync(Uh->p, E.U.p.p, (size_t)(E.U.n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream()));
     fact->U = Uh;
   }
   fact->qinv = (int *)spasm_malloc((i64)std::max(m, 1) * (i64)sizeof(int));
