@@ -1223,6 +1223,101 @@ static void echelonize_dense(const struct spasm_csr *A, const int *p, int n, con
   free(qpos);
 }
 
+/* counter-based random numbers for the low-rank mode (no sequential state: the CUDA code evaluates the
+ * same function in parallel) */
+static u64 lowrank_hash(u64 blk, u64 t, u64 k) {
+  u64 z = SPASM_SEED ^ (blk * 0x9e3779b97f4a7c15ULL) ^ (t * 0xbf58476d1ce4e5b9ULL + 0x1234567ULL) ^ (k * 0x94d049bb133111ebULL + 0x89abcdefULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+
+/* low-rank / tall-and-skinny mode (prototype spasm_schur_dense_randomized, src/SpaSM.jl:767-769;
+ * SURVEY.md A.7): blocks of dense_block_size RANDOM LINEAR COMBINATIONS of the remaining rows are
+ * eliminated against U, put in RREF and appended, until a full-weight block brings no new pivot.
+ * Combination t of block blk: with weight w < n, w terms (row lowrank_hash(blk,t,2s) % n, coefficient
+ * 1 + lowrank_hash(blk,t,2s+1) % (p-1)); at full weight every row k with coefficient
+ * lowrank_hash(blk,t,k) % p.  The weight starts at low_rank_start_weight (full weight when < 1) and
+ * doubles whenever a block yields nothing. */
+static void echelonize_dense_lowrank(const struct spasm_csr *A, const int *p, int n, struct spasm_lu *fact, struct echelonize_opts *opts) {
+  int m = A->m;
+  struct spasm_csr *U = fact->U;
+  int *Uqinv = fact->qinv;
+  const i64 prime = A->field->p;
+  const int block = opts->dense_block_size > 0 ? opts->dense_block_size : 1000;
+  int w = (opts->low_rank_start_weight >= 1) ? (int)opts->low_rank_start_weight : n;
+  if (w > n) w = n;
+  spasm_ZZp *y = spasm_malloc((i64)m * sizeof(*y));
+  int *q = spasm_malloc((i64)m * sizeof(int));
+  int *pivcol_of_row = NULL;
+  logprintf("[echelonize/low-rank] %d rows, %d columns left, block size %d, starting weight %d\n", n, m - U->n, block, w);
+  for (u64 blk = 0;; blk++) {
+    int Sm = m - U->n;
+    if (Sm == 0 || n == 0) break;
+    int c = 0;
+    for (int j = 0; j < m; j++)
+      if (Uqinv[j] < 0) q[c++] = j;
+    spasm_ZZp *S = spasm_calloc((i64)block * Sm, sizeof(spasm_ZZp));
+    int *pivcol = spasm_malloc((i64)block * sizeof(int));
+    for (int t = 0; t < block; t++) {
+      memset(y, 0, (i64)m * sizeof(*y));
+      if (w >= n) {
+        for (int k = 0; k < n; k++) {
+          spasm_ZZp coef = spasm_ZZp_init(A->field, (i64)(lowrank_hash(blk, t, k) % (u64)prime));
+          if (coef != 0) spasm_scatter(A, p[k], coef, y);
+        }
+      } else {
+        for (int s = 0; s < w; s++) {
+          int k = (int)(lowrank_hash(blk, t, 2 * (u64)s) % (u64)n);
+          spasm_ZZp coef = spasm_ZZp_init(A->field, (i64)(1 + lowrank_hash(blk, t, 2 * (u64)s + 1) % (u64)(prime - 1)));
+          spasm_scatter(A, p[k], coef, y);
+        }
+      }
+      /* eliminate against U, rows in increasing index (each only references later pivots) */
+      for (int i = 0; i < U->n; i++) {
+        int jp = U->j[U->p[i]];
+        if (y[jp] != 0) spasm_scatter(U, i, spasm_ZZp_sub(U->field, 0, y[jp]), y);
+      }
+      for (int k = 0; k < Sm; k++) S[(i64)t * Sm + k] = y[q[k]];
+    }
+    int rr = spasm_dense_rref(prime, block, Sm, S, Sm, pivcol);
+    if (rr == 0) {
+      free(S);
+      free(pivcol);
+      if (w >= n) break;
+      w = (2 * w < n) ? 2 * w : n;
+      continue;
+    }
+    for (int i = 0; i < rr; i++) {
+      const spasm_ZZp *row = S + (i64)i * Sm;
+      i64 cntnz = 0;
+      for (int k = 0; k < Sm; k++)
+        if (row[k] != 0) cntnz++;
+      csr_ensure_room(U, spasm_nnz(U) + cntnz);
+      i64 unz = U->p[U->n];
+      int jp = q[pivcol[i]];
+      Uqinv[jp] = U->n;
+      U->j[unz] = jp;
+      U->x[unz] = 1;
+      unz++;
+      for (int k = 0; k < Sm; k++) {
+        if (k == pivcol[i] || row[k] == 0) continue;
+        U->j[unz] = q[k];
+        U->x[unz] = row[k];
+        unz++;
+      }
+      U->n += 1;
+      U->p[U->n] = unz;
+    }
+    free(S);
+    free(pivcol);
+    logprintf("[echelonize/low-rank] block %d: %d new pivots (weight %d), rank %d\n", (int)blk, rr, w, U->n);
+  }
+  (void)pivcol_of_row;
+  free(y);
+  free(q);
+}
+
 /* src/SpaSM.jl:860-866 — THE entry point.  Loop (README.md:19-32): structural pivots -> density
  * estimate -> Schur complement, at most max_round times; then finish dense or GPLU. */
 struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_opts *opts) {
@@ -1309,6 +1404,8 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
     logprintf("[echelonize] finishing; density = %.3f; aspect ratio = %.1f\n", density, aspect_ratio);
     if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
       echelonize_GPLU(cur, p + npiv, rem_rows, p_in, fact, opts);
+    else if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio)
+      echelonize_dense_lowrank(cur, p + npiv, rem_rows, fact, opts);
     else if (opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
       echelonize_dense(cur, p + npiv, rem_rows, p_in, fact, opts);
     else if (opts->enable_GPLU)

@@ -865,6 +865,117 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
 using namespace sb;
 
 namespace sb {
+
+// ------------------------------------------------------------------ low-rank / tall-and-skinny mode
+// (prototype spasm_schur_dense_randomized, src/SpaSM.jl:767-769).  Same counter-based
+// random numbers as the oracle.  The dense Schur complement D of ALL remaining rows is built once;
+// a block of random combinations is then simply  Blk = D^T-layout GEMM  (Sm0 x B) = Dt . Coef^T, which is
+// what eliminating the combined rows against U would give (elimination is linear).  The block is
+// factored like a panel; the trailing update touches every row of D (rows are never consumed).
+__host__ __device__ inline unsigned long long lowrank_hash(unsigned long long blk, unsigned long long t, unsigned long long k) {
+  unsigned long long z = 0x5a5a5a5a2e6306e0ULL ^ (blk * 0x9e3779b97f4a7c15ULL) ^ (t * 0xbf58476d1ce4e5b9ULL + 0x1234567ULL) ^
+                         (k * 0x94d049bb133111ebULL + 0x89abcdefULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__global__ void k_coef_full(uint32_t *__restrict__ coef, long long ldc, int B, int n, unsigned long long blk, uint32_t p, int negate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (k >= n || t >= B) return;
+  uint32_t c = (uint32_t)(lowrank_hash(blk, t, k) % p);
+  coef[(long long)t * ldc + k] = (negate && c) ? p - c : c;
+}
+__global__ void k_coef_sparse(uint32_t *__restrict__ coef, long long ldc, int B, int n, int w, unsigned long long blk, Fp F) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // one combination per thread: its w terms may collide
+  if (t >= B) return;
+  for (int s = 0; s < w; s++) {
+    const int k = (int)(lowrank_hash(blk, t, 2ULL * s) % (unsigned long long)n);
+    const uint32_t c = (uint32_t)(1 + lowrank_hash(blk, t, 2ULL * s + 1) % (unsigned long long)(F.p - 1));
+    uint32_t *q = coef + (long long)t * ldc + k;
+    *q = addmod(*q, c, F);
+  }
+}
+__global__ void k_negate_rows(uint32_t *a, long long ld, int cols, uint32_t p) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cols) return;
+  uint32_t *q = a + (long long)blockIdx.y * ld + k;
+  if (*q) *q = p - *q;
+}
+
+void echelonize_lowrank_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
+                               double start_weight) {
+  cudaStream_t s = stream();
+  if (block_size <= 0) block_size = 1000;
+  if (nrows == 0 || A.m == U.n) return;
+  const int B = block_size;
+  int w = (start_weight >= 1) ? (int)start_weight : nrows;
+  if (w > nrows) w = nrows;
+  DenseSchur D;
+  build_dense_schur(A, rows, nrows, U, Uqinv.p, F, D);  // every rank holds all rows: no exchange in this mode
+  const int Sm0 = D.Sm0;
+  const long long ld = D.ld;
+  logf("[echelonize/low-rank] %d rows, %d columns left, block size %d, starting weight %d\n", nrows, Sm0, B, w);
+  const long long ldb = ((long long)B + 63) / 64 * 64;
+  DBuf<uint32_t> Coef((size_t)B * ld), Blk((size_t)Sm0 * ldb), T((size_t)B * B), Tsel((size_t)B * B), R((size_t)B * Sm0), Rt, Pt;
+  DBuf<int> ispiv, pivrow, pc_tmp, ident(B), cflag(Sm0 + 1), cand(std::max(Sm0, 1));
+  DBuf<long long> cpos(Sm0 + 1);
+  DBuf<unsigned char> colpiv(std::max(Sm0, 1));
+  colpiv.zero();
+  k_iota2<<<cdiv(B, 256), 256, 0, s>>>(ident.p, B);
+  const int KCH = 16384;  // the tensor-core GEMM takes K <= 16384 per call
+  for (unsigned long long blk = 0;; blk++) {
+    if (U.n == A.m) break;
+    // ---- coefficients and the combined block  Blk[c][t] = sum_k Dt[c][k] * Coef[t][k]
+    if (w >= nrows) {
+      k_coef_full<<<dim3(cdiv(nrows, 256), B), 256, 0, s>>>(Coef.p, ld, B, nrows, blk, F.p, 0);
+    } else {
+      Coef.zero();
+      k_coef_sparse<<<cdiv(B, 128), 128, 0, s>>>(Coef.p, ld, B, nrows, w, blk, F);
+    }
+    for (int kc = 0; kc < nrows; kc += KCH) {
+      const int kk = std::min(KCH, nrows - kc);
+      if (kc > 0) {  // C += A.B as C -= A.(-B)
+        k_negate_rows<<<dim3(cdiv(kk, 256), B), 256, 0, s>>>(Coef.p + kc, ld, kk, F.p);
+      }
+      gemm_nt(Blk.p, ldb, Sm0, B, D.Dt.p + kc, ld, Coef.p + kc, ld, kk, kc > 0, F);
+    }
+    // ---- factor the block like a panel
+    k_not_flag<<<cdiv(Sm0 + 1, 256), 256, 0, s>>>(colpiv.p, Sm0, cflag.p);
+    exclusive_scan_i32_to_i64(cflag.p, cpos.p, Sm0 + 1);
+    k_compact_flags_i32(cflag.p, cpos.p, Sm0, cand.p);
+    const int ncand = (int)fetch(cpos.p + Sm0);
+    const int rr = panel_factor(Blk.p, ldb, cand.p, ncand, 0, B, T.p, ispiv, pivrow, pc_tmp, F);
+    if (rr == 0) {
+      if (w >= nrows) break;
+      w = (2 * w < nrows) ? 2 * w : nrows;
+      continue;
+    }
+    k_gather_T_rows<<<dim3(cdiv(B, 256), rr), 256, 0, s>>>(T.p, B, pivrow.p, nullptr, rr, Tsel.p);
+    gemm_nt(R.p, Sm0, rr, Sm0, Tsel.p, B, Blk.p, ldb, B, false, F);
+    k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pc_tmp.p, rr, colpiv.p);
+    {
+      DBuf<int> cnt(rr + 1);
+      DBuf<long long> rpos(rr + 1);
+      k_count_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, rr, cnt.p);
+      exclusive_scan_i32_to_i64(cnt.p, rpos.p, rr + 1);
+      const long long add = fetch(rpos.p + rr);
+      csr_reserve(U, U.nnz + add, U.n + rr);
+      k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pc_tmp.p, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
+      CK(cudaGetLastError());
+      U.nnz += add;
+      U.n += rr;
+    }
+    // ---- trailing update of EVERY row:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
+    const long long ldk = ((long long)rr + 15) / 16 * 16;
+    Rt.alloc((size_t)Sm0 * ldk);
+    Pt.alloc((size_t)nrows * ldk);
+    k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
+    k_gather_pivot_cols_T<<<dim3(cdiv(nrows, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pc_tmp.p, rr, 0, nrows, Pt.p, ldk);
+    gemm_nt(D.Dt.p, ld, Sm0, nrows, Rt.p, ldk, Pt.p, ldk, rr, true, F);
+    logf("[echelonize/low-rank] block %d: %d new pivots (weight %d), rank %d\n", (int)blk, rr, w, U.n);
+  }
+}
+
 __global__ void k_fill_random(uint32_t *__restrict__ a, long long n, uint32_t p, unsigned long long seed) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -33,5 +33,8 @@ void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long l
 
 // eliminate the rows `rows` of A against U block by block, RREF each block, append to U
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);
+// low-rank / tall-and-skinny mode: blocks of random combinations of ALL remaining rows
+void echelonize_lowrank_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
+                               double start_weight);
 
 }  // namespace sb

@@ -190,3 +190,63 @@ def test_gl7d19_shaped_sparse_regime(gpu, oracle):
     checks.check_U_structure(gpu, fg)
     fo2, fg2 = oracle.echelonize(A, L=True), gpu.echelonize(A, L=True)
     checks.assert_same(checks.lu_arrays(fo2), checks.lu_arrays(fg2), "L: ")
+
+
+def test_dense_tail_entry_point(gpu):
+    """BASELINE configs[3] entry point at small size: a random dense n x n matrix mod 65521 has full rank
+    (probability 1 - 1/p) and the blocked elimination must find it, for several block sizes"""
+    f = gpu.lib.spasm_b200_dense_tail_bench
+    f.restype = C.c_int
+    f.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(C.c_double)]
+    ms = C.c_double(0)
+    for (n, m, block) in [(700, 700, 256), (1500, 1200, 1000), (900, 2000, 300)]:
+        assert f(65521, n, m, block, 1234, C.byref(ms)) == min(n, m)
+
+
+def test_multi_gpu_sharded_tail():
+    """torchrun with 2 ranks when the box has >= 2 GPUs (the driver's single-GPU run skips this)"""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", "tests/dist_gpu_check.py"], cwd=str(root), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "dist check OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+LOWRANK = [
+    # n, m, k, prime, seed, options
+    (3000, 200, 3, 42013, 5, {}),
+    (2500, 150, 2, 7, 6, dict(dense_block_size=64)),
+    (4000, 300, 3, 65521, 7, dict(low_rank_start_weight=4, dense_block_size=100)),
+    (800, 120, 2, 4294967291, 8, dict(dense_block_size=50)),
+    (1500, 90, 3, 42013, 9, dict(max_round=0, dense_block_size=16)),                              # every pivot through the low-rank blocks
+    (1500, 90, 3, 251, 10, dict(max_round=0, dense_block_size=16, low_rank_start_weight=1)),      # weight doubling
+    (20000, 60, 2, 42013, 11, dict(max_round=0, dense_block_size=32)),                            # K > 16384: chunked tensor-core GEMM
+]
+
+
+@pytest.mark.parametrize("case", LOWRANK)
+def test_low_rank_mode(gpu, oracle, case):
+    """tall-and-skinny finish (spasm_schur_dense_randomized, src/SpaSM.jl:767-769): random combinations of the
+    remaining rows, same counter-based random numbers on both sides -> bit-exact"""
+    n, m, k, prime, seed, kw = case
+    p, j, x = synth.random_rows(n, m, k, prime, seed)
+    A = gpu.from_arrays(n, m, p, j, x, prime)
+    lines = []
+    oracle.log(lambda s: lines.append(s) or 0)
+    try:
+        fo = oracle.echelonize(A, verbose=True, **kw)
+    finally:
+        oracle.log(None)
+    assert any("low-rank" in l for l in lines)
+    fg = gpu.echelonize(A, **kw)
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg), f"{kw}: ")
+    checks.check_U_structure(gpu, fg)
+    if n <= 4000:
+        checks.check_rank_and_rowspace(gpu, A, fg)

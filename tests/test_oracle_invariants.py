@@ -181,3 +181,22 @@ def test_thread_count_invariance(oracle, pkg):
         env = dict(os.environ, OMP_NUM_THREADS=nt)
         outs.add(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(pkg.PKG_DIR.parent), check=True).stdout.strip())
     assert len(outs) == 1, outs
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(dense_block_size=16, max_round=0), dict(dense_block_size=16, max_round=0, low_rank_start_weight=1)])
+@pytest.mark.parametrize("prime", [7, 42013, 4294967291])
+def test_low_rank_mode_oracle(oracle, prime, kw):
+    """tall-and-skinny finish: rank and row space are right whatever the weights / block size"""
+    n, m, k = 900, 70, 2
+    A = _mk(oracle, n, m, k, prime, 77)
+    lines = []
+    oracle.log(lambda s: lines.append(s) or 0)
+    try:
+        fact = oracle.echelonize(A, verbose=True, **kw)
+    finally:
+        oracle.log(None)
+    assert any("low-rank" in l for l in lines)
+    checks.check_U_structure(oracle, fact)
+    checks.check_rank_and_rowspace(oracle, A, fact)
+    K = oracle.kernel(fact)
+    checks.check_kernel(oracle, A, fact, K)
