@@ -591,6 +591,72 @@ class SpaSM:
             X = CSR(self, self.lib.spasm_gesv(fact.data, B.data, ok.ctypes.data_as(_P(C.c_bool))))
         return X, ok
 
+    # ---- src/blocks.jl
+    def Block(self, A: CSR) -> Block:
+        """src/blocks.jl:35-105.  Blocks are numbered by their smallest row (row-less blocks last, by column)."""
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import connected_components
+
+        n, m = A.shape
+        p, j, x = A.arrays()
+        rows = np.repeat(np.arange(n), np.diff(p))
+        G = sp.coo_matrix((np.ones(len(j), dtype=np.int8), (rows, j.astype(np.int64) + n)), shape=(n + m, n + m))
+        ncomp, label = connected_components(G, directed=False)
+        first = np.full(ncomp, n + m, dtype=np.int64)
+        np.minimum.at(first, label, np.arange(n + m))
+        order = np.argsort(first, kind="stable")
+        renum = np.empty(ncomp, dtype=np.int64)
+        renum[order] = np.arange(ncomp)
+        label = renum[label]
+        block2row = [np.nonzero(label[:n] == b)[0].astype(np.int32) for b in range(ncomp)]
+        block2col = [np.nonzero(label[n:] == b)[0].astype(np.int32) for b in range(ncomp)]
+        colpos = np.zeros(m, dtype=np.int32)
+        for b in range(ncomp):
+            colpos[block2col[b]] = np.arange(len(block2col[b]), dtype=np.int32)
+        blocks = []
+        for b in range(ncomp):
+            rs = block2row[b]
+            lens = (p[rs + 1] - p[rs]) if len(rs) else np.zeros(0, dtype=np.int64)
+            sp_ = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            idx = np.concatenate([np.arange(p[r], p[r + 1]) for r in rs]) if len(rs) and sp_[-1] else np.zeros(0, dtype=np.int64)
+            blocks.append(self.from_arrays(len(rs), len(block2col[b]), sp_, colpos[j[idx]] if len(idx) else np.zeros(0, np.int32),
+                                           x[idx] if len(idx) else np.zeros(0, np.int32), A.prime))
+        return Block(blocks, block2row, block2col, (n, m))
+
+    def block_echelonize(self, block: Block, **kw) -> Block:  # src/blocks.jl:107-115 (blocks run one after the other)
+        return Block([self.echelonize(Bk, **kw) for Bk in block.blocks], block.block2row, block.block2col, block.shape)
+
+    def block_rank(self, block: Block, **kw) -> int:  # src/blocks.jl:117
+        return sum((Bk.r if isinstance(Bk, LU) else self.rank(Bk, **kw)) for Bk in block.blocks)
+
+    def block_kernel(self, block: Block, **kw) -> Block:  # src/blocks.jl:119-139
+        if block.blocks and isinstance(block.blocks[0], CSR):
+            block = self.block_echelonize(block, **kw)
+        ks = [self.kernel(f) for f in block.blocks]
+        b2r, start = [], 0
+        for k in ks:
+            b2r.append(np.arange(start, start + k.n, dtype=np.int32))
+            start += k.n
+        return Block(ks, b2r, block.block2col, (start, block.shape[1]))
+
+    def block_CSR(self, block: Block) -> CSR:  # src/blocks.jl:143-170: reassemble with global column numbers
+        n, m = block.shape
+        owner = np.zeros((n, 2), dtype=np.int64)
+        for b, rs in enumerate(block.block2row):
+            owner[rs, 0] = b
+            owner[rs, 1] = np.arange(len(rs))
+        pp, jj, xx = [0], [], []
+        parts = [Bk.arrays() for Bk in block.blocks]
+        for i in range(n):
+            b, si = owner[i]
+            bp, bj, bx = parts[b]
+            jj.append(block.block2col[b][bj[bp[si] : bp[si + 1]]])
+            xx.append(bx[bp[si] : bp[si + 1]])
+            pp.append(pp[-1] + int(bp[si + 1] - bp[si]))
+        prime = block.blocks[0].prime if block.blocks else PRIME0
+        return self.from_arrays(n, m, np.array(pp, dtype=np.int64), np.concatenate(jj) if jj else np.zeros(0, np.int32),
+                                np.concatenate(xx) if xx else np.zeros(0, np.int32), prime)
+
     def dense_rref(self, prime: int, A: np.ndarray):
         """in-place RREF of a C-contiguous int32 matrix; returns (rank, pivcol[:rank])"""
         assert A.dtype == np.int32 and A.flags["C_CONTIGUOUS"] and A.ndim == 2
@@ -598,6 +664,18 @@ class SpaSM:
         piv = np.zeros(max(n, 1), dtype=np.int32)
         r = int(self.lib.spasm_dense_rref(prime, n, m, _i32ptr(A.reshape(-1)), m, _i32ptr(piv)))
         return r, piv[:r].copy()
+
+
+class Block:
+    """Block-diagonal decomposition of a matrix by the connected components of its row/column graph
+    (src/blocks.jl:1-105).  blocks[b] is a CSR / LU / kernel of component b; block2row / block2col list the
+    global 0-based rows / columns of each block in increasing order (a block may have no row or no column)."""
+
+    def __init__(self, blocks, block2row, block2col, shape):
+        self.blocks, self.block2row, self.block2col, self.shape = blocks, block2row, block2col, shape
+
+    def __len__(self):
+        return len(self.blocks)
 
 
 class _quiet:

@@ -250,3 +250,9 @@ def test_low_rank_mode(gpu, oracle, case):
     checks.check_U_structure(gpu, fg)
     if n <= 4000:
         checks.check_rank_and_rowspace(gpu, A, fg)
+
+
+def test_blocks_gpu(gpu):
+    from test_blocks import check_blocks
+
+    check_blocks(gpu)
