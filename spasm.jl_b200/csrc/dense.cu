@@ -1,5 +1,7 @@
 // dense.cu — dense tail, first version: Gauss-Jordan by pivot steps on CUDA cores.
 // (The blocked tcgen05 path that replaces the elimination step lives in dense_mma.cu.)
+#include <cooperative_groups.h>
+
 #include "dense.cuh"
 #include "dist.cuh"
 #include "sink.cuh"
@@ -297,6 +299,7 @@ void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long l
 // Gauss-Jordan on W among the rows that are not pivots yet (at most 32 new pivots per tile) while
 // recording the operations as the columns Gc of the update  T <- G.T.
 static constexpr int PB = 32;   // pivots per tile call (number of recorded operation columns Gc)
+static constexpr int WKS = 4;   // K slices of the narrow W product (k_wtile): 4x more CTAs, summed when the tile is loaded
 static constexpr int WMAX = 2048;
 struct PanelCtl {
   int npiv;      // pivots found so far in this panel
@@ -413,7 +416,14 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
     return;
   }
   const int wc = min(32, Sm0 - c0);
-  for (int c = 0; c < 32; c++) tile[c * SP + r] = (live && c < wc) ? (unsigned short)Wt[(long long)c * ldw + r] : 0;
+  for (int c = 0; c < 32; c++) {
+    uint32_t v = 0;
+    if (live && c < wc) {
+      for (int z = 0; z < WKS; z++) v += Wt[((long long)z * 32 + c) * ldw + r];  // KS partial products, each < p < 2^16
+      v %= F.p;
+    }
+    tile[c * SP + r] = (unsigned short)v;
+  }
   for (int s = 0; s < PB; s++) tile[(32 + s) * SP + r] = 0;
   int my_ispiv = live ? ispiv[r] : 1;
   int npiv = ctl->npiv, found = 0, cc = 0;
@@ -482,6 +492,122 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
   }
 }
 
+// CLUSTER version of the tile Gauss-Jordan: the (<= 1024) rows are split over a thread-block cluster
+// of 8 CTAs (one row per thread, the tile slice in each CTA's shared memory).  Per pivot: every CTA
+// publishes its best candidate row into all eight CTAs' shared memory (DSMEM), cluster.sync, the
+// owner of the winning row broadcasts the scaled pivot row the same way, cluster.sync, everybody
+// eliminates its own rows.  The arithmetic per pivot drops 8x against the single-CTA kernel.
+static constexpr int GC = 8;     // CTAs per cluster
+static constexpr int GRP = 128;  // rows (= threads) per CTA
+__global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(GRP)
+k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long ldw, int *__restrict__ ispiv, int *__restrict__ pivrow,
+                     int *__restrict__ pivcol, uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
+                     const int *__restrict__ cand, Fp F) {
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  __shared__ unsigned short tile[32 + PB][GRP];
+  __shared__ int s_best[2][GC];          // candidate of every CTA (double buffered by pivot parity)
+  __shared__ uint32_t s_prow[2][32 + PB];  // scaled pivot row
+  __shared__ int red[GRP / 32];
+  const int cta = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r = cta * GRP + tid;  // my row
+  const bool live = r < Sn;
+  const int c0 = ctl->c0;
+  const int npiv0 = ctl->npiv;
+  if (npiv0 >= Sn || c0 >= Sm0) {  // panel finished: no-op launch (uniform over the cluster)
+    if (cta == 0 && tid == 0) ctl->found = 0, ctl->consumed = 0;
+    return;
+  }
+  const int wc = min(32, Sm0 - c0);
+  for (int c = 0; c < 32; c++) {
+    uint32_t v = 0;
+    if (live && c < wc) {
+      for (int z = 0; z < WKS; z++) v += Wt[((long long)z * 32 + c) * ldw + r];  // KS partial products, each < p < 2^16
+      v %= F.p;
+    }
+    tile[c][tid] = (unsigned short)v;
+  }
+  for (int sx = 0; sx < PB; sx++) tile[32 + sx][tid] = 0;
+  int my_ispiv = live ? ispiv[r] : 1;
+  int npiv = npiv0, found = 0, cc = 0, step = 0;
+  cluster.sync();
+  for (; cc < wc && found < PB && npiv < Sn; cc++) {
+    const int par = step & 1;
+    // ---- best candidate of this CTA, published to every CTA of the cluster
+    int best = (!my_ispiv && tile[cc][tid] != 0) ? r : 0x7fffffff;
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) red[wid] = best;
+    __syncthreads();
+    if (tid < GC) {
+      int b2 = red[0];
+      for (int i = 1; i < GRP / 32; i++) b2 = min(b2, red[i]);
+      int *remote = cluster.map_shared_rank(&s_best[par][0], tid);  // CTA `tid` of the cluster
+      remote[cta] = b2;
+    }
+    cluster.sync();
+    int pr = s_best[par][0];
+#pragma unroll
+    for (int i = 1; i < GC; i++) pr = min(pr, s_best[par][i]);
+    step++;
+    if (pr == 0x7fffffff) continue;  // no pivot on this column (uniform decision)
+    // ---- the owner scales its pivot row and broadcasts it
+    if (pr / GRP == cta) {
+      const int pt = pr - cta * GRP;
+      if (tid == pt) {
+        my_ispiv = 1;
+        ispiv[r] = 1;
+        pivrow[npiv] = r;
+        pivcol[npiv] = cand[c0 + cc];
+        tilepiv[found] = r;
+        tile[32 + found][tid] = 1;
+      }
+      __syncthreads();
+      if (tid < 32 + PB) {
+        const bool used = (tid < 32) ? (tid >= cc && tid < wc) : (tid - 32 <= found);
+        uint32_t v = 0;
+        if (used) {
+          const uint32_t alpha = dev_inv_small(tile[cc][pt], F);
+          v = mulmod<true>(alpha, tile[tid][pt], F);
+        }
+#pragma unroll
+        for (int dst = 0; dst < GC; dst++) cluster.map_shared_rank(&s_prow[par][0], dst)[tid] = v;
+      }
+    }
+    cluster.sync();
+    // ---- everybody eliminates its own row
+    if (live) {
+      const uint32_t *prow = s_prow[par];
+      if (r == pr) {
+        for (int k = cc; k < wc; k++) tile[k][tid] = (unsigned short)prow[k];
+        for (int sx = 0; sx <= found; sx++) tile[32 + sx][tid] = (unsigned short)prow[32 + sx];
+      } else {
+        const uint32_t f = tile[cc][tid];
+        if (f != 0) {
+          const uint32_t nf = F.p - f;
+          for (int k = cc; k < wc; k++) {
+            uint32_t t = (uint32_t)tile[k][tid] + mulmod<true>(nf, prow[k], F);
+            tile[k][tid] = (unsigned short)(t >= F.p ? t - F.p : t);
+          }
+          for (int sx = 0; sx <= found; sx++) {
+            uint32_t t = (uint32_t)tile[32 + sx][tid] + mulmod<true>(nf, prow[32 + sx], F);
+            tile[32 + sx][tid] = (unsigned short)(t >= F.p ? t - F.p : t);
+          }
+        }
+      }
+    }
+    found++;
+    npiv++;
+  }
+  if (live)
+    for (int sx = 0; sx < found; sx++) Gc[(long long)sx * ldw + r] = tile[32 + sx][tid];
+  if (cta == 0 && tid == 0) {
+    ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc, ctl->c0 = c0 + cc;
+    if (found < PB / 2 && npiv < Sn) ctl->low += 1;
+  }
+  cluster.sync();  // nobody leaves while its shared memory may still be written remotely
+}
+
 // Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]  for a narrow tile (c < wc <= 32): one CTA per 32 rows r
 template <bool SMALL>
 __global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt_panel, long long ld, const uint32_t *__restrict__ T, int Sn, int Sm0,
@@ -495,15 +621,19 @@ __global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt_p
   __shared__ uint32_t Ts[32][33], Ds[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // tx: r within the tile, ty: column within the group
   const int r0 = blockIdx.x * 32, cg = blockIdx.y * 8;
+  // blockIdx.z takes one of the KS slices of the K range; the partial sums land in separate planes of Wt
+  const int kslice = ((Sn + 31) / 32 + gridDim.z - 1) / gridDim.z * 32;
+  const int tbeg = blockIdx.z * kslice, tend = min(Sn, tbeg + kslice);
+  Wt += (long long)blockIdx.z * 32 * ldw;
   unsigned long long acc = 0;
-  for (int t0 = 0; t0 < Sn; t0 += 32) {
+  for (int t0 = tbeg; t0 < tend; t0 += 32) {
     for (int idx = threadIdx.x; idx < 32 * 32; idx += 256) {
       const int a = idx >> 5, t = idx & 31;
-      Ts[a][t] = (r0 + a < Sn && t0 + t < Sn) ? T[(long long)(r0 + a) * Sn + t0 + t] : 0u;
+      Ts[a][t] = (r0 + a < Sn && t0 + t < tend) ? T[(long long)(r0 + a) * Sn + t0 + t] : 0u;
     }
     {
       const int a = threadIdx.x >> 5, t = threadIdx.x & 31;
-      Ds[a][t] = (cg + a < wc && t0 + t < Sn) ? Dt_panel[(long long)cand[c0 + cg + a] * ld + t0 + t] : 0u;
+      Ds[a][t] = (cg + a < wc && t0 + t < tend) ? Dt_panel[(long long)cand[c0 + cg + a] * ld + t0 + t] : 0u;
     }
     __syncthreads();
 #pragma unroll 8
@@ -622,6 +752,7 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
   pivcol.alloc(Sn);
   k_set_identity<<<cdiv((long long)Sn * Sn, 256), 256, 0, s>>>(T, Sn);
   const bool fast = F.small && Sn <= 1024;
+  static const bool use_cluster = getenv("SPASM_B200_NO_CLUSTER") == nullptr;
   static bool attr = false;
   const size_t gsm = (size_t)(32 + PB) * 1024 * sizeof(unsigned short);
   if (fast && !attr) {
@@ -639,8 +770,11 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
   // ---- dense phase: 32-column tiles, 8 tiles per host round trip, cursor advanced on the device
   while (fast && h.npiv < Sn && h.c0 < Sm0 && h.low == 0) {
     for (int g = 0; g < 8; g++) {
-      k_wtile<true><<<dim3(cdiv(Sn, 32), 4), 256, 0, s>>>(Dt + k0, ld, T, Sn, Sm0, ctl.p, cand, Wt.p, ldw, F);
-      k_tile_gauss_smem<<<1, 1024, gsm, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
+      k_wtile<true><<<dim3(cdiv(Sn, 32), 4, WKS), 256, 0, s>>>(Dt + k0, ld, T, Sn, Sm0, ctl.p, cand, Wt.p, ldw, F);
+      if (use_cluster)
+        k_tile_gauss_cluster<<<GC, GRP, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
+      else
+        k_tile_gauss_smem<<<1, 1024, gsm, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
       apply_T();
     }
     CK(cudaGetLastError());
@@ -1043,7 +1177,7 @@ extern "C" int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, 
     S.download(hu.data(), hu.size());
     std::vector<int> pc(std::max(rr, 1)), pr(std::max(rr, 1));
     if (rr) pivcol.download(pc.data(), rr), pivrow.download(pr.data(), rr);
-    sync();
+    sb::sync();
     // reduced rows first (by increasing pivot column), the rest are zero
     for (int r = 0; r < n; r++)
       for (int k = 0; k < m; k++) A[(size_t)r * ldA + k] = 0;
