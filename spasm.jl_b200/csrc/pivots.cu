@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
     }
     // ---- my turn: every earlier row is final and all their pivots are applied (nn is final too,
     // because only the row at the cursor can publish)
+    unsigned long long t_turn = 0;
+    if (g.prof && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_turn));
     int nn_now = nn;
     if (surviving > 0) {
       const long long a = g.Ap[i], b = g.Ap[i + 1];
@@ -366,6 +368,12 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
       d = __shfl_sync(0xffffffffu, d, 0);
       if (!d) break;
       nxt = cur2;
+    }
+    if (g.prof && lane == 0) {
+      unsigned long long t_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      atomicAdd(g.prof + 4, t_end - t_turn);  // time spent holding the cursor (serial part)
+      atomicAdd(g.prof + 5, 1ULL);
     }
     // a row that became final between our scan and the store re-checks the cursor itself (top of loop)
     return;
@@ -871,8 +879,10 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
         prof.download(hp, 8);
         sync();
         if (getenv("SPASM_B200_PROFILE"))
-          fprintf(stderr, "[greedy] windows=%d W=%d rows=%d  longest speculative BFS %.1f ms, mean %.3f ms, pivot rows expanded %.3g, alive after speculation %llu\n",
-                  P.greedy_windows, W, ncand, hp[0] * 1e-6, hp[1] * 1e-6 / std::max(ncand, 1), (double)hp[2], hp[3]);
+          fprintf(stderr, "[greedy] windows=%d W=%d rows=%d  longest speculative BFS %.1f ms, mean %.3f ms, pivot rows expanded %.3g, alive after speculation %llu; "
+                          "cursor held %.3f s over %llu turns (%.1f us / turn)\n",
+                  P.greedy_windows, W, ncand, hp[0] * 1e-6, hp[1] * 1e-6 / std::max(ncand, 1), (double)hp[2], hp[3], hp[4] * 1e-9, hp[5],
+                  hp[5] ? hp[4] * 1e-3 / hp[5] : 0.0);
       }
       }
       counts[2] = fetch(ctr.p);
