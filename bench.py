@@ -280,16 +280,70 @@ def run_ours(args):
     roofline = {
         "kernel": "k_gemm_i8limb (tcgen05.mma.kind::i8, SASS UTCIMMA; TMA-fed, TMEM accumulators)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "frac": (achieved / peak) if achieved else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
+        # profiles/r01_ncu_gemm_i8limb_persistent_prefetch.csv (M=32768 N=16384 K=1024; the bench's launches have
+        # other shapes, see traffic_note); algorithmic bytes of that launch: 4.29e9 (C read+write) + 1.0e8 (limb planes)
+        "traffic": 2.804927e9 + 2.110347e9,
+        "traffic_note": "ncu capture of the kernel alone at M=32768 N=16384 K=1024 (4.92e9 B vs 4.39e9 B algorithmic, x1.12); not re-measured per bench launch",
         "peak_source": f"2 x bf16_tflops_sustained of {src} (int8 dense = 2x bf16 nominal; proxy, no int8 figure is measured)",
         "algorithmic": "8 int8 ops per modular multiply-add (4 limb MMAs x 2), M*N*K per launch (unpadded)",
         "kernel_ms_per_step": mma_ms / K, "launches_per_step": mma_calls / K,
         "share_of_step": (mma_ms / K / 1e3) / my if my > 0 else None,
     }
 
+    # ---- secondary figures of BASELINE.json's metric (1 GPU only; outside the timed region of `value`):
+    # the dense tail alone on configs[3], and the sparse Schur complement on a GL7d19-shaped instance
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = {}
+        f = lib.spasm_b200_dense_tail_bench
+        f.restype = C.c_int
+        f.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(C.c_double)]
+        nd, best = 32768, None
+        for _ in range(3):
+            ms = C.c_double(0)
+            lib.spasm_b200_mma_stats(st, 1)
+            rd = f(65521, nd, nd, 1000, 0x5A5A0004, C.byref(ms))
+            lib.spasm_b200_mma_stats(st, 0)
+            assert rd == nd
+            if best is None or ms.value < best[0]:
+                best = (ms.value, st[0], st[1])
+        secondary["dense_tail_configs3"] = {
+            "workload": "dense 32768x32768 mod 65521 into the dense-tail entry point (block 1000), generated on the device",
+            "seconds": best[0] / 1e3, "rank": nd, "modp_gops": 2 * nd ** 3 / 3 / (best[0] * 1e-3) / 1e9,
+            "modp_gops_definition": "2*(n^3/3)/t (SURVEY 8d); the elimination itself performs about n^3 modular MACs (reduced form)",
+            "tcgen05_kernel_ms": best[1], "tcgen05_int8_tops": 8 * best[2] / max(best[1], 1e-9) / 1e9}
+        import synth
+
+        sc = 64
+        ns, ms_, rs = 1911130 // sc, 1955309 // sc, 1033568 // sc
+        pjx = synth.banded_planted(ns, ms_, rs, 12.0, 40, 42013, 0x5A5A0003, spread=16, colblock=8)
+        As = gpu.from_arrays(ns, ms_, *pjx, 42013)
+        gpu.echelonize(As)
+        t = time.perf_counter()
+        fs = gpu.echelonize(As)
+        ts = time.perf_counter() - t
+        assert fs.r == rs
+        Ls = (C.c_longlong * 7)()
+        lib.spasm_b200_last_stats.argtypes = [C.POINTER(C.c_longlong)]
+        lib.spasm_b200_last_stats(Ls)
+        lib.spasm_b200_last_timings(T)
+        ph = dict(zip(TIMING_NAMES, T))
+        secondary["sparse_regime_configs2_scaled"] = {
+            "workload": f"GL7d19-shaped banded planted-rank generator at 1/{sc} scale ({ns}x{ms_}, rank {rs} by construction), "
+                        "rounds of structural pivots + sparse Schur complement + GPLU tail",
+            "seconds_e2e": ts, "rank": fs.r,
+            "last_schur_algorithmic_gbps": (Ls[0] / (Ls[6] * 1e-6) / 1e9) if Ls[6] > 0 else None,
+            "last_schur_gmacs_per_s": (Ls[1] / (Ls[6] * 1e-6) / 1e9) if Ls[6] > 0 else None,
+            "schur_bytes_definition": "SURVEY 8d B_schur: 8 B per CSR entry read or written once per use + 8 B per row touched",
+            "hbm_peak_gbps": hbm_gbs,
+            "phases_s": {k: round(v, 5) for k, v in ph.items() if v}}
+        del fs, As
+
     # ---- CPU baseline: the oracle on a bounded sample, rank 0 only
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         ora = pkg.SpaSM(entry.build_oracle())
         ns = CPU_SAMPLE_N if n >= CPU_SAMPLE_N else n
         ps, js, xs = make_input(ns)
@@ -323,6 +377,7 @@ def run_ours(args):
         "clocks": clk.summary(),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "secondary": secondary,
         "phases_last_step_s": phases,
         "wall_s_timed_region": wall,
     }
@@ -340,6 +395,7 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="debug: override the matrix size (the bench value is only valid at the default)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[3] dense tail / sparse Schur side figures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

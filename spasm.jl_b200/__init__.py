@@ -623,11 +623,35 @@ class SpaSM:
                                            x[idx] if len(idx) else np.zeros(0, np.int32), A.prime))
         return Block(blocks, block2row, block2col, (n, m))
 
-    def block_echelonize(self, block: Block, **kw) -> Block:  # src/blocks.jl:107-115 (blocks run one after the other)
-        return Block([self.echelonize(Bk, **kw) for Bk in block.blocks], block.block2row, block.block2col, block.shape)
+    @staticmethod
+    def block_owner(block: Block, world: int) -> np.ndarray:
+        """Owner rank of every block when independent blocks are spread over `world` processes (one GPU each):
+        blocks by decreasing number of non-zeros (ties: block number), each to the least loaded rank so far
+        (ties: lowest rank).  Pure host arithmetic, identical on every rank; no communication is needed because
+        the blocks of src/blocks.jl share neither rows nor columns."""
+        w = np.array([Bk.nnz() if isinstance(Bk, CSR) else Bk.U.nnz() for Bk in block.blocks], dtype=np.int64)
+        owner = np.zeros(len(w), dtype=np.int32)
+        load = np.zeros(max(world, 1), dtype=np.int64)
+        for b in sorted(range(len(w)), key=lambda b: (-int(w[b]), b)):
+            r = int(np.argmin(load))
+            owner[b] = r
+            load[r] += max(int(w[b]), 1)
+        return owner
 
-    def block_rank(self, block: Block, **kw) -> int:  # src/blocks.jl:117
-        return sum((Bk.r if isinstance(Bk, LU) else self.rank(Bk, **kw)) for Bk in block.blocks)
+    def block_echelonize(self, block: Block, part=None, **kw) -> Block:  # src/blocks.jl:107-115 (blocks run one after the other)
+        """part=(rank, world): factor only the blocks block_owner() gives to `rank`; the others stay None."""
+        if part is None:
+            fs = [self.echelonize(Bk, **kw) for Bk in block.blocks]
+        else:
+            owner = self.block_owner(block, part[1])
+            fs = [self.echelonize(Bk, **kw) if owner[b] == part[0] else None for b, Bk in enumerate(block.blocks)]
+        return Block(fs, block.block2row, block.block2col, block.shape)
+
+    def block_rank(self, block: Block, part=None, **kw) -> int:  # src/blocks.jl:117
+        """with part=(rank, world): the sum over this rank's blocks only — add the partial ranks up (all_reduce)"""
+        owner = self.block_owner(block, part[1]) if part is not None else None
+        mine = [Bk for b, Bk in enumerate(block.blocks) if Bk is not None and (owner is None or owner[b] == part[0])]
+        return sum((Bk.r if isinstance(Bk, LU) else self.rank(Bk, **kw)) for Bk in mine)
 
     def block_kernel(self, block: Block, **kw) -> Block:  # src/blocks.jl:119-139
         if block.blocks and isinstance(block.blocks[0], CSR):

@@ -1124,7 +1124,17 @@ __global__ void k_fill_random(uint32_t *__restrict__ a, long long n, uint32_t p,
 // BASELINE configs[3]: dense n x m Schur complement mod `prime`, generated on the device, through the
 // blocked elimination of the dense tail (panel factorisation + tcgen05 trailing updates).
 // Returns the rank; ms = CUDA-event time of the elimination (generation excluded).
+static int dense_tail_bench_impl(long long prime, int n, int m, int planted_rank, int block_size, unsigned long long seed, double *ms);
 extern "C" int spasm_b200_dense_tail_bench(long long prime, int n, int m, int block_size, unsigned long long seed, double *ms) {
+  return dense_tail_bench_impl(prime, n, m, 0, block_size, seed, ms);
+}
+// same with a PLANTED rank r < min(n, m): the matrix is the product of a random n x r and a random r x m
+// matrix (rank r unless a random r x r minor is singular, probability about 1/p), SURVEY.md configs[3] variant
+extern "C" int spasm_b200_dense_tail_bench_planted(long long prime, int n, int m, int r, int block_size, unsigned long long seed,
+                                                   double *ms) {
+  return dense_tail_bench_impl(prime, n, m, r, block_size, seed, ms);
+}
+static int dense_tail_bench_impl(long long prime, int n, int m, int planted_rank, int block_size, unsigned long long seed, double *ms) {
   try {
     require_gpu();
     Fp F = make_field(prime);
@@ -1132,7 +1142,16 @@ extern "C" int spasm_b200_dense_tail_bench(long long prime, int n, int m, int bl
     D.n_rem = n, D.Sm0 = m, D.levels = 0;
     D.ld = ((long long)n + 63) / 64 * 64;
     D.Dt.alloc((size_t)m * D.ld);
-    k_fill_random<<<cdiv((long long)m * D.ld, 256), 256, 0, stream()>>>(D.Dt.p, (long long)m * D.ld, F.p, seed);
+    if (planted_rank > 0) {
+      const long long ldr = ((long long)planted_rank + 15) / 16 * 16;
+      DBuf<uint32_t> Yt((size_t)m * ldr), X((size_t)n * ldr);
+      k_fill_random<<<cdiv((long long)m * ldr, 256), 256, 0, stream()>>>(Yt.p, (long long)m * ldr, F.p, seed ^ 0x1111);
+      k_fill_random<<<cdiv((long long)n * ldr, 256), 256, 0, stream()>>>(X.p, (long long)n * ldr, F.p, seed ^ 0x2222);
+      D.Dt.zero();
+      for (int k0 = 0; k0 < planted_rank; k0 += 8192)  // Dt[c][k] = - sum_s Y[s][c] X[k][s], in K chunks the tensor-core path takes
+        gemm_nt(D.Dt.p, D.ld, m, n, Yt.p + k0, ldr, X.p + k0, ldr, std::min(8192, planted_rank - k0), true, F);
+    } else
+      k_fill_random<<<cdiv((long long)m * D.ld, 256), 256, 0, stream()>>>(D.Dt.p, (long long)m * D.ld, F.p, seed);
     D.q0.alloc(m);
     k_iota2<<<cdiv(m, 256), 256, 0, stream()>>>(D.q0.p, m);
     DCsr U;

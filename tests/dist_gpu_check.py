@@ -28,6 +28,14 @@ for (n, m, k, prime, seed, kw) in cases:  # single-GPU results first (no communi
     p, j, x = synth.random_rows(n, m, k, prime, seed)
     A = gpu.from_arrays(n, m, p, j, x, prime)
     single.append(checks.lu_arrays(gpu.echelonize(A, **kw)))
+# second axis (src/blocks.jl): independent blocks, one owner rank each, no data-path collective
+from test_blocks import blocky_matrix
+
+Ab = blocky_matrix(gpu)
+Bb = gpu.Block(Ab)
+part = torch.tensor([gpu.block_rank(Bb, part=(rank, world))], device="cuda")
+dist.all_reduce(part)
+assert int(part.item()) == gpu.echelonize(Ab).r, (rank, int(part.item()))
 bench.dist_init(gpu.lib, dist, rank, world)
 ok = True
 for idx, (n, m, k, prime, seed, kw) in enumerate(cases):

@@ -39,3 +39,20 @@ def check_blocks(api):
 
 def test_blocks_oracle(oracle):
     check_blocks(oracle)
+
+
+def test_block_owner_partition(oracle):
+    """blocks spread over ranks (second multi-GPU axis): every block has one owner, the partial ranks add up,
+    and the heaviest rank carries at most the lightest one's load plus one block"""
+    A = blocky_matrix(oracle)
+    B = oracle.Block(A)
+    full = oracle.echelonize(A).r
+    for world in (1, 2, 3, 8):
+        owner = oracle.block_owner(B, world)
+        assert owner.min() >= 0 and owner.max() < world and len(owner) == len(B)
+        assert sum(oracle.block_rank(B, part=(r, world)) for r in range(world)) == full
+        w = np.array([max(Bk.nnz(), 1) for Bk in B.blocks])
+        load = np.array([w[owner == r].sum() for r in range(world)])
+        assert load.max() - load.min() <= w.max()
+        fs = oracle.block_echelonize(B, part=(0, world))
+        assert [f is not None for f in fs.blocks] == (owner == 0).tolist()

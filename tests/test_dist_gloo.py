@@ -36,6 +36,15 @@ for (n_rem, block) in [(10, 3), (1000, 1000), (2501, 1000), (7, 100), (0, 5), (4
     sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([cnt]))
     assert max(int(s) for s in sizes) - min(int(s) for s in sizes) <= block
+# independent blocks (src/blocks.jl) spread over the ranks: partial ranks add up to the rank of the whole matrix
+from test_blocks import blocky_matrix
+pkg = e.load_package()
+ora = pkg.SpaSM(e.build_oracle())
+A = blocky_matrix(ora)
+B = ora.Block(A)
+part = torch.tensor([ora.block_rank(B, part=(rank, world))])
+dist.all_reduce(part)
+assert int(part) == ora.echelonize(A).r
 # bootstrap plumbing: rank 0's 128-byte id reaches everyone unchanged
 ident = torch.arange(128, dtype=torch.uint8) if rank == 0 else torch.zeros(128, dtype=torch.uint8)
 dist.broadcast(ident, src=0)
