@@ -113,7 +113,12 @@ __global__ void k_flc_commit(const long long *__restrict__ Ap, const int *__rest
 }
 
 // ------------------------------------------------------------------ greedy cycle-free search
-static constexpr unsigned ST_CAND = 1, ST_SEEN = 2, ST_EXP = 3;
+// Closure marks of one row: TWO BITS per column, 16 columns per 32-bit word, private to the row's warp and
+// cleared by it before use (m/4 bytes: 50 KB for 200 000 columns, so the marks of a whole window stay in
+// or near L2 instead of being 2 bytes per column of random HBM traffic).
+//   MV: the column has been reached by the row's closure;  MC: the column is one of the row's candidates.
+// One atomicOr both tests and sets MV and settles duplicates inside a warp step.
+static constexpr unsigned MV = 1u, MC = 2u;
 
 struct GreedyArgs {
   const long long *Ap;
@@ -122,41 +127,48 @@ struct GreedyArgs {
   int *pinv, *qinv;
   const int *cand;  // non-pivotal rows, increasing
   int ncand;
-  unsigned short *marks;  // [W][m]   (gen << 2 | state)
-  int *queue;             // [W][qcap]
+  unsigned *marks;  // [W][mw] packed 2-bit marks
+  int mw;           // words per row of marks (multiple of 4)
+  int *queue;       // [W][qcap]
   int qcap;
-  int *surv, *head, *tail;  // [W]
-  int *ctl;                 // [0] cursor (rows decided)  [1] pivots published in this window
-  int *newcol;              // [W] columns of the pivots published in this window
+  int *done;        // [ncand] row is decided
+  int *ctl;         // one 64-bit word: cursor << 32 | pivots published
+  int *next;        // next candidate row to hand out
+  int *newcol;      // [ncand] columns of the pivots published, in order
   int *npiv;
-  unsigned long long *prof;  // [0] max end-of-speculation time [1] min  [2] commit ns [3] spec ns [4] iterations
+  unsigned long long *prof;
 };
 
-__device__ __forceinline__ unsigned mark_state(unsigned short s, unsigned gen) { return ((unsigned)s >> 2) == gen ? (s & 3u) : 0u; }
+__device__ __forceinline__ unsigned mark_or(unsigned *marks, int j, unsigned bits) {
+  const int sh = (j & 15) * 2;
+  return (atomicOr(&marks[j >> 4], bits << sh) >> sh) & 3u;
+}
+__device__ __forceinline__ unsigned mark_get(const unsigned *marks, int j) { return (__ldcg(&marks[j >> 4]) >> ((j & 15) * 2)) & 3u; }
 
-// claim column jj for this row's closure; returns 0 (already reached), 1 (newly reached), and sets
-// `killed` when it was a surviving candidate.  16-bit CAS: two lanes of the warp may meet the same column.
-__device__ __forceinline__ int claim(unsigned short *marks, int jj, unsigned gen, unsigned newstate, int &killed) {
-  for (;;) {
-    unsigned short cur = ((volatile unsigned short *)marks)[jj];
-    unsigned st = mark_state(cur, gen);
-    if (st == ST_SEEN || st == ST_EXP) return 0;
-    unsigned short nv = (unsigned short)((gen << 2) | newstate);
-    if (atomicCAS(&marks[jj], cur, nv) == cur) {
-      killed = (st == ST_CAND);
-      return 1;
-    }
+// the queue holds each pivotal column once, except when a pivot published by another row is met by the
+// closure and then applied again from the published list (harmless, rare): slide the live part down
+// instead of sizing the queue for that
+__device__ __forceinline__ void queue_room(const GreedyArgs &g, int *q, int &head, int &tail, int lane) {
+  if (tail + 32 <= g.qcap) return;
+  const int live = tail - head;
+  for (int k0 = 0; k0 < live; k0 += 32) {
+    const int k = k0 + lane;
+    int v = 0;
+    if (k < live) v = q[head + k];
+    __syncwarp();
+    if (k < live) q[k] = v;
   }
+  __syncwarp();
+  head = 0, tail = live;
+  if (tail + 32 > g.qcap) __trap();
 }
 
 // Expand queued pivotal columns until the queue is empty or no candidate survives.  Up to 32 queue
 // entries are expanded together: lane l owns entry head+l, and the entries of those pivot rows are
 // walked as one flattened index space, 32 at a time (full lanes even though rows are short).  The
-// column index of the NEXT chunk is fetched while the current one is resolved, and duplicates inside
-// a chunk are settled with __match_any (no atomics: the marks are private to the row), so the
-// dependent chain per chunk is one round trip (mark + qinv loads issue together).
-__device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *marks, int *q, int &head, int &tail, int &surviving,
-                                        unsigned gen, int lane) {
+// column index of the NEXT chunk is fetched while the current one is resolved; per chunk the mark
+// atomic and the qinv load issue together, so the dependent chain is one round trip.
+__device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned *marks, int *q, int &head, int &tail, int &surviving, int lane) {
   while (head < tail && surviving > 0) {
     const int nb = min(32, tail - head);
     long long a = 0;
@@ -194,16 +206,13 @@ __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *mar
     for (int f0 = 0; f0 < total; f0 += 32) {
       const int jj = jj_next;
       if (f0 + 32 < total) jj_next = fetch_col(f0 + 32);  // in flight while this chunk is resolved
+      queue_room(g, q, head, tail, lane);
       int push = 0, killed = 0;
       if (jj >= 0) {
-        const unsigned short cur = marks[jj];
+        const unsigned old = mark_or(marks, jj, MV);
         const bool piv = __ldcg(&g.qinv[jj]) >= 0;
-        const unsigned st = mark_state(cur, gen);
-        // one lane per distinct column acts
-        const unsigned same = __match_any_sync(__activemask(), jj);
-        if ((st == 0 || st == ST_CAND) && lane == __ffs(same) - 1) {
-          killed = (st == ST_CAND);
-          marks[jj] = (unsigned short)((gen << 2) | (piv ? ST_EXP : ST_SEEN));
+        if (!(old & MV)) {
+          killed = (old & MC) != 0;
           push = piv;
         }
       }
@@ -218,24 +227,40 @@ __device__ __forceinline__ void bfs_run(const GreedyArgs &g, unsigned short *mar
   }
 }
 
-// one cooperative launch per window, ONE WARP PER ROW, all rows of the window co-resident:
-//   1. every row runs its BFS against the pivots known at window start;
-//   2. rows are then decided strictly in row order.  Pivots committed in this window are published in
-//      an append-only list; every waiting row keeps applying them to its own closure as they appear
-//      (continuing its BFS), so when its turn comes only the last few remain.  A row whose candidates
-//      are all reached is final at once (reachability only grows) and is skipped by the cursor.
-// ctl: [0] cursor (rows decided)   [1] number of pivots published   done[]: row is final
-__global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int wn, unsigned gen) {
-  const int lane = threadIdx.x & 31;
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (t >= wn) return;
-  volatile int *ctl = g.ctl;
-  volatile int *done = g.head;  // reuse: head[] is not needed across warps any more
-  const int i = g.cand[w0 + t];
-  unsigned short *marks = g.marks + (size_t)t * g.m;
-  int *q = g.queue + (size_t)t * g.qcap;
+// ONE cooperative launch, ONE WARP PER ROW AT A TIME.  The grid is W warps (all co-resident); each warp
+// takes the next candidate row from a counter, so rows are handed out in increasing order and the W
+// rows in flight form a window that slides as rows are decided (no barrier between windows: a slow
+// closure delays nobody but its own successors in the commit order).  For its row a warp
+//   1. runs the BFS against the pivots known when it starts;
+//   2. waits for its turn: rows are decided strictly in row order.  Pivots committed meanwhile are
+//      published in an append-only list; every waiting row keeps applying them to its own closure as
+//      they appear (continuing its BFS), so when its turn comes only the last few remain.  A row whose
+//      candidates are all reached is final at once (reachability only grows) and is skipped by the cursor.
+// The row at the cursor is always in flight or the next to be handed out (rows are handed out in order),
+// so the spin-waits cannot deadlock.
+// ctl64: (cursor = rows decided) << 32 | pivots published     done[]: 1 final without pivot, 2 decided with one
+__device__ void greedy_row(const GreedyArgs &g, const int t, const int wn, unsigned *marks, int *q, const int lane) {
+  volatile int *done = g.done;
+  const int i = g.cand[t];
+  unsigned long long *ctl64 = (unsigned long long *)g.ctl;
+  auto read_ctl = [&](int &cur, int &nn) {
+    unsigned long long w = 0;
+    if (lane == 0) w = *(volatile unsigned long long *)ctl64;
+    w = __shfl_sync(0xffffffffu, w, 0);
+    cur = (int)(w >> 32), nn = (int)(w & 0xffffffffu);
+  };
+  // pivots published before this point are in qinv for every load below (they are written before the count)
+  int applied = 0;
+  {
+    int cur0;
+    read_ctl(cur0, applied);
+    __threadfence();
+  }
   int head = 0, tail = 0, surviving = 0;
   {
+    uint4 *mz = (uint4 *)marks;
+    for (int k = lane; k < (g.mw >> 2); k += 32) __stcg(&mz[k], make_uint4(0u, 0u, 0u, 0u));
+    __syncwarp();
     const long long a = g.Ap[i], b = g.Ap[i + 1];
     for (long long e0 = a; e0 < b; e0 += 32) {
       long long e = e0 + lane;
@@ -243,10 +268,10 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
       if (e < b) {
         j = g.Aj[e];
         if (__ldcg(&g.qinv[j]) < 0) {
-          marks[j] = (unsigned short)((gen << 2) | ST_CAND);
+          mark_or(marks, j, MC);
           isc = 1;
         } else {
-          marks[j] = (unsigned short)((gen << 2) | ST_EXP);
+          mark_or(marks, j, MV);
           push = 1;
         }
       }
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
     __syncwarp();
     unsigned long long tb = 0, te = 0;
     if (g.prof && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
-    bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+    bfs_run(g, marks, q, head, tail, surviving, lane);
     if (g.prof && lane == 0) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te));
       atomicMax(g.prof + 0, te - tb);                 // longest speculative BFS (ns)
@@ -267,106 +292,117 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
       if (surviving > 0) atomicAdd(g.prof + 3, 1ULL);   // rows alive after speculation
     }
   }
-  int applied = 0;
+  // first surviving candidate of the row, in storage order
+  auto first_candidate = [&]() -> int {
+    const long long a = g.Ap[i], b = g.Ap[i + 1];
+    int jp = -1;
+    for (long long e0 = a; e0 < b && jp < 0; e0 += 32) {
+      long long e = e0 + lane;
+      int j = e < b ? g.Aj[e] : -1;
+      unsigned c = __ballot_sync(0xffffffffu, j >= 0 && mark_get(marks, j) == MC);
+      if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
+    }
+    return jp;
+  };
+  int jp_ready = -2;  // -2: not computed for the current closure
   unsigned backoff = 32;
   for (;;) {
+    int cur, nn;
     if (surviving <= 0) {  // final: no pivot on this row
       if (lane == 0) {
         done[t] = 1;
         __threadfence();
       }
-      // the cursor may be waiting on us
-      int cur = 0;
-      if (lane == 0) cur = ctl[0];
-      cur = __shfl_sync(0xffffffffu, cur, 0);
+      read_ctl(cur, nn);  // the cursor may be waiting on us
       if (cur != t) return;
       // fall through to advance the cursor below
-    }
-    int cur = 0, nn = 0;
-    if (lane == 0) {
-      cur = ctl[0];
-      __threadfence();  // the pivot count is read AFTER the cursor: if it is our turn the count is final
-      nn = ctl[1];
-    }
-    cur = __shfl_sync(0xffffffffu, cur, 0);
-    nn = __shfl_sync(0xffffffffu, nn, 0);
-    if (surviving > 0 && applied < nn) {
-      // apply the pivots published since last time
-      for (; applied < nn && surviving > 0; applied++) {
-        const int jc = __ldcg(&g.newcol[applied]);
-        const unsigned st = mark_state(marks[jc], gen);
-        if (st != ST_CAND && st != ST_SEEN) continue;
-        if (st == ST_CAND) surviving--;
-        __syncwarp();
-        if (lane == 0) {
-          marks[jc] = (unsigned short)((gen << 2) | ST_EXP);
-          q[tail] = jc;
+    } else {
+      read_ctl(cur, nn);
+      if (applied < nn) {
+        // apply the pivots published since last time: a column this closure has reached (it was not pivotal
+        // then) or that is one of its candidates must now be expanded; one it has not reached will be
+        // treated as pivotal when the closure gets there
+        for (; applied < nn && surviving > 0; applied++) {
+          const int jc = __ldcg(&g.newcol[applied]);
+          const unsigned st = mark_get(marks, jc);
+          if (st == 0) continue;
+          if (st == MC) surviving--;
+          queue_room(g, q, head, tail, lane);
+          if (lane == 0) {
+            mark_or(marks, jc, MV);
+            q[tail] = jc;
+          }
+          tail++;
+          __syncwarp();
+          bfs_run(g, marks, q, head, tail, surviving, lane);
+          jp_ready = -2;
         }
-        tail++;
-        __syncwarp();
-        bfs_run(g, marks, q, head, tail, surviving, gen, lane);
+        backoff = 32;
+        continue;  // re-read the control word
       }
-      backoff = 32;
-      continue;  // re-read the control words
-    }
-    if (cur != t) {
-      __nanosleep(backoff);
-      if (backoff < 1024) backoff <<= 1;
-      continue;
+      if (cur != t) {
+        if (jp_ready == -2) {  // use the wait: have the answer ready when the turn comes
+          jp_ready = first_candidate();
+          continue;
+        }
+        __nanosleep(backoff);
+        if (backoff < 512) backoff <<= 1;
+        continue;
+      }
     }
     // ---- my turn: every earlier row is final and all their pivots are applied (nn is final too,
     // because only the row at the cursor can publish)
     unsigned long long t_turn = 0;
     if (g.prof && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_turn));
-    int nn_now = nn;
+    int npub = nn;
     if (surviving > 0) {
-      const long long a = g.Ap[i], b = g.Ap[i + 1];
-      int jp = -1;
-      for (long long e0 = a; e0 < b && jp < 0; e0 += 32) {
-        long long e = e0 + lane;
-        int j = e < b ? g.Aj[e] : -1;
-        unsigned c = __ballot_sync(0xffffffffu, j >= 0 && mark_state(marks[j], gen) == ST_CAND);
-        if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
-      }
+      const int jp = jp_ready != -2 ? jp_ready : first_candidate();
+      npub = nn + 1;
       if (lane == 0) {
         g.pinv[i] = jp;
         g.qinv[jp] = i;
         g.newcol[nn] = jp;
         atomicAdd(g.npiv, 1);
+        done[t] = 2;  // decided WITH a pivot (1: final without)
         __threadfence();
-        ctl[1] = nn + 1;
-        done[t] = 1;
-        __threadfence();
+        // publish the count at once (cursor unchanged): the waiting rows start applying it while we look for the next row
+        atomicMax(ctl64, ((unsigned long long)t << 32) | (unsigned)npub);
       }
-      nn_now = nn + 1;
     }
-    (void)nn_now;
-    // advance the cursor over every following row that is already final.  atomicMax keeps it
+    // advance the cursor over every following row that is already final.  atomicMax keeps the word
     // monotone when a row that just became final advances it concurrently; the re-check after the
     // fence closes the missed-wakeup window (that row does store-done / fence / load-cursor).
+    // A row seen with done == 2 has had its turn AFTER ours: the cursor is in other hands and our
+    // pivot count is stale, so we stop at once instead of writing it back.
     int nxt = t + 1;
     for (;;) {
+      bool stale = false;
       for (;;) {
-        int tt = nxt + lane;
-        unsigned fin = __ballot_sync(0xffffffffu, tt < wn && done[tt] != 0);
-        int run = (fin == 0xffffffffu) ? 32 : __ffs(~fin) - 1;
+        const int tt = nxt + lane;
+        const int dv = tt < wn ? done[tt] : 0;
+        const unsigned fin = __ballot_sync(0xffffffffu, dv != 0);
+        const int run = (fin == 0xffffffffu) ? 32 : __ffs(~fin) - 1;
+        const unsigned passed = run == 32 ? 0xffffffffu : ((1u << run) - 1u);
+        if (__ballot_sync(0xffffffffu, dv == 2) & passed) {
+          stale = true;
+          break;
+        }
         nxt += run;
         if (run < 32 || nxt >= wn) break;
       }
+      if (stale) break;
       if (nxt > wn) nxt = wn;
-      int cur2 = 0;
+      int cur2 = 0, d = 0;
       if (lane == 0) {
+        const unsigned long long mine = ((unsigned long long)nxt << 32) | (unsigned)npub;
+        const unsigned long long old = atomicMax(ctl64, mine);
+        cur2 = (int)((old > mine ? old : mine) >> 32);
         __threadfence();
-        int old = atomicMax(g.ctl, nxt);
-        cur2 = old > nxt ? old : nxt;
-        __threadfence();
+        if (cur2 < wn) d = done[cur2];
       }
       cur2 = __shfl_sync(0xffffffffu, cur2, 0);
-      if (cur2 >= wn) break;
-      int d = 0;
-      if (lane == 0) d = done[cur2];
       d = __shfl_sync(0xffffffffu, d, 0);
-      if (!d) break;
+      if (cur2 >= wn || d != 1) break;  // handed over (0), or that row already took its turn (2)
       nxt = cur2;
     }
     if (g.prof && lane == 0) {
@@ -377,6 +413,21 @@ __global__ void __launch_bounds__(256) k_greedy_window(GreedyArgs g, int w0, int
     }
     // a row that became final between our scan and the store re-checks the cursor itself (top of loop)
     return;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_greedy_stream(GreedyArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned *marks = g.marks + (size_t)slot * g.mw;
+  int *q = g.queue + (size_t)slot * g.qcap;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(g.next, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= g.ncand) return;
+    greedy_row(g, t, g.ncand, marks, q, lane);
+    __syncwarp();
   }
 }
 
@@ -843,35 +894,30 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
         }
         CK(cudaGetLastError());
       } else {
-      const int qcap = std::min(n, m) + 1;
-      const size_t per = (size_t)m * 2 + (size_t)qcap * 4;
+      const int qcap = std::min(n, m) + 1 + 1024;
+      const int mw = (((m + 15) >> 4) + 3) & ~3;
+      const size_t per = (size_t)mw * 4 + (size_t)qcap * 4;
       size_t budget = std::min<size_t>(dev_free_bytes() / 3, (size_t)24 << 30);
       int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy_window, 256, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy_stream, 256, 0));
       const int grid = std::max(1, occ) * sm_count();
-      int W = (int)std::max<size_t>(32, std::min<size_t>((size_t)grid * 8, budget / per));
-      W = std::min(W, ncand);
-      DBuf<unsigned short> marks((size_t)W * m);
-      DBuf<int> queue((size_t)W * qcap), surv(W), head(W), tail(W), ctl(4), newcol(W);
-      marks.zero();
-      ctr.zero();
+      // rows in flight: enough warps to keep the memory system busy, few enough that their marks
+      // (mw words each) stay close to the 126 MB L2 — measured at 200 000 columns: 16 warps per SM beat 32 and 48
+      int W = std::min(grid * 8, sm_count() * 16);
+      W = (int)std::max<size_t>(32, std::min<size_t>((size_t)W, budget / per));
+      if (const char *e = getenv("SPASM_B200_GREEDY_W")) W = std::max(32, std::min(grid * 8, atoi(e)));
+      W = std::max(8, std::min(W, (ncand + 7) / 8 * 8));
+      DBuf<unsigned> marks((size_t)W * mw);
+      DBuf<int> queue((size_t)W * qcap), done(ncand), ctl(4), next(1), newcol(ncand);
+      ctr.zero(), ctl.zero(), next.zero(), done.zero();
       DBuf<unsigned long long> prof(8);
       prof.zero();
-      GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, queue.p, qcap, surv.p, head.p, tail.p, ctl.p, newcol.p, ctr.p, prof.p};
-      unsigned gen = 1;
-      for (int w0 = 0; w0 < ncand; w0 += W) {
-        int wn = std::min(W, ncand - w0);
-        ctl.zero();
-        head.zero();
-        void *args[] = {&g, &w0, &wn, &gen};
-        CK(cudaLaunchCooperativeKernel((void *)k_greedy_window, dim3(cdiv((long long)wn * 32, 256)), dim3(256), args, 0, s));
-        gen++;
+      GreedyArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, marks.p, mw, queue.p, qcap, done.p, ctl.p, next.p, newcol.p, ctr.p, prof.p};
+      {
+        void *args[] = {&g};
+        CK(cudaLaunchCooperativeKernel((void *)k_greedy_stream, dim3(W / 8), dim3(256), args, 0, s));
         g_launches += 1;
-        P.greedy_windows++;
-        if (gen == (1u << 14)) {
-          marks.zero();
-          gen = 1;
-        }
+        P.greedy_windows = W;
       }
       CK(cudaGetLastError());
       {
@@ -879,7 +925,7 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
         prof.download(hp, 8);
         sync();
         if (getenv("SPASM_B200_PROFILE"))
-          fprintf(stderr, "[greedy] windows=%d W=%d rows=%d  longest speculative BFS %.1f ms, mean %.3f ms, pivot rows expanded %.3g, alive after speculation %llu; "
+          fprintf(stderr, "[greedy] rows in flight=%d W=%d rows=%d  longest speculative BFS %.1f ms, mean %.3f ms, pivot rows expanded %.3g, alive after speculation %llu; "
                           "cursor held %.3f s over %llu turns (%.1f us / turn)\n",
                   P.greedy_windows, W, ncand, hp[0] * 1e-6, hp[1] * 1e-6 / std::max(ncand, 1), (double)hp[2], hp[3], hp[4] * 1e-9, hp[5],
                   hp[5] ? hp[4] * 1e-3 / hp[5] : 0.0);
