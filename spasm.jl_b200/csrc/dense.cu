@@ -715,6 +715,12 @@ __global__ void k_gather_pivot_cols_T(const uint32_t *__restrict__ Dt, long long
     if (k < nk && s < rr) Pt[(long long)k * ldp + s] = tile[threadIdx.x][y];
   }
 }
+// out[s][u] = in[idx[s]][u], u < cols
+__global__ void k_gather_rows_ld(const uint32_t *__restrict__ in, long long ldi, const int *__restrict__ idx, int rows, int cols,
+                                 uint32_t *__restrict__ out, long long ldo) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, sidx = blockIdx.y;
+  if (u < cols && sidx < rows) out[(long long)sidx * ldo + u] = in[(long long)idx[sidx] * ldi + u];
+}
 __global__ void k_iota2(int *a, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = i;
@@ -910,10 +916,44 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   k_iota2<<<cdiv(Bmax, 256), 256, 0, s>>>(ident.p, Bmax);
   const long long nb = ((long long)nrows + block_size - 1) / block_size;
   long long lb = 0;  // my panels already factored
+  // ---- deferred trailing updates.  A panel's update has K = its rank (<= block_size), and at K = 1000 the
+  // tensor-core kernel spends 1/3 of its time in the read-modify-write epilogue of C.  So only the NEAR rows
+  // (my next `group` panels) are updated at once; for the FAR rows [fe, n_local) the factors are appended to
+  //     Rt_acc (Sm0 x Kacc)  and  Pt_acc (n_local x Kacc)
+  // and applied in ONE product of depth Kacc <= kcap when the near rows are used up (or kcap is reached).
+  // The multipliers of a new panel on far rows are read from columns that still miss the pending updates and
+  // are corrected first:  Pt_b[k][s] = Dt[pc_b[s]][k] - sum_u Pt_acc[k][u] . Rt_acc[pc_b[s]][u]  (exact mod p,
+  // so the result is bit-identical to the eager order).
+  const int B16 = (Bmax + 15) / 16 * 16;
+  int kcap = 4096;
+  if (const char *e = getenv("SPASM_B200_LAZY_K")) kcap = atoi(e);
+  kcap = std::max(0, std::min(kcap, 16384 - B16));
+  while (kcap >= 2 * B16 && (size_t)(Sm0 + n_local + B16) * (size_t)(kcap + B16) * 4 > dev_free_bytes() / 4) kcap /= 2;  // keep the two factor buffers small
+  const bool lazy = kcap >= 2 * B16 && n_local > 2 * block_size;
+  const int group = lazy ? std::max(1, kcap / std::max(block_size, 1)) : 1;
+  const long long LDK = lazy ? (long long)kcap + B16 : 0;
+  DBuf<uint32_t> Rt_acc, Pt_acc, Rsel;
+  if (lazy) Rt_acc.alloc((size_t)Sm0 * LDK), Pt_acc.alloc((size_t)n_local * LDK), Rsel.alloc((size_t)B16 * LDK);
+  int Kacc = 0;                                         // depth of the pending product
+  long long gend = (long long)group * block_size;       // my local rows [.., gend) are always up to date
+  auto flush_far = [&]() {
+    const long long fe = std::min<long long>(gend, n_local);
+    if (Kacc > 0 && fe < n_local) gemm_nt(D.Dt.p + fe, ld, Sm0, (int)(n_local - fe), Rt_acc.p, LDK, Pt_acc.p + fe * LDK, LDK, Kacc, true, F);
+    Kacc = 0;
+  };
   for (long long b = 0; b < nb; b++) {
     const long long kg = b * block_size;
     const int Sn = (int)std::min<long long>(block_size, nrows - kg);
     const int owner = panel_owner(b, NR);
+    if (lazy && owner == me && lb * block_size >= gend) {  // the near rows are used up: bring the far rows up to date
+      double tf = spasm_wtime();
+      flush_far();
+      gend = lb * block_size + (long long)group * block_size;
+      if (prof) {
+        sync();
+        tp[4] += spasm_wtime() - tf;
+      }
+    }
     logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - kg, m_total - U.n,
          block_size);
     double t1 = spasm_wtime();
@@ -975,7 +1015,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       // trailing update of MY later rows:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
       const long long kb = lb * block_size;
       const int nk = (int)std::max<long long>(0, n_local - kb);
-      if (nk > 0) {
+      if (nk > 0 && !lazy) {
         const long long ldk = ((long long)rr + 15) / 16 * 16;
         Rt.alloc((size_t)Sm0 * ldk);
         Pt.alloc((size_t)nk * ldk);
@@ -984,7 +1024,26 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         tick(3, t1);
         gemm_nt(D.Dt.p + kb, ld, Sm0, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F);
         tick(4, t1);
+      } else if (nk > 0) {
+        const int rr16 = (rr + 15) / 16 * 16;
+        const long long fe = std::min<long long>(std::max(gend, kb), n_local);  // near rows [kb, fe), far rows [fe, n_local)
+        uint32_t *Rt_b = Rt_acc.p + Kacc, *Pt_b = Pt_acc.p + kb * LDK + Kacc;
+        k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt_b, LDK);
+        if (rr16 > rr) CK(cudaMemset2DAsync(Rt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, Sm0, s));  // zero pad columns: the pad of Pt may hold anything
+        k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt_b, LDK);
+        if (Kacc > 0 && fe < n_local) {
+          // the far rows of these pivot columns still miss the pending updates
+          k_gather_rows_ld<<<dim3(cdiv(Kacc, 256), rr), 256, 0, s>>>(Rt_acc.p, LDK, pivcol.p, rr, Kacc, Rsel.p, LDK);
+          gemm_nt(Pt_acc.p + fe * LDK + Kacc, LDK, (int)(n_local - fe), rr, Pt_acc.p + fe * LDK, LDK, Rsel.p, LDK, Kacc, true, F);
+          g_launches += 1;
+        }
+        tick(3, t1);
+        if (fe > kb) gemm_nt(D.Dt.p + kb, ld, Sm0, (int)(fe - kb), Rt_b, LDK, Pt_b, LDK, rr, true, F);
+        Kacc += rr16;
+        if (Kacc + B16 > kcap || fe >= n_local) flush_far();
+        tick(4, t1);
       }
+      g_launches += 2;
     }
     logf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U.n);
     if (U.n == m_total) break;
