@@ -87,6 +87,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // kind::i8, D = s32, A = B = u8, both K-major, M = 128, N = 128
 static constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 
+// Tile order.  The CTAs in flight work on consecutive tile numbers, so the order decides what the L2 has to
+// hold: row-major order re-streams ALL of B (N x K limbs, up to 900 MB in the bench) for every row of tiles
+// (ncu, M=32768 N=16384 K=4096: 22 GB of DRAM reads for 2.5 GB of operands).  Tiles are therefore walked in
+// column groups of RASTER_GN tiles: inside a group the B tiles (16 x 128 rows x K, 16 MB at K = 4096) stay in
+// L2 while the rows of A stream past once.
+static constexpr int RASTER_GN = 16;
+__device__ __forceinline__ void tile_origin(long long tile, int tiles_m, int tiles_n, int &m0, int &n0) {
+  const long long per_group = (long long)RASTER_GN * tiles_m;
+  const int grp = (int)(tile / per_group);
+  const int within = (int)(tile - (long long)grp * per_group);
+  const int gw = min(RASTER_GN, tiles_n - grp * RASTER_GN);
+  m0 = (within / gw) * TILE;
+  n0 = (grp * RASTER_GN + within % gw) * TILE;
+}
+
 struct __align__(8) MmaShared {
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
@@ -141,7 +156,8 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     if (lane == 0) {
       long long kbg = 0;  // k-blocks issued so far (ring position)
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (int)(tile / tiles_n) * TILE, n0 = (int)(tile % tiles_n) * TILE;
+        int m0, n0;
+        tile_origin(tile, tiles_m, tiles_n, m0, n0);
         for (int kb = 0; kb < nkb; kb++, kbg++) {
           const int s = (int)(kbg % STAGES);
           const uint32_t ph = (uint32_t)((kbg / STAGES) & 1);
@@ -197,7 +213,8 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-      const int m0 = (int)(tile / tiles_n) * TILE, n0 = (int)(tile % tiles_n) * TILE;
+      int m0, n0;
+        tile_origin(tile, tiles_m, tiles_n, m0, n0);
 #pragma unroll 1
       for (int h = 0; h < 2; h++) {
         const int nh = n0 + h * HALF;
