@@ -32,6 +32,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
 
 PRIME = 42013
+SM_COUNT = 148
 FULL_N = 200_000
 NNZ_ROW = 10
 SEED = 0x5A5A0002
@@ -282,10 +283,12 @@ def run_ours(args):
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if achieved else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
-        # profiles/r01_ncu_gemm_i8limb_persistent_prefetch.csv (M=32768 N=16384 K=1024; the bench's launches have
-        # other shapes, see traffic_note); algorithmic bytes of that launch: 4.29e9 (C read+write) + 1.0e8 (limb planes)
-        "traffic": 2.804927e9 + 2.110347e9,
-        "traffic_note": "ncu capture of the kernel alone at M=32768 N=16384 K=1024 (4.92e9 B vs 4.39e9 B algorithmic, x1.12); not re-measured per bench launch",
+        # profiles/r01_ncu_gemm_i8limb_k4096_grouped_tiles.csv (M=32768 N=16384 K=4096, the depth of the deferred
+        # trailing updates; the bench's launches have other M and N, see traffic_note).  Algorithmic bytes of that
+        # launch: 4.29e9 (C read + write) + 4.0e8 (u8 limb planes of A and B read once)
+        "traffic": 5.429282e9 + 2.143989e9,
+        "traffic_note": "ncu capture of the kernel alone at M=32768 N=16384 K=4096: 7.57e9 B of DRAM traffic vs 4.70e9 B algorithmic (x1.6; "
+                        "it was 24.5e9 B before the tiles were walked in column groups); not re-measured per bench launch",
         "peak_source": f"2 x bf16_tflops_sustained of {src} (int8 dense = 2x bf16 nominal; proxy, no int8 figure is measured)",
         "algorithmic": "8 int8 ops per modular multiply-add (4 limb MMAs x 2), M*N*K per launch (unpadded)",
         "kernel_ms_per_step": mma_ms / K, "launches_per_step": mma_calls / K,
@@ -363,6 +366,12 @@ def run_ours(args):
                "sample": f"oracle restatement of libspasm (oracle/), {cores} cores, {ns}x{ns} instance of the same generator; "
                          f"the CUDA library takes {tg:.3f} s end to end on that sample"}
 
+    clocks = clk.summary()
+    if achieved and clocks.get("sm_max_mhz"):
+        # ncu's sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained: 16384 int8 ops per cycle per SM (profiles/r01_ncu_gemm_i8limb_k4096_*.csv)
+        hw = 16384.0 * SM_COUNT * clocks["sm_max_mhz"] * 1e6 / 1e12
+        roofline["hw_int8_peak_tops_at_max_clock"] = hw
+        roofline["frac_of_hw_int8_peak"] = achieved / hw
     line = {
         "metric": "echelonize_time_to_rank", "value": my, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * my, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -374,7 +383,7 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": "s", "steps": e2e_steps, "h2d_bytes_per_step": csr_bytes(n, nnz),
                 "d2h_bytes_per_step": int(8 * (rank_found + 1) + 8 * u_nnz + 4 * n)},
         "gpu_launches": int(launches),
-        "clocks": clk.summary(),
+        "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "secondary": secondary,
