@@ -33,6 +33,7 @@ struct HostSink::Impl {
   cudaEvent_t ev[2];
   static constexpr size_t CH = (size_t)128 << 20;
   int threads = 1;
+  bool pin_cached = false;
 
   void run() {
     cudaSetDevice(device);
@@ -78,11 +79,26 @@ struct HostSink::Impl {
 
 HostSink *g_sink = nullptr;
 
+// the two pinned bounce buffers cost ~0.1 s to allocate: keep one pair for the life of the process
+static std::mutex g_pin_mu;
+static void *g_pin_cache[2] = {nullptr, nullptr};
+static bool g_pin_busy = false;
+
 HostSink::HostSink() : impl(new Impl) {
   CK(cudaGetDevice(&impl->device));
   CK(cudaStreamCreateWithFlags(&impl->cs, cudaStreamNonBlocking));
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (!g_pin_busy) {
+      for (int i = 0; i < 2; i++)
+        if (g_pin_cache[i] == nullptr) CK(cudaHostAlloc(&g_pin_cache[i], Impl::CH, cudaHostAllocDefault));
+      impl->pin[0] = g_pin_cache[0], impl->pin[1] = g_pin_cache[1];
+      g_pin_busy = true;
+      impl->pin_cached = true;
+    }
+  }
   for (int i = 0; i < 2; i++) {
-    CK(cudaHostAlloc(&impl->pin[i], Impl::CH, cudaHostAllocDefault));
+    if (!impl->pin_cached) CK(cudaHostAlloc(&impl->pin[i], Impl::CH, cudaHostAllocDefault));
     CK(cudaEventCreateWithFlags(&impl->ev[i], cudaEventDisableTiming));
   }
   impl->threads = std::max(1, std::min(12, omp_get_num_procs() - 2));
@@ -97,8 +113,12 @@ HostSink::~HostSink() {
   impl->cv.notify_all();
   if (impl->th.joinable()) impl->th.join();
   for (int i = 0; i < 2; i++) {
-    cudaFreeHost(impl->pin[i]);
+    if (!impl->pin_cached) cudaFreeHost(impl->pin[i]);
     cudaEventDestroy(impl->ev[i]);
+  }
+  if (impl->pin_cached) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_busy = false;
   }
   cudaStreamDestroy(impl->cs);
   free(hj);
