@@ -19,22 +19,30 @@ __global__ void k_pivcol_of_rows(const long long *__restrict__ Up, const int *__
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < r) pivcol[i] = Uj[Up[i]];
 }
+static constexpr int RELAX_SWEEPS = 8;
 // level[i] = 1 + max level of the rows i' != i that hold column pc_i (they must be final first)
 __global__ void k_level_relax(const long long *__restrict__ Tp, const int *__restrict__ Tj, const int *__restrict__ pivcol, int r,
                               int *__restrict__ level, int *__restrict__ changed) {
   int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= r) return;
   const int c = pivcol[i];
-  int h = 0;
-  for (long long e = Tp[c] + lane; e < Tp[c + 1]; e += 32) {
-    int i2 = Tj[e];
-    if (i2 != i) h = max(h, ((volatile int *)level)[i2] + 1);
-  }
+  // several sweeps per launch: the iteration is monotone (levels only grow towards the longest-path
+  // fixpoint), so re-evaluating against whatever the neighbours hold right now is safe, and a launch
+  // in which nobody changed anything proves the fixpoint.  Cuts the number of launches of this
+  // latency-bound loop (thousands of levels) by the sweep count.
+  for (int sweep = 0; sweep < RELAX_SWEEPS; sweep++) {
+    int h = 0;
+    for (long long e = Tp[c] + lane; e < Tp[c + 1]; e += 32) {
+      int i2 = Tj[e];
+      if (i2 != i) h = max(h, ((volatile int *)level)[i2] + 1);
+    }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
-  if (lane == 0 && h > level[i]) {
-    level[i] = h;
-    *changed = 1;
+    for (int o = 16; o; o >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
+    if (lane == 0 && h > ((volatile int *)level)[i]) {
+      ((volatile int *)level)[i] = h;
+      *changed = 1;
+    }
+    __syncwarp();
   }
 }
 __global__ void k_iota_int(int *a, int n) {
