@@ -1,0 +1,66 @@
+"""The C driver (tests/c_driver/driver.c) talks to the library through dlopen/dlsym only — the way a C or Julia
+host would — and replays the reference's own test vectors (test/runtests.jl:7-24, README.md:9-48).
+Kernel bases are compared as the reference does: sparse(k) is the TRANSPOSE of the SpaSM matrix."""
+import json
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import __graft_entry__ as entry
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = json.loads((ROOT / "tests" / "golden" / "reference_goldens.json").read_text())
+
+
+def build_driver(tmp_path):
+    exe = tmp_path / "c_driver"
+    subprocess.run(["/usr/bin/gcc", "-O1", "-std=gnu11", "-I", str(ROOT / "include"), str(ROOT / "tests" / "c_driver" / "driver.c"), "-ldl", "-o", str(exe)],
+                   check=True)
+    return exe
+
+
+def run_case(exe, lib, case):
+    r = subprocess.run([str(exe), str(lib), case], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    head = {l.split()[0]: [int(t) for t in l.split()[1:]] for l in lines[:3]}
+    entries = sorted(tuple(int(t) for t in l.split()) for l in lines[3:])
+    return head, entries
+
+
+def golden_entries(k):
+    # Julia (I, J, V), 1-based, of sparse(kernel) = transpose of the SpaSM matrix -> SpaSM (row, col, v) 0-based
+    return sorted((j - 1, i - 1, v) for i, j, v in zip(k["I"], k["J"], k["V"]))
+
+
+def check(exe, lib):
+    head, ent = run_case(exe, lib, "runtests")
+    g = GOLD["runtests"]["kernel"]
+    assert head["kernel"][:2] == [g["shape"][1], g["shape"][0]] and ent == golden_entries(g)
+    head, ent = run_case(exe, lib, "runtests_t")
+    g = GOLD["runtests"]["kernel_transpose"]
+    assert head["kernel"][:2] == [g["shape"][1], g["shape"][0]] and ent == golden_entries(g)
+    head, ent = run_case(exe, lib, "readme")
+    g = GOLD["readme"]
+    assert head["rank"] == [g["rank"]] and head["nnzU"] == [g["nz_in_basis"]] and head["kernel"][2] == g["nnz_K"]
+    assert ent == golden_entries(g["kernel"])
+
+
+def test_c_driver_on_oracle(tmp_path):
+    check(build_driver(tmp_path), entry.build_oracle())
+
+
+@pytest.mark.gpu
+def test_c_driver_on_cuda_library(tmp_path):
+    check(build_driver(tmp_path), entry.build_product())
+
+
+def test_c_driver_product_refuses_without_gpu(tmp_path):
+    """on a box without a GPU the CUDA library must load, export the ABI and fail loudly — never compute on the CPU"""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([str(build_driver(tmp_path)), str(entry.build_product()), "readme"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 4 and "no CPU fallback" in r.stderr and "rank" not in r.stdout
