@@ -64,3 +64,26 @@ def test_c_driver_product_refuses_without_gpu(tmp_path):
         pytest.skip("a GPU is present")
     r = subprocess.run([str(build_driver(tmp_path)), str(entry.build_product()), "readme"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 4 and "no CPU fallback" in r.stderr and "rank" not in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("SPASM_B200_EDGE_TESTS") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a GPU; set SPASM_B200_EDGE_TESTS=1")
+def test_degenerate_inputs_on_cuda_library(gpu, oracle):
+    """all-zero matrices, a single entry, the identity (tests/test_oracle_invariants.py::test_edge_cases on the GPU)"""
+    import numpy as np
+
+    import checks
+
+    for n, m in [(5, 7), (1, 1), (7, 5)]:
+        Z = gpu.spzeros(gpu.CSR(np.zeros((1, 1))).field, n, m)
+        fact = gpu.echelonize(Z)
+        assert fact.r == 0
+        K = gpu.kernel(fact)
+        assert K.shape == (m, m) and K.nnz() == m
+    for M in (np.array([[0, 0, 5], [0, 0, 0]]), np.eye(6, dtype=np.int64), np.ones((4, 9), dtype=np.int64)):
+        A = gpu.CSR(M)
+        fo, fg = oracle.echelonize(A), gpu.echelonize(A)
+        checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg))
+        for a, b in zip(oracle.kernel(fo).arrays(), gpu.kernel(fg).arrays()):
+            assert np.array_equal(a, b)
