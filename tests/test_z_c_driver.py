@@ -87,3 +87,22 @@ def test_degenerate_inputs_on_cuda_library(gpu, oracle):
         checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg))
         for a, b in zip(oracle.kernel(fo).arrays(), gpu.kernel(fg).arrays()):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("SPASM_B200_EDGE_TESTS") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a GPU; set SPASM_B200_EDGE_TESTS=1")
+@pytest.mark.parametrize("lazy_k", ["64", "96", "0"])
+def test_deferred_updates_small_depth_bit_exact(gpu, oracle, lazy_k, monkeypatch):
+    """the deferred trailing updates with a tiny flush depth (near rows = a few 16-row panels, many corrections and
+    flushes) against the oracle, bit for bit.  At the default depth the far path only runs on matrices too large
+    for the oracle; there it is covered by the planted-rank and rank(A) = rank(A^T) tests."""
+    import checks
+    import synth
+
+    monkeypatch.setenv("SPASM_B200_LAZY_K", lazy_k)
+    for (n, m, k, prime, seed) in [(1500, 1500, 5, 42013, 3), (900, 1300, 4, 65521, 12), (700, 650, 4, 4294967291, 13)]:
+        p, j, x = synth.random_rows(n, m, k, prime, seed)
+        A = gpu.from_arrays(n, m, p, j, x, prime)
+        kw = dict(dense_block_size=16, sparsity_threshold=0.0, max_round=1)
+        checks.assert_same(checks.lu_arrays(oracle.echelonize(A, **kw)), checks.lu_arrays(gpu.echelonize(A, **kw)), f"lazy_k={lazy_k}: ")
