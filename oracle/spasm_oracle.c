@@ -1008,7 +1008,7 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
 
 /* In-place Gauss-Jordan with leftmost pivots.  The reduced row echelon form is unique, so the
  * VALUES equal what FFPACK's RREF produces; pivcol = column rank profile. */
-int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, int *pivcol) {
+static int dense_rref_unblocked(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, int *pivcol) {
   spasm_field F;
   spasm_field_init(prime, F);
   int rank = 0;
@@ -1152,7 +1152,7 @@ static void echelonize_GPLU(const struct spasm_csr *A, const int *p, int n, cons
 /* dense tail (prototypes src/SpaSM.jl:765-766, :805): blocks of dense_block_size
  * rows are eliminated against U, gathered on the non-pivotal columns, put in RREF; the reduced
  * rows are appended to U as (pivot col, 1) then the non-pivot part in increasing column order. */
-static void echelonize_dense(const struct spasm_csr *A, const int *p, int n, const int *p_in, struct spasm_lu *fact,
+static void echelonize_dense_rowwise(const struct spasm_csr *A, const int *p, int n, const int *p_in, struct spasm_lu *fact,
                              struct echelonize_opts *opts) {
   (void)p_in;
   int m = A->m;
@@ -1219,6 +1219,245 @@ static void echelonize_dense(const struct spasm_csr *A, const int *p, int n, con
   }
   free(x);
   free(xj);
+  free(q);
+  free(qpos);
+}
+
+/* ---- blocked, multi-threaded form of the same dense tail (what FFLAS-FFPACK + OpenMP give libspasm).
+ * The row-by-row form above eliminates every row of a block against the growing U one sparse triangular
+ * solve at a time (single thread, random scatter).  Here the dense Schur complement D of ALL remaining rows
+ * with respect to the structural part of U is built once (independent rows: one OpenMP loop), and each block
+ * is then (1) put in RREF in place and (2) eliminated from the rows below it with a delayed-reduction
+ * matrix product in double precision (exact: |sum| < 2^52), rows in parallel.  Arithmetic in F_p is exact and
+ * the rows of a block are reduced, so "right-looking" (update the later rows now) and "left-looking"
+ * (eliminate a row against all earlier pivots when its block comes up) give the same values: the output is
+ * bit-identical to echelonize_dense_rowwise (tests/test_oracle_invariants.py::test_blocked_dense_equals_rowwise;
+ * SPASM_ORACLE_ROWWISE=1 selects the row-by-row form). */
+typedef double v8d __attribute__((vector_size(64), aligned(8)));
+#define DT_JB 16 /* columns per register tile: two v8d per row */
+#define DT_IB 4  /* rows per register tile */
+
+/* acc[DT_IB][DT_JB] += sum_s c[i][s] * Rp[s][0:DT_JB];  Rp packed (s-major, DT_JB doubles per s) */
+__attribute__((target_clones("default", "avx512f"))) static void dt_microkernel(int K, const double *restrict c, i64 ldc, const double *restrict Rp,
+                                                                                 double *restrict acc) {
+  v8d a00 = *(v8d *)(acc + 0), a01 = *(v8d *)(acc + 8), a10 = *(v8d *)(acc + 16), a11 = *(v8d *)(acc + 24);
+  v8d a20 = *(v8d *)(acc + 32), a21 = *(v8d *)(acc + 40), a30 = *(v8d *)(acc + 48), a31 = *(v8d *)(acc + 56);
+  for (int s = 0; s < K; s++) {
+    const v8d r0 = *(const v8d *)(Rp + (i64)s * DT_JB), r1 = *(const v8d *)(Rp + (i64)s * DT_JB + 8);
+    const double c0 = c[s], c1 = c[ldc + s], c2 = c[2 * ldc + s], c3 = c[3 * ldc + s];
+    a00 += c0 * r0, a01 += c0 * r1;
+    a10 += c1 * r0, a11 += c1 * r1;
+    a20 += c2 * r0, a21 += c2 * r1;
+    a30 += c3 * r0, a31 += c3 * r1;
+  }
+  *(v8d *)(acc + 0) = a00, *(v8d *)(acc + 8) = a01, *(v8d *)(acc + 16) = a10, *(v8d *)(acc + 24) = a11;
+  *(v8d *)(acc + 32) = a20, *(v8d *)(acc + 40) = a21, *(v8d *)(acc + 48) = a30, *(v8d *)(acc + 56) = a31;
+}
+
+/* D[i][:] -= sum_s D[i][pivcol[s]] * R[s][:]  for the nrows rows of D (leading dimension ld, width w) */
+static void dense_trailing_update(spasm_ZZp *D, i64 nrows, int w, i64 ld, const spasm_ZZp *R, i64 ldr, const int *pivcol, int rr,
+                                  const spasm_field F) {
+  if (nrows <= 0 || rr <= 0) return;
+  const i64 prime = F->p;
+  if (prime >= (1LL << 26)) { /* products do not fit a double: exact scalar arithmetic, rows in parallel */
+#pragma omp parallel for schedule(dynamic, 4)
+    for (i64 i = 0; i < nrows; i++) {
+      spasm_ZZp *row = D + i * ld;
+      for (int s = 0; s < rr; s++) {
+        const spasm_ZZp f = row[pivcol[s]];
+        if (f == 0) continue;
+        const spasm_ZZp mf = spasm_ZZp_sub(F, 0, f);
+        const spasm_ZZp *Rs = R + (i64)s * ldr;
+        for (int k = 0; k < w; k++) row[k] = spasm_ZZp_axpy(F, mf, Rs[k], row[k]);
+      }
+    }
+    return;
+  }
+  const double dp = (double)prime, dinv = 1.0 / dp, half = (double)F->halfp, mhalf = (double)F->mhalfp;
+  /* depth of one exact accumulation: |acc| <= halfp + KC * halfp^2 < 2^52 */
+  i64 KC = (i64)(((double)(1LL << 52) - half) / (half * half + 1.0));
+  if (KC > rr) KC = rr;
+  if (KC < 1) KC = 1;
+  const int wt = (w + DT_JB - 1) / DT_JB;
+  double *Rp = spasm_malloc((i64)wt * KC * DT_JB * sizeof(double));
+  const i64 nrows4 = (nrows + DT_IB - 1) / DT_IB * DT_IB;
+  double *coef = spasm_malloc(nrows4 * (i64)rr * sizeof(double));
+  /* the multipliers are read BEFORE the rows change: coef[i][s] = -D[i][pivcol[s]] */
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < nrows4; i++)
+    for (int s = 0; s < rr; s++) coef[i * rr + s] = (i < nrows) ? -(double)D[i * ld + pivcol[s]] : 0.0;
+  for (i64 s0 = 0; s0 < rr; s0 += KC) {
+    const int kc = (int)((rr - s0 < KC) ? rr - s0 : KC);
+    /* pack R[s0:s0+kc][:] into column tiles of DT_JB doubles (zero padded) */
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < wt; t++)
+      for (int s = 0; s < kc; s++) {
+        const spasm_ZZp *Rs = R + (s0 + s) * ldr;
+        double *dst = Rp + ((i64)t * kc + s) * DT_JB;
+        for (int u = 0; u < DT_JB; u++) dst[u] = (t * DT_JB + u < w) ? (double)Rs[t * DT_JB + u] : 0.0;
+      }
+#pragma omp parallel for schedule(dynamic, 2)
+    for (i64 i0 = 0; i0 < nrows; i0 += DT_IB) {
+      double acc[DT_IB * DT_JB] __attribute__((aligned(64)));
+      const int ib = (int)((nrows - i0 < DT_IB) ? nrows - i0 : DT_IB);
+      for (int t = 0; t < wt; t++) {
+        const int j0 = t * DT_JB, jb = (w - j0 < DT_JB) ? w - j0 : DT_JB;
+        for (int a = 0; a < DT_IB; a++)
+          for (int u = 0; u < DT_JB; u++) acc[a * DT_JB + u] = (a < ib && u < jb) ? (double)D[(i0 + a) * ld + j0 + u] : 0.0;
+        dt_microkernel(kc, coef + i0 * rr + s0, rr, Rp + (i64)t * kc * DT_JB, acc);
+        for (int a = 0; a < ib; a++)
+          for (int u = 0; u < jb; u++) {
+            double v = acc[a * DT_JB + u];
+            v -= rint(v * dinv) * dp;
+            if (v > half) v -= dp;
+            if (v < mhalf) v += dp;
+            D[(i0 + a) * ld + j0 + u] = (spasm_ZZp)v;
+          }
+      }
+    }
+  }
+  free(Rp);
+  free(coef);
+}
+
+/* RREF of a dense n x m block.  The reduced row echelon form of a matrix is unique, so it may be computed in
+ * any order: sub-blocks of DT_SB rows are reduced by the textbook loop above and eliminated from ALL the other
+ * rows of the block (earlier pivot rows included) with the delayed-reduction product, which turns the
+ * n^2 m row operations into matrix products.  Invariant: the leftmost non-zero of every pivot row is its pivot
+ * column, so a new pivot never reaches to the left of an older pivot row's leading entry and the final rows
+ * are the reduced row echelon form.  Output contract as before: the reduced rows first, by increasing pivot
+ * column (column rank profile), zero rows after. */
+#define DT_SB 64
+int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, int *pivcol) {
+  if (n <= 2 * DT_SB || getenv("SPASM_ORACLE_ROWWISE") != NULL) return dense_rref_unblocked(prime, n, m, A, ldA, pivcol);
+  spasm_field F;
+  spasm_field_init(prime, F);
+  int *prow = spasm_malloc((i64)n * sizeof(int)), *pcol = spasm_malloc((i64)n * sizeof(int));
+  int *subcol = spasm_malloc((i64)DT_SB * sizeof(int));
+  int npiv = 0;
+  for (int r0 = 0; r0 < n; r0 += DT_SB) {
+    const int sb = (n - r0 < DT_SB) ? n - r0 : DT_SB;
+    spasm_ZZp *S = A + (i64)r0 * ldA;
+    const int rs = dense_rref_unblocked(prime, sb, m, S, ldA, subcol);
+    if (rs == 0) continue;
+    for (int t = 0; t < rs; t++) prow[npiv + t] = r0 + t, pcol[npiv + t] = subcol[t];
+    npiv += rs;
+    dense_trailing_update(A, r0, m, ldA, S, ldA, subcol, rs, F);                                        /* rows above */
+    dense_trailing_update(A + (i64)(r0 + sb) * ldA, n - r0 - sb, m, ldA, S, ldA, subcol, rs, F);        /* rows below */
+    if (npiv == m) break;
+  }
+  /* pivot rows to the top by increasing pivot column; everything else is zero */
+  int *order = spasm_malloc((i64)(npiv > 0 ? npiv : 1) * sizeof(int));
+  for (int t = 0; t < npiv; t++) order[t] = t;
+  for (int a = 1; a < npiv; a++) { /* insertion sort: pcol is already sorted inside each sub-block */
+    int o = order[a], b = a - 1;
+    while (b >= 0 && pcol[order[b]] > pcol[o]) order[b + 1] = order[b], b--;
+    order[b + 1] = o;
+  }
+  spasm_ZZp *tmp = spasm_malloc((i64)(npiv > 0 ? npiv : 1) * m * sizeof(spasm_ZZp));
+#pragma omp parallel for schedule(static)
+  for (int t = 0; t < npiv; t++) memcpy(tmp + (i64)t * m, A + (i64)prow[order[t]] * ldA, (i64)m * sizeof(spasm_ZZp));
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < n; r++) {
+    if (r < npiv)
+      memcpy(A + (i64)r * ldA, tmp + (i64)r * m, (i64)m * sizeof(spasm_ZZp));
+    else
+      memset(A + (i64)r * ldA, 0, (i64)m * sizeof(spasm_ZZp));
+  }
+  for (int t = 0; t < npiv; t++) pivcol[t] = pcol[order[t]];
+  free(tmp);
+  free(order);
+  free(subcol);
+  free(prow);
+  free(pcol);
+  return npiv;
+}
+
+static void echelonize_dense(const struct spasm_csr *A, const int *p, int n, const int *p_in, struct spasm_lu *fact,
+                             struct echelonize_opts *opts) {
+  if (getenv("SPASM_ORACLE_ROWWISE") != NULL) {
+    echelonize_dense_rowwise(A, p, n, p_in, fact, opts);
+    return;
+  }
+  const int m = A->m;
+  struct spasm_csr *U = fact->U;
+  int *Uqinv = fact->qinv;
+  const i64 prime = A->field->p;
+  const int block = opts->dense_block_size > 0 ? opts->dense_block_size : 1000;
+  const int Sm0 = m - U->n;
+  if (Sm0 == 0 || n == 0) return;
+  int *q = spasm_malloc((i64)m * sizeof(int));
+  int *qpos = spasm_malloc((i64)m * sizeof(int));
+  int c = 0;
+  for (int j = 0; j < m; j++) {
+    qpos[j] = -1;
+    if (Uqinv[j] < 0) {
+      q[c] = j;
+      qpos[j] = c++;
+    }
+  }
+  assert(c == Sm0);
+  /* dense Schur complement of every remaining row w.r.t. the structural U (U is not modified in this loop) */
+  const double t_build = spasm_wtime();
+  spasm_ZZp *D = spasm_calloc((i64)n * Sm0, sizeof(spasm_ZZp));
+#pragma omp parallel
+  {
+    spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
+    int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
+#pragma omp for schedule(dynamic, 8)
+    for (int k = 0; k < n; k++) {
+      int top = spasm_sparse_triangular_solve(U, A, p[k], xj, x, Uqinv);
+      for (int px = top; px < m; px++) {
+        int j = xj[px];
+        if (Uqinv[j] < 0) D[(i64)k * Sm0 + qpos[j]] = x[j];
+      }
+    }
+    free(x);
+    free(xj);
+  }
+  logprintf("[echelonize/dense] dense schur complement %d x %d built in %.2fs\n", n, Sm0, spasm_wtime() - t_build);
+  double t_rref = 0, t_upd = 0;
+  int *pivcol = spasm_malloc((i64)block * sizeof(int));
+  int processed = 0;
+  while (processed < n) {
+    if (m - U->n == 0) break;
+    int Sn = (n - processed < block) ? n - processed : block;
+    logprintf("[echelonize/dense] processing dense schur complement of dimension %d x %d; block size=%d\n",
+              n - processed, m - U->n, block);
+    spasm_ZZp *S = D + (i64)processed * Sm0;
+    double t0 = spasm_wtime();
+    int rr = spasm_dense_rref(prime, Sn, Sm0, S, Sm0, pivcol);
+    t_rref += spasm_wtime() - t0;
+    for (int i = 0; i < rr; i++) {
+      const spasm_ZZp *row = S + (i64)i * Sm0;
+      i64 cntnz = 0;
+      for (int k = 0; k < Sm0; k++)
+        if (row[k] != 0) cntnz++;
+      csr_ensure_room(U, spasm_nnz(U) + cntnz);
+      i64 unz = U->p[U->n];
+      int jp = q[pivcol[i]];
+      Uqinv[jp] = U->n;
+      U->j[unz] = jp;
+      U->x[unz] = 1;
+      unz++;
+      for (int k = 0; k < Sm0; k++) {
+        if (k == pivcol[i] || row[k] == 0) continue;
+        U->j[unz] = q[k];
+        U->x[unz] = row[k];
+        unz++;
+      }
+      U->n += 1;
+      U->p[U->n] = unz;
+    }
+    processed += Sn;
+    t0 = spasm_wtime();
+    if (U->n < m) dense_trailing_update(D + (i64)processed * Sm0, n - processed, Sm0, Sm0, S, Sm0, pivcol, rr, A->field);
+    t_upd += spasm_wtime() - t0;
+    logprintf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U->n);
+  }
+  logprintf("[echelonize/dense] block RREFs %.2fs, trailing updates %.2fs\n", t_rref, t_upd);
+  free(pivcol);
+  free(D);
   free(q);
   free(qpos);
 }

@@ -135,7 +135,7 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
                               struct spasm_triplet *L, const int *p_in, int *p_out) {
   (void)est_density;
   try {
-    require_gpu();
+    ApiCall api_scope_;
     double t0 = spasm_wtime();
     DevFactor f;
     f.upload(fact);
@@ -181,7 +181,7 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
 double spasm_schur_estimate_density(const struct spasm_csr *A, const int *p, int n, const struct spasm_csr *U, const int *qinv,
                                     int R_) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     if (n == 0 || A->m == U->n) return 0;
     Fp F = make_field(A->field->p);
     DCsr dA, dU;
@@ -214,7 +214,7 @@ double spasm_schur_estimate_density(const struct spasm_csr *A, const int *p, int
 int spasm_sparse_triangular_solve(const struct spasm_csr *U, const struct spasm_csr *B, int k, int *xj, spasm_ZZp *x,
                                   const int *qinv) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     const int m = U->m;
     Fp F = make_field(U->field->p);
     DCsr dU, dB;
@@ -264,7 +264,7 @@ int spasm_sparse_triangular_solve(const struct spasm_csr *U, const struct spasm_
 // src/SpaSM.jl:876-882; README.md:39-41
 struct spasm_csr *spasm_kernel(const struct spasm_lu *fact) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     double t0 = spasm_wtime();
     const int r = fact->U->n, m = fact->U->m;
     logf("[kernel] start. U is %d x %d (%lld nnz). Transposing U\n", r, m, (long long)spasm_nnz(fact->U));
@@ -294,7 +294,7 @@ struct spasm_csr *spasm_kernel(const struct spasm_lu *fact) {
 // src/SpaSM.jl:871
 struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     const int r = fact->U->n, m = fact->U->m;
     DevFactor f;
     f.upload(fact);

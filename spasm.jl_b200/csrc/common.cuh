@@ -34,6 +34,15 @@ void errf(const char *fmt, ...);  // errors: always stderr, and the callback whe
 
 // The product has no CPU fallback: every compute entry point calls this first.
 void require_gpu();
+// RAII scope of one public compute entry point: require_gpu() on entry; when the outermost scope ends the
+// cached device memory goes back to the driver (runtime.cu, "Memory policy").  Declare it FIRST in the entry
+// point so that every DBuf of the call is released before it.
+struct ApiCall {
+  ApiCall();
+  ~ApiCall();
+  ApiCall(const ApiCall &) = delete;
+  ApiCall &operator=(const ApiCall &) = delete;
+};
 cudaStream_t stream();
 int sm_count();
 

@@ -208,6 +208,9 @@ __global__ void k_write_rows(const uint32_t *__restrict__ S, long long ld, int m
 }
 
 void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);
+// counters of the deferred trailing updates since the last reset (tests assert that the far-row path ran):
+// [0] far flushes with far rows  [1] multiplier-correction GEMMs  [2] far rows x depth flushed  [3] near updates
+long long g_tail_stats[4] = {0, 0, 0, 0};
 
 void make_free_columns(const int *qinv, int m, int *flag, long long *pos, int *q, int *qpos) {
   cudaStream_t s = stream();
@@ -938,7 +941,10 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   long long gend = (long long)group * block_size;       // my local rows [.., gend) are always up to date
   auto flush_far = [&]() {
     const long long fe = std::min<long long>(gend, n_local);
-    if (Kacc > 0 && fe < n_local) gemm_nt(D.Dt.p + fe, ld, Sm0, (int)(n_local - fe), Rt_acc.p, LDK, Pt_acc.p + fe * LDK, LDK, Kacc, true, F);
+    if (Kacc > 0 && fe < n_local) {
+      gemm_nt(D.Dt.p + fe, ld, Sm0, (int)(n_local - fe), Rt_acc.p, LDK, Pt_acc.p + fe * LDK, LDK, Kacc, true, F);
+      g_tail_stats[0] += 1, g_tail_stats[2] += (n_local - fe) * (long long)Kacc;
+    }
     Kacc = 0;
   };
   for (long long b = 0; b < nb; b++) {
@@ -1031,14 +1037,16 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt_b, LDK);
         if (rr16 > rr) CK(cudaMemset2DAsync(Rt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, Sm0, s));  // zero pad columns: the pad of Pt may hold anything
         k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt_b, LDK);
+        if (rr16 > rr) CK(cudaMemset2DAsync(Pt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, nk, s));  // and the pad of Pt: no garbage x 0
         if (Kacc > 0 && fe < n_local) {
           // the far rows of these pivot columns still miss the pending updates
           k_gather_rows_ld<<<dim3(cdiv(Kacc, 256), rr), 256, 0, s>>>(Rt_acc.p, LDK, pivcol.p, rr, Kacc, Rsel.p, LDK);
           gemm_nt(Pt_acc.p + fe * LDK + Kacc, LDK, (int)(n_local - fe), rr, Pt_acc.p + fe * LDK, LDK, Rsel.p, LDK, Kacc, true, F);
           g_launches += 1;
+          g_tail_stats[1] += 1;
         }
         tick(3, t1);
-        if (fe > kb) gemm_nt(D.Dt.p + kb, ld, Sm0, (int)(fe - kb), Rt_b, LDK, Pt_b, LDK, rr, true, F);
+        if (fe > kb) gemm_nt(D.Dt.p + kb, ld, Sm0, (int)(fe - kb), Rt_b, LDK, Pt_b, LDK, rr, true, F), g_tail_stats[3] += 1;
         Kacc += rr16;
         if (Kacc + B16 > kcap || fe >= n_local) flush_far();
         tick(4, t1);
@@ -1195,7 +1203,7 @@ extern "C" int spasm_b200_dense_tail_bench_planted(long long prime, int n, int m
 }
 static int dense_tail_bench_impl(long long prime, int n, int m, int planted_rank, int block_size, unsigned long long seed, double *ms) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     Fp F = make_field(prime);
     DenseSchur D;
     D.n_rem = n, D.Sm0 = m, D.levels = 0;
@@ -1238,10 +1246,16 @@ static int dense_tail_bench_impl(long long prime, int n, int m, int planted_rank
   }
 }
 
+extern "C" void spasm_b200_tail_stats(long long *out, int reset) {
+  for (int i = 0; i < 4; i++) out[i] = sb::g_tail_stats[i];
+  if (reset)
+    for (int i = 0; i < 4; i++) sb::g_tail_stats[i] = 0;
+}
+
 // the dense-tail entry point of the ABI (replaces spasm_ffpack_rref, src/SpaSM.jl:805)
 extern "C" int spasm_dense_rref(i64 prime, int n, int m, spasm_ZZp *A, i64 ldA, int *pivcol_out) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     Fp F = make_field(prime);
     DBuf<int> tmp((size_t)n * m);
     DBuf<uint32_t> S((size_t)n * m);

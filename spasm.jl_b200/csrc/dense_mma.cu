@@ -423,7 +423,7 @@ extern "C" int spasm_b200_gemm_nt_host(long long prime, int M, int N, int K, con
                                        int path, double *ms_out) {
   using namespace sb;
   try {
-    require_gpu();
+    ApiCall api_scope_;
     Fp F = make_field(prime);
     DBuf<uint32_t> dA((size_t)M * K), dB((size_t)N * K), dC((size_t)M * N);
     dA.upload(A, (size_t)M * K);

@@ -76,7 +76,7 @@ int spasm_b200_nccl_unique_id(unsigned char *out128) {
 }
 int spasm_b200_dist_init(int rank, int nranks, const unsigned char *id128) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     if (nranks <= 1) {
       dist() = Dist();
       return 0;

@@ -255,7 +255,7 @@ static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, in
 // ------------------------------------------------------------------ the driver
 static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, const DCsr *resident = nullptr, bool download = true,
                                  int *rank_out = nullptr) {
-  require_gpu();
+  ApiCall api_scope_;
   echelonize_opts defaults;
   if (opts == nullptr) {
     spasm_echelonize_init_opts(&defaults);
@@ -514,7 +514,7 @@ struct ResidentMatrix {
 };
 void *spasm_b200_upload(const struct spasm_csr *A) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     auto *h = new ResidentMatrix{A, {}};
     upload_csr(A, h->dev, make_field(A->field->p));
     sync();
@@ -526,7 +526,7 @@ void *spasm_b200_upload(const struct spasm_csr *A) {
 }
 int spasm_b200_echelonize_resident(void *handle, struct echelonize_opts *opts, double *ms) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     auto *h = (ResidentMatrix *)handle;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -567,7 +567,7 @@ void spasm_lu_free(struct spasm_lu *N) {
 int spasm_pivots_extract_structural(const struct spasm_csr *A, const int *p_in, struct spasm_lu *fact, int *p,
                                     struct echelonize_opts *opts) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     Echelon E;
     E.prime = A->field->p;
     E.F = make_field(E.prime);

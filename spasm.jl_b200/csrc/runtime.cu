@@ -12,6 +12,14 @@ long long g_launches = 0;
 static cudaStream_t g_stream = nullptr;
 static int g_sms = 0;
 static bool g_ready = false;
+// Memory policy.  By default the library holds device memory only while one of its entry points runs: a
+// second process (CUDA.jl in the same Julia session, another library instance) must find the HBM free after a
+// 200k x 200k echelonization.  A host that calls the library in a loop on same-shaped inputs (bench.py) may
+// opt in to keeping the large blocks and the pool across calls with spasm_b200_set_cache(1) /
+// SPASM_B200_KEEP_CACHE=1 and give them back with spasm_b200_trim().
+static bool g_keep_cache = false;
+static int g_api_depth = 0;
+static const size_t POOL_KEEP_BYTES = (size_t)64 << 20;
 
 void require_gpu() {
   if (g_ready) return;
@@ -28,8 +36,11 @@ void require_gpu() {
   CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t thresh = UINT64_MAX;  // keep freed blocks cached in the pool
+  // freed blocks stay cached in the pool WHILE a call runs (thousands of stream-ordered allocations per
+  // echelonization); ApiCall gives everything back to the driver when the outermost call returns.
+  uint64_t thresh = UINT64_MAX;
   CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  if (const char *e = getenv("SPASM_B200_KEEP_CACHE")) g_keep_cache = atoi(e) != 0;
   g_ready = true;
 }
 cudaStream_t stream() { return g_stream; }
@@ -50,6 +61,23 @@ static const size_t BIG = (size_t)256 << 20;
 static void big_trim() {
   for (auto &b : g_big_free) cudaFreeAsync(b.p, g_stream);
   g_big_free.clear();
+}
+
+static void release_cached(size_t keep) {
+  if (!g_stream) return;
+  big_trim();
+  cudaStreamSynchronize(g_stream);
+  cudaMemPool_t pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, keep);
+}
+ApiCall::ApiCall() {
+  require_gpu();
+  g_api_depth++;
+}
+ApiCall::~ApiCall() {
+  if (--g_api_depth == 0 && !g_keep_cache) release_cached(POOL_KEEP_BYTES);
 }
 
 void *dmalloc_bytes(size_t bytes) {
@@ -273,21 +301,32 @@ void transpose_csr(const DCsr &A, DCsr &T) {
 }  // namespace sb
 
 // give the cached large device blocks back to the driver
-extern "C" void spasm_b200_trim(void) {
+extern "C" void spasm_b200_trim(void) { sb::release_cached(0); }
+// keep != 0: device blocks stay cached between calls (same-shaped calls in a loop allocate nothing);
+// keep == 0 (default): everything is returned to the driver when an entry point returns
+extern "C" void spasm_b200_set_cache(int keep) {
+  sb::g_keep_cache = keep != 0;
+  if (!keep) sb::release_cached(0);
+}
+// bytes of device memory this process still holds in the library's caches (0 after a trim)
+extern "C" long long spasm_b200_cached_bytes(void) {
+  long long tot = 0;
+  for (auto &b : sb::g_big_free) tot += (long long)b.bytes;
   if (sb::g_stream) {
-    sb::big_trim();
-    cudaStreamSynchronize(sb::g_stream);
     cudaMemPool_t pool;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    uint64_t reserved = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess)
+      tot += (long long)reserved;
   }
+  return tot;
 }
 
 // src/SpaSM.jl:589 — ONE argument; values always kept (test/runtests.jl:12-15)
 extern "C" struct spasm_csr *spasm_transpose(const struct spasm_csr *A) {
   try {
-    sb::require_gpu();
+    sb::ApiCall api_scope_;
     sb::Fp F = sb::make_field(A->field->p);
     sb::DCsr dA, dT;
     if (A->x == nullptr) throw sb::Error("spasm_transpose: pattern-only matrices are not supported");

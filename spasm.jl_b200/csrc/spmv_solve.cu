@@ -169,7 +169,7 @@ extern "C" {
 
 void spasm_xApy(const spasm_ZZp *x, const struct spasm_csr *A, spasm_ZZp *y) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     Fp F = make_field(A->field->p);
     DCsr dA, dT;
     upload_csr(A, dA, F);
@@ -181,7 +181,7 @@ void spasm_xApy(const spasm_ZZp *x, const struct spasm_csr *A, spasm_ZZp *y) {
 }
 void spasm_Axpy(const struct spasm_csr *A, const spasm_ZZp *x, spasm_ZZp *y) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     Fp F = make_field(A->field->p);
     DCsr dA;
     upload_csr(A, dA, F);
@@ -193,7 +193,7 @@ void spasm_Axpy(const struct spasm_csr *A, const spasm_ZZp *x, spasm_ZZp *y) {
 
 bool spasm_dense_forward_solve(const struct spasm_csr *U, spasm_ZZp *b, spasm_ZZp *x, const int *q) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     const int m = U->m, r = U->n;
     DevFactor f;
     f.prime = U->field->p;
@@ -216,7 +216,7 @@ bool spasm_dense_forward_solve(const struct spasm_csr *U, spasm_ZZp *b, spasm_ZZ
 }
 bool spasm_dense_back_solve(const struct spasm_csr *L, spasm_ZZp *b, spasm_ZZp *x, const int *p) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     Fp F = make_field(L->field->p);
     LSystem S;
     build_Lsystem(L, p, F, S);
@@ -234,7 +234,7 @@ bool spasm_dense_back_solve(const struct spasm_csr *L, spasm_ZZp *b, spasm_ZZp *
 
 bool spasm_solve(const struct spasm_lu *fact, const spasm_ZZp *b, spasm_ZZp *x) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     if (fact->L == nullptr) throw Error("spasm_solve needs a factorisation computed with L=true");
     DevFactor f;
     f.upload(fact);
@@ -257,7 +257,7 @@ bool spasm_solve(const struct spasm_lu *fact, const spasm_ZZp *b, spasm_ZZp *x) 
 
 struct spasm_csr *spasm_gesv(const struct spasm_lu *fact, const struct spasm_csr *B, bool *ok) {
   try {
-    require_gpu();
+    ApiCall api_scope_;
     if (fact->L == nullptr) throw Error("spasm_gesv needs a factorisation computed with L=true");
     DevFactor f;
     f.upload(fact);
