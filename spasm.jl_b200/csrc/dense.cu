@@ -227,7 +227,8 @@ void make_free_columns(const int *qinv, int m, int *flag, long long *pos, int *q
 // over for p < 2^16 and large shapes.)
 template <bool SMALL>
 __global__ void __launch_bounds__(256) k_gemm_nt(uint32_t *__restrict__ C, long long ldc, int M, int N, const uint32_t *__restrict__ A,
-                                                  long long lda, const uint32_t *__restrict__ B, long long ldb, int K, int subtract, Fp F) {
+                                                  long long lda, const uint32_t *__restrict__ B, long long ldb, int K, int subtract,
+                                                  const int *__restrict__ rowmap, Fp F) {
   __shared__ uint32_t As[64][33], Bs[64][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256) k_gemm_nt(uint32_t *__restrict__ C, long 
     for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
       const int rr = idx >> 5, kk = idx & 31;
       const int gi = i0 + rr, gj = j0 + rr, gk = k0 + kk;
-      As[rr][kk] = (gi < M && gk < K) ? A[(long long)gi * lda + gk] : 0u;
+      As[rr][kk] = (gi < M && gk < K) ? A[(long long)(rowmap ? rowmap[gi] : gi) * lda + gk] : 0u;
       Bs[rr][kk] = (gj < N && gk < K) ? B[(long long)gj * ldb + gk] : 0u;
     }
     __syncthreads();
@@ -270,28 +271,28 @@ __global__ void __launch_bounds__(256) k_gemm_nt(uint32_t *__restrict__ C, long 
       const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
       if (gi < M && gj < N) {
         uint32_t v = red64(acc[a][b], F);
-        uint32_t *c = C + (long long)gi * ldc + gj;
+        uint32_t *c = C + (long long)(rowmap ? rowmap[gi] : gi) * ldc + gj;
         *c = subtract ? addmod(*c, negmod(v, F), F) : v;
       }
     }
 }
 
 bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
-                 bool subtract, const Fp &F);  // dense_mma.cu: returns false when the shape / prime is not handled
+                 bool subtract, const Fp &F, const int *rowmap);  // dense_mma.cu: returns false when the shape / prime is not handled
 
 void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
-             bool subtract, const Fp &F) {
+             bool subtract, const Fp &F, const int *rowmap) {
   if (M <= 0 || N <= 0) return;
-  if (gemm_nt_mma(C, ldc, M, N, A, lda, B, ldb, K, subtract, F)) {
+  if (gemm_nt_mma(C, ldc, M, N, A, lda, B, ldb, K, subtract, F, rowmap)) {
     g_launches += 3;  // two limb splits + the tcgen05 kernel
     return;
   }
   g_launches += 1;
   dim3 grid(cdiv(N, 64), cdiv(M, 64));
   if (F.small)
-    k_gemm_nt<true><<<grid, 256, 0, stream()>>>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F);
+    k_gemm_nt<true><<<grid, 256, 0, stream()>>>(C, ldc, M, N, A, lda, B, ldb, K, subtract, rowmap, F);
   else
-    k_gemm_nt<false><<<grid, 256, 0, stream()>>>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F);
+    k_gemm_nt<false><<<grid, 256, 0, stream()>>>(C, ldc, M, N, A, lda, B, ldb, K, subtract, rowmap, F);
   CK(cudaGetLastError());
 }
 
@@ -939,10 +940,20 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   if (lazy) Rt_acc.alloc((size_t)Sm0 * LDK), Pt_acc.alloc((size_t)n_local * LDK), Rsel.alloc((size_t)B16 * LDK);
   int Kacc = 0;                                         // depth of the pending product
   long long gend = (long long)group * block_size;       // my local rows [.., gend) are always up to date
+  // live columns: cand[0:nlive) = the columns that are not pivots of a panel factored so far, increasing.  Pivoted
+  // columns are dead (zero on every remaining row): the panel factorisation scans, and the trailing products
+  // update, the live columns only — the work shrinks with the elimination (n^3/3 instead of n^3/2).
+  int nlive = Sm0;
+  auto refresh_live = [&]() {
+    k_not_flag<<<cdiv(Sm0 + 1, 256), 256, 0, s>>>(colpiv.p, Sm0, cflag.p);
+    exclusive_scan_i32_to_i64(cflag.p, cpos.p, Sm0 + 1);
+    k_compact_flags_i32(cflag.p, cpos.p, Sm0, cand.p);
+  };
+  refresh_live();
   auto flush_far = [&]() {
     const long long fe = std::min<long long>(gend, n_local);
-    if (Kacc > 0 && fe < n_local) {
-      gemm_nt(D.Dt.p + fe, ld, Sm0, (int)(n_local - fe), Rt_acc.p, LDK, Pt_acc.p + fe * LDK, LDK, Kacc, true, F);
+    if (Kacc > 0 && fe < n_local && nlive > 0) {
+      gemm_nt(D.Dt.p + fe, ld, nlive, (int)(n_local - fe), Rt_acc.p, LDK, Pt_acc.p + fe * LDK, LDK, Kacc, true, F, cand.p);
       g_tail_stats[0] += 1, g_tail_stats[2] += (n_local - fe) * (long long)Kacc;
     }
     Kacc = 0;
@@ -968,11 +979,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       const long long k0 = lb * block_size;
       DBuf<int> pc_tmp;
       // candidate columns of this panel: everything that is not a pivot of an earlier panel
-      k_not_flag<<<cdiv(Sm0 + 1, 256), 256, 0, s>>>(colpiv.p, Sm0, cflag.p);
-      exclusive_scan_i32_to_i64(cflag.p, cpos.p, Sm0 + 1);
-      k_compact_flags_i32(cflag.p, cpos.p, Sm0, cand.p);
-      const int ncand = (int)fetch(cpos.p + Sm0);
-      rr = panel_factor(D.Dt.p, ld, cand.p, ncand, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F);
+      rr = panel_factor(D.Dt.p, ld, cand.p, nlive, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F);
       if (rr > 0) CK(cudaMemcpyAsync(pivcol.p, pc_tmp.p, (size_t)rr * sizeof(int), cudaMemcpyDeviceToDevice, s));
       tick(0, t1);
       if (rr > 0) {
@@ -996,6 +1003,8 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     }
     if (rr > 0) {
       k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pivcol.p, rr, colpiv.p);
+      refresh_live();
+      nlive -= rr;
       if (emit_rows) {
         // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
         DBuf<int> cnt(rr + 1);
@@ -1028,7 +1037,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
         k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt.p, ldk);
         tick(3, t1);
-        gemm_nt(D.Dt.p + kb, ld, Sm0, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F);
+        if (nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F, cand.p);
         tick(4, t1);
       } else if (nk > 0) {
         const int rr16 = (rr + 15) / 16 * 16;
@@ -1046,7 +1055,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
           g_tail_stats[1] += 1;
         }
         tick(3, t1);
-        if (fe > kb) gemm_nt(D.Dt.p + kb, ld, Sm0, (int)(fe - kb), Rt_b, LDK, Pt_b, LDK, rr, true, F), g_tail_stats[3] += 1;
+        if (fe > kb && nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, (int)(fe - kb), Rt_b, LDK, Pt_b, LDK, rr, true, F, cand.p), g_tail_stats[3] += 1;
         Kacc += rr16;
         if (Kacc + B16 > kcap || fe >= n_local) flush_far();
         tick(4, t1);

@@ -28,8 +28,9 @@ void dense_rows_to_sparse(const uint32_t *M, long long ld, int nvec, const int *
 void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U, const int *Uqinv, const Fp &F, DenseSchur &D);
 
 // C (M x N, row-major, ldc) = [C -] A (M x K, row-major lda) . B^T (B is N x K, row-major ldb)   (mod p)
+// rowmap (device, M entries, optional): row r of the product reads row rowmap[r] of A and updates row rowmap[r] of C
 void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
-             bool subtract, const Fp &F);
+             bool subtract, const Fp &F, const int *rowmap = nullptr);
 
 // eliminate the rows `rows` of A against U block by block, RREF each block, append to U
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);

@@ -122,7 +122,7 @@ template <bool SUB>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, uint32_t *__restrict__ C, long long ldc,
-              int M, int N, int nkb, int tiles_m, int tiles_n, Fp F) {
+              int M, int N, int nkb, int tiles_m, int tiles_n, const int *__restrict__ rowmap, Fp F) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *tiles = (uint8_t *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   uint32_t *stage = (uint32_t *)(tiles + STAGES * STAGE_BYTES);
@@ -219,21 +219,27 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       for (int h = 0; h < 2; h++) {
         const int nh = n0 + h * HALF;
         uint4 cv[16];
-        // interior tiles: 16 unconditional 16-byte loads off one base pointer (all in flight together)
+        // interior tiles: 16 unconditional 16-byte loads (all in flight together).  Row r of the product is row
+        // rowmap[r] of C when a map is given (the dense tail only updates the columns that are still live).
         const bool interior = vec_ok && (m0 + TILE <= M) && (nh + HALF <= N);
-        uint32_t *cbase = C + (long long)(m0 + e * 2 + sub) * ldc + nh + l16 * 4;
-        const long long rstep = 8 * ldc;
+        uint32_t *crow[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int row = m0 + (i * 4 + e) * 2 + sub;
+          const long long grow = (rowmap != nullptr) ? (long long)(row < M ? rowmap[row] : 0) : (long long)row;
+          crow[i] = C + grow * ldc + nh + l16 * 4;
+        }
         if (SUB) {
           if (interior) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) cv[i] = *(const uint4 *)(cbase + i * rstep);
+            for (int i = 0; i < 16; i++) cv[i] = *(const uint4 *)crow[i];
           } else {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
               const int row = m0 + (i * 4 + e) * 2 + sub, col = nh + l16 * 4;
               cv[i] = make_uint4(0, 0, 0, 0);
               if (row < M) {
-                const uint32_t *p = cbase + i * rstep;
+                const uint32_t *p = crow[i];
                 if (col + 0 < N) cv[i].x = p[0];
                 if (col + 1 < N) cv[i].y = p[1];
                 if (col + 2 < N) cv[i].z = p[2];
@@ -277,7 +283,7 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
               r.z = addmod(cv[i].z, negmod(r.z, F), F);
               r.w = addmod(cv[i].w, negmod(r.w, F), F);
             }
-            *(uint4 *)(cbase + i * rstep) = r;
+            *(uint4 *)crow[i] = r;
           }
         } else {
 #pragma unroll
@@ -292,7 +298,7 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                 r.z = addmod(cv[i].z, negmod(r.z, F), F);
                 r.w = addmod(cv[i].w, negmod(r.w, F), F);
               }
-              uint32_t *p = cbase + i * rstep;
+              uint32_t *p = crow[i];
               if (col + 0 < N) p[0] = r.x;
               if (col + 1 < N) p[1] = r.y;
               if (col + 2 < N) p[2] = r.z;
@@ -312,14 +318,14 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
 
 // ------------------------------------------------------------------ limb split (u32 residues -> two K-major u8 planes, zero padded)
 __global__ void k_split_limbs(const uint32_t *__restrict__ in, long long ld, int rows, int K, uint8_t *__restrict__ lo, uint8_t *__restrict__ hi,
-                              int rows_pad, int Kpad) {
+                              int rows_pad, int Kpad, const int *__restrict__ rowmap) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one thread per 4 k
   const int kq = Kpad >> 2;
   if (idx >= (long long)rows_pad * kq) return;
   const int r = (int)(idx / kq), k = (int)(idx % kq) * 4;
   uchar4 l = make_uchar4(0, 0, 0, 0), h = make_uchar4(0, 0, 0, 0);
   if (r < rows) {
-    const uint32_t *src = in + (long long)r * ld + k;
+    const uint32_t *src = in + (long long)(rowmap ? rowmap[r] : r) * ld + k;
     uint32_t v0 = k + 0 < K ? src[0] : 0u, v1 = k + 1 < K ? src[1] : 0u, v2 = k + 2 < K ? src[2] : 0u, v3 = k + 3 < K ? src[3] : 0u;
     l = make_uchar4(v0 & 255, v1 & 255, v2 & 255, v3 & 255);
     h = make_uchar4(v0 >> 8, v1 >> 8, v2 >> 8, v3 >> 8);
@@ -361,8 +367,23 @@ double g_mma_macs = 0;  // modular MACs (x4 int8 MACs)
 long long g_mma_calls = 0;
 static bool g_mma_disabled = false;
 
+// optional timing of the tcgen05 launches (bench.py / SPASM_B200_PROFILE): events are recorded around each launch
+// and only read when the statistics are queried — no host synchronisation on the launch path
+static bool g_mma_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_pending, g_ev_free;
+static void mma_collect_timings() {
+  for (auto &pr : g_ev_pending) {
+    if (cudaEventSynchronize(pr.second) == cudaSuccess) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) g_mma_ms += ms;
+    }
+    g_ev_free.push_back(pr);
+  }
+  g_ev_pending.clear();
+}
+
 bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
-                 bool subtract, const Fp &F) {
+                 bool subtract, const Fp &F, const int *rowmap) {
   if (g_mma_disabled || !F.small) return false;
   if (K < 64 || K > 16384 || (long long)M * N < 4LL * TILE * TILE) return false;
   static bool env_checked = false;
@@ -376,8 +397,8 @@ bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, lo
   cudaStream_t s = stream();
   const int Mp = (M + TILE - 1) / TILE * TILE, Np = (N + TILE - 1) / TILE * TILE, Kp = (K + BK - 1) / BK * BK;
   DBuf<uint8_t> a0((size_t)Mp * Kp), a1((size_t)Mp * Kp), b0((size_t)Np * Kp), b1((size_t)Np * Kp);
-  k_split_limbs<<<cdiv((long long)Mp * (Kp >> 2), 256), 256, 0, s>>>(A, lda, M, K, a0.p, a1.p, Mp, Kp);
-  k_split_limbs<<<cdiv((long long)Np * (Kp >> 2), 256), 256, 0, s>>>(B, ldb, N, K, b0.p, b1.p, Np, Kp);
+  k_split_limbs<<<cdiv((long long)Mp * (Kp >> 2), 256), 256, 0, s>>>(A, lda, M, K, a0.p, a1.p, Mp, Kp, rowmap);
+  k_split_limbs<<<cdiv((long long)Np * (Kp >> 2), 256), 256, 0, s>>>(B, ldb, N, K, b0.p, b1.p, Np, Kp, nullptr);
   CUtensorMap mA0 = make_map(a0.p, Mp, Kp), mA1 = make_map(a1.p, Mp, Kp), mB0 = make_map(b0.p, Np, Kp), mB1 = make_map(b1.p, Np, Kp);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + sizeof(MmaShared) + 64;
   static bool attr_set = false;
@@ -388,22 +409,27 @@ bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, lo
   }
   const int tiles_m = Mp / TILE, tiles_n = Np / TILE;
   const int grid = (int)std::min<long long>((long long)tiles_m * tiles_n, sm_count());
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0, s));
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (g_mma_timing) {
+    if (g_ev_pending.size() >= 4096) mma_collect_timings();
+    if (!g_ev_free.empty()) {
+      ev = g_ev_free.back();
+      g_ev_free.pop_back();
+    } else {
+      CK(cudaEventCreate(&ev.first));
+      CK(cudaEventCreate(&ev.second));
+    }
+    CK(cudaEventRecord(ev.first, s));
+  }
   if (subtract)
-    k_gemm_i8limb<true><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, F);
+    k_gemm_i8limb<true><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, rowmap, F);
   else
-    k_gemm_i8limb<false><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, F);
+    k_gemm_i8limb<false><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, rowmap, F);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e1, s));
-  CK(cudaEventSynchronize(e1));
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  g_mma_ms += ms;
+  if (g_mma_timing) {
+    CK(cudaEventRecord(ev.second, s));
+    g_ev_pending.push_back(ev);
+  }
   g_mma_macs += (double)M * N * K;  // algorithmic (unpadded) modular MACs
   g_mma_calls++;
   return true;
@@ -412,9 +438,100 @@ bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, lo
 }  // namespace sb
 
 // {ms in the tcgen05 kernel, modular MACs it computed, calls, kernels launched by the library}
+extern "C" void spasm_b200_mma_timing(int on) { sb::g_mma_timing = on != 0; }
 extern "C" void spasm_b200_mma_stats(double *out, int reset) {
+  sb::mma_collect_timings();
   out[0] = sb::g_mma_ms, out[1] = sb::g_mma_macs, out[2] = (double)sb::g_mma_calls, out[3] = (double)sb::g_launches;
   if (reset) sb::g_mma_ms = sb::g_mma_macs = 0, sb::g_mma_calls = 0, sb::g_launches = 0;
+}
+
+// ------------------------------------------------------------------ measured tensor-pipe peak
+// Back-to-back tcgen05.mma.kind::i8 M128 x N256 x K32 (SASS UTCIMMA) on every SM, operands resident in shared
+// memory (no TMA, no epilogue): the denominator SURVEY.md section 8d asks for.  One CTA per SM, one issuing
+// thread, two 256-column accumulators used alternately; `iters` groups of 8 instructions per CTA.
+namespace sb {
+static constexpr uint32_t IDESC_N256 = (2u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__global__ void __launch_bounds__(128, 1) k_utcimma_peak(int iters) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *tiles = (uint8_t *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  for (int i = threadIdx.x; i < (128 + 256) * 128 / 4; i += blockDim.x) ((uint32_t *)tiles)[i] = 0x01010101u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  if (threadIdx.x == 0) {
+    const uint32_t base = smem_u32(tiles);
+    const uint64_t a = make_desc(base), b = make_desc(base + 128 * 128);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        const uint64_t adv = (uint64_t)(ks * 32 >> 4);
+        const uint32_t acc = (it | ks) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+            "l"(a + adv), "l"(b + adv), "r"(IDESC_N256), "r"(acc)
+            : "memory");
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + 256),
+            "l"(a + adv), "l"(b + adv), "r"(IDESC_N256), "r"(acc)
+            : "memory");
+      }
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+}  // namespace sb
+
+// returns the measured int8 tensor throughput in TOP/s (2 ops per int8 MAC), best of `reps`; < 0 on failure
+extern "C" double spasm_b200_utcimma_peak(int iters, int reps) {
+  using namespace sb;
+  try {
+    ApiCall api_scope_;
+    if (iters <= 0) iters = 4096;
+    if (reps <= 0) reps = 5;
+    const size_t smem = (size_t)(128 + 256) * 128 + 1024;
+    CK(cudaFuncSetAttribute(k_utcimma_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int r = 0; r < reps + 1; r++) {
+      CK(cudaEventRecord(e0, stream()));
+      k_utcimma_peak<<<sm_count(), 128, smem, stream()>>>(iters);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(e1, stream()));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double ops = 2.0 * 128 * 256 * 32 * 8.0 * iters * sm_count();
+      if (r > 0) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+  } catch (const std::exception &e) {
+    errf("[spasm_b200] utcimma peak measurement failed: %s\n", e.what());
+    return -1;
+  }
 }
 
 // test / bench hook: C = [C -] A . B^T mod p on host arrays of residues in [0,p).
