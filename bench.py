@@ -37,7 +37,9 @@ FULL_N = 200_000
 KNOWN_RANK_FULL = 199_993
 NNZ_ROW = 10
 SEED = 0x5A5A0002
-CPU_SAMPLE_N = 3000  # ~10 s of oracle work with 8 threads
+CPU_SAMPLE_N = 20000       # cpu_baseline leg of the product arm: ~20 s of oracle work on 8 cores (blocked OpenMP dense tail)
+REF_BUDGET_S = 150.0       # --impl reference: total CPU seconds the K + W sample steps may take
+REF_SAMPLE_MAX = 24000     # largest sample the oracle finishes in <= 60 s on 8 cores
 TIMING_NAMES = "total upload FL FLcol greedy reorder_extract density schur tail download rounds flcol_rounds greedy_windows schur_bytes schur_macs schur_ms".split()
 
 
@@ -101,8 +103,52 @@ def csr_bytes(n, nnz):
     return 8 * (n + 1) + 8 * nnz
 
 
+def gpu_same_sample(pkg, entry, n, p, j, x, expect_rank):
+    """the SAME sample through the CUDA library, when a device is present: (resident s, end-to-end s) or (None, None)"""
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return None, None
+        gpu = pkg.SpaSM()
+        gpu.log(False)
+        lib = gpu.lib
+        lib.spasm_b200_upload.restype = C.c_void_p
+        lib.spasm_b200_upload.argtypes = [C.c_void_p]
+        lib.spasm_b200_echelonize_resident.restype = C.c_int
+        lib.spasm_b200_echelonize_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        lib.spasm_b200_release.argtypes = [C.c_void_p]
+        Ag = gpu.from_arrays(n, n, p, j, x, PRIME)
+        opts = gpu.EchelonizeOpts()
+        h = lib.spasm_b200_upload(C.cast(Ag.data, C.c_void_p))
+        res, e2e = [], []
+        for it in range(3):
+            ms = C.c_double(0)
+            r = lib.spasm_b200_echelonize_resident(h, C.byref(opts), C.byref(ms))
+            assert r == expect_rank, (r, expect_rank)
+            if it:
+                res.append(ms.value / 1e3)
+        lib.spasm_b200_release(h)
+        for it in range(3):
+            t = time.perf_counter()
+            f = gpu.echelonize(Ag)
+            rk = f.r
+            dt = time.perf_counter() - t
+            assert rk == expect_rank
+            del f
+            if it:
+                e2e.append(dt)
+        return sum(res) / len(res), sum(e2e) / len(e2e)
+    except Exception as exc:  # the reference arm must not die because of the product
+        print(f"bench.py: same-sample GPU leg skipped: {exc}", file=sys.stderr)
+        return None, None
+
+
 def run_reference(args):
-    """CPU arm: the oracle restatement of libspasm (oracle/), all host threads, bounded sample."""
+    """CPU arm: the oracle restatement of libspasm (oracle/), all host threads, on a BOUNDED SAMPLE of the
+    workload (same generator, fewer rows).  time-to-rank of a sample is not the time-to-rank of the 200k matrix,
+    so this line carries NO top-level value (null): the comparable numbers are cpu_baseline.value (CPU seconds on the
+    sample) next to cpu_baseline.gpu_same_sample_s / gpu_same_sample_e2e_s (the CUDA library on the same sample)."""
     import __graft_entry__ as entry
 
     rank = int(os.environ.get("RANK", "0"))
@@ -110,14 +156,27 @@ def run_reference(args):
         return
     pkg = entry.load_package()
     ora = pkg.SpaSM(entry.build_oracle())
-    n = args.rows or CPU_SAMPLE_N
+    ora.log(False)
+    ora.lib.spasm_oracle_set_num_threads(0)  # every host core, whatever OMP_NUM_THREADS the launcher exported
+    cores = int(ora.lib.spasm_get_num_threads())
+    W = 0 if args.warmup is None else args.warmup
+    K = args.steps or 1
+    n = args.rows
+    if not n:
+        # calibrate: one 4000-row run, cubic growth, K + W steps inside the budget
+        p4, j4, x4 = make_input(4000)
+        A4 = ora.from_arrays(4000, 4000, p4, j4, x4, PRIME)
+        t = time.perf_counter()
+        ora.echelonize(A4)
+        t4 = max(time.perf_counter() - t, 1e-3)
+        per_step = REF_BUDGET_S / (K + W)
+        n = int(4000 * (per_step / t4) ** (1.0 / 3.0)) // 1000 * 1000
+        n = max(4000, min(REF_SAMPLE_MAX, n))
     p, j, x = make_input(n)
     A = ora.from_arrays(n, n, p, j, x, PRIME)
-    cores = ora.lib.spasm_get_num_threads()
-    for _ in range(args.warmup if args.warmup is not None else 0):
+    for _ in range(W):
         ora.echelonize(A)
     times = []
-    K = args.steps or 1
     r = None
     for _ in range(K):
         t = time.perf_counter()
@@ -126,18 +185,21 @@ def run_reference(args):
         r = f.r
         del f
     val = sum(times) / len(times)
+    g_res, g_e2e = gpu_same_sample(pkg, entry, n, p, j, x, r)
     line = {
         "impl": "reference",
-        "metric": "echelonize_time_to_rank", "value": val, "unit": "s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup or 0,
-        "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "int32 residues mod p (i64 products)",
+        "metric": "echelonize_time_to_rank", "value": None, "unit": "s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "int32 residues mod p (fp64 delayed-reduction products)",
         "data": "synthetic",
-        "config": {"workload": f"random sparse {FULL_N}x{FULL_N}, {NNZ_ROW} nnz/row, echelonize+rank mod {PRIME} (BASELINE configs[1])",
-                   "sample": f"same generator at n={n} ({n}x{n}); the value is the time of this SAMPLE, not of the full matrix"},
-        "cpu_baseline": {"value": val, "unit": "s", "cores": int(cores), "kind": "port",
-                         "sample": f"oracle restatement of libspasm, {cores} cores, {n}x{n} instance of the same generator (rank {r})",
-                         "extrapolated_full_s": val * (FULL_N / n) ** 3,
-                         "extrapolation": "cubic in the number of rows (the dense tail dominates); an estimate, not a measurement"},
-        "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "value_note": "null on purpose: the CPU cannot echelonize the 200000-row matrix in bounded time, and the time of a smaller sample is not "
+                      "this metric; compare cpu_baseline.value with cpu_baseline.gpu_same_sample_s / gpu_same_sample_e2e_s (same matrix, same box)",
+        "config": {"workload": f"BOUNDED SAMPLE of BASELINE configs[1]: random sparse {n}x{n}, {NNZ_ROW} nnz/row, echelonize+rank mod {PRIME} "
+                               f"(full workload: {FULL_N}x{FULL_N})", "sample_n": n, "rank": r},
+        "cpu_baseline": {"value": val, "unit": "s", "cores": cores, "kind": "port", "sample_n": n, "sample_rank": r,
+                         "sample": f"oracle restatement of libspasm (blocked dense tail, OpenMP, {cores} threads), {n}x{n} instance of the same generator",
+                         "gpu_same_sample_s": g_res, "gpu_same_sample_e2e_s": g_e2e,
+                         "speedup_same_sample_e2e": (val / g_e2e) if g_e2e else None},
+        "e2e": {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -191,6 +253,12 @@ def run_ours(args):
     lib.spasm_b200_release.argtypes = [C.c_void_p]
     lib.spasm_b200_last_timings.argtypes = [C.POINTER(C.c_double)]
     lib.spasm_b200_mma_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
+    lib.spasm_b200_mma_timing.argtypes = [C.c_int]
+    lib.spasm_b200_set_cache.argtypes = [C.c_int]
+    lib.spasm_b200_utcimma_peak.restype = C.c_double
+    lib.spasm_b200_utcimma_peak.argtypes = [C.c_int, C.c_int]
+    lib.spasm_b200_mma_timing(1)  # CUDA events around every tcgen05 launch (read once, after the timed region)
+    lib.spasm_b200_set_cache(1)   # same-shaped calls in a loop: keep the device blocks between calls (opt-in; default is to return them)
     if world > 1:
         dist_init(lib, dist, rank, world)
 
@@ -250,7 +318,7 @@ def run_ours(args):
         assert rank_found == KNOWN_RANK_FULL, f"rank {rank_found} != {KNOWN_RANK_FULL}"
 
     # ---- end to end through the C ABI on host structs (upload + download of the factor inside)
-    e2e_steps = max(1, min(K, args.e2e_steps))
+    e2e_steps = max(1, args.e2e_steps)
     lu = gpu.echelonize(A)  # warm-up (page cache of the host allocator, pinned bounce buffers)
     u_nnz = lu.U.nnz()
     assert lu.r == rank_found
@@ -282,20 +350,23 @@ def run_ours(args):
     # dominant kernel of this workload: k_gemm_i8limb (tcgen05.mma.kind::i8 -> SASS UTCIMMA), timed with
     # CUDA events on the launching stream inside the library.  4 int8 MACs per modular MAC, 2 ops per MAC.
     achieved = (8.0 * mma_macs / (mma_ms * 1e-3) / 1e12) if mma_ms > 0 else None
-    peak = 2.0 * bf16_sust  # dense int8 = 2x bf16 on sm_100; no measured int8 figure on this pool
+    # denominator: back-to-back tcgen05.mma.kind::i8 M128 N256 K32 from shared memory on all SMs, measured on THIS box now
+    # (SURVEY.md 8d "builder must measure"); MEASURED_PEAKS.json has no int8 figure
+    peak = lib.spasm_b200_utcimma_peak(4096, 5)
+    peak_source = "measured in this run: back-to-back UTCIMMA M128xN256xK32, operands in shared memory, 148 CTAs (spasm_b200_utcimma_peak)"
+    if not peak or peak <= 0:
+        peak, peak_source = 2.0 * bf16_sust, f"fallback: 2 x bf16_tflops_sustained of {src}"
     roofline = {
         "kernel": "k_gemm_i8limb (tcgen05.mma.kind::i8, SASS UTCIMMA; TMA-fed, TMEM accumulators)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if achieved else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
-        # profiles/r01_ncu_gemm_i8limb_k4096_grouped_tiles.csv (M=32768 N=16384 K=4096, the depth of the deferred
-        # trailing updates; the bench's launches have other M and N, see traffic_note).  Algorithmic bytes of that
-        # launch: 4.29e9 (C read + write) + 4.0e8 (u8 limb planes of A and B read once)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture (profiles/), see traffic_note
         "traffic": 5.429282e9 + 2.143989e9,
-        "traffic_note": "ncu capture of the kernel alone at M=32768 N=16384 K=4096: 7.57e9 B of DRAM traffic vs 4.70e9 B algorithmic (x1.6; "
-                        "it was 24.5e9 B before the tiles were walked in column groups); not re-measured per bench launch",
-        "peak_source": f"2 x bf16_tflops_sustained of {src} (int8 dense = 2x bf16 nominal; proxy, no int8 figure is measured)",
-        "algorithmic": "8 int8 ops per modular multiply-add (4 limb MMAs x 2), M*N*K per launch (unpadded)",
+        "traffic_note": "ncu capture of the kernel alone at M=32768 N=16384 K=4096: 7.57e9 B of DRAM traffic vs 4.70e9 B algorithmic (x1.6); "
+                        "the bench's launches have other M and N",
+        "peak_source": peak_source,
+        "proxy_2x_bf16_sustained": 2.0 * bf16_sust,
+        "algorithmic": "8 int8 ops per modular multiply-add (4 limb MMAs x 2), M*N*K per launch (unpadded, live columns only)",
         "kernel_ms_per_step": mma_ms / K, "launches_per_step": mma_calls / K,
         "share_of_step": (mma_ms / K / 1e3) / my if my > 0 else None,
     }
@@ -349,10 +420,12 @@ def run_ours(args):
             "phases_s": {k: round(v, 5) for k, v in ph.items() if v}}
         del fs, As
 
-    # ---- CPU baseline: the oracle on a bounded sample, rank 0 only
+    # ---- CPU baseline: the oracle on a bounded sample, rank 0 only, with the SAME sample through the CUDA library
     cpu = None
     if not args.no_cpu and world == 1:
         ora = pkg.SpaSM(entry.build_oracle())
+        ora.log(False)
+        ora.lib.spasm_oracle_set_num_threads(0)
         ns = CPU_SAMPLE_N if n >= CPU_SAMPLE_N else n
         ps, js, xs = make_input(ns)
         As = ora.from_arrays(ns, ns, ps, js, xs, PRIME)
@@ -360,16 +433,11 @@ def run_ours(args):
         fo = ora.echelonize(As)
         tc = time.perf_counter() - t
         cores = int(ora.lib.spasm_get_num_threads())
-        # the same sample through the GPU library, for a like-for-like ratio
-        Ag = gpu.from_arrays(ns, ns, ps, js, xs, PRIME)
-        gpu.echelonize(Ag)
-        t = time.perf_counter()
-        fg = gpu.echelonize(Ag)
-        tg = time.perf_counter() - t
-        assert fg.r == fo.r
-        cpu = {"value": tc, "unit": "s", "cores": cores, "kind": "port",
-               "sample": f"oracle restatement of libspasm (oracle/), {cores} cores, {ns}x{ns} instance of the same generator; "
-                         f"the CUDA library takes {tg:.3f} s end to end on that sample"}
+        g_res, g_e2e = gpu_same_sample(pkg, entry, ns, ps, js, xs, fo.r)
+        cpu = {"value": tc, "unit": "s", "cores": cores, "kind": "port", "sample_n": ns, "sample_rank": fo.r,
+               "sample": f"oracle restatement of libspasm (oracle/: blocked dense tail, OpenMP, {cores} threads), {ns}x{ns} instance of the same generator",
+               "gpu_same_sample_s": g_res, "gpu_same_sample_e2e_s": g_e2e,
+               "speedup_same_sample_e2e": (tc / g_e2e) if g_e2e else None}
 
     clocks = clk.summary()
     if achieved and clocks.get("sm_max_mhz"):
@@ -377,6 +445,7 @@ def run_ours(args):
         hw = 16384.0 * SM_COUNT * clocks["sm_max_mhz"] * 1e6 / 1e12
         roofline["hw_int8_peak_tops_at_max_clock"] = hw
         roofline["frac_of_hw_int8_peak"] = achieved / hw
+    lib.spasm_b200_set_cache(0)
     line = {
         "metric": "echelonize_time_to_rank", "value": my, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * my, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -407,7 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=None, help="debug: override the matrix size (the bench value is only valid at the default)")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs[3] dense tail / sparse Schur side figures")
     args = ap.parse_args()

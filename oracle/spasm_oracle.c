@@ -130,6 +130,16 @@ int spasm_get_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1: bench.py --impl reference asks for every host core explicitly */
+void spasm_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_num_procs();
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int spasm_get_thread_num(void) {
 #ifdef _OPENMP
   return omp_get_thread_num();
@@ -916,18 +926,44 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
   i64 *loff = spasm_malloc((i64)(n + 1) * sizeof(i64));
   int *owner = spasm_malloc((i64)(n + 1) * sizeof(int));
   i64 bytes = 0, macs = 0;
-#pragma omp parallel reduction(+ : bytes, macs)
+  /* SPASM_ORACLE_STATS=1: shape of the elimination DAG as the rows see it (design input for the GPU engine) */
+  const int want_stats = getenv("SPASM_ORACLE_STATS") != NULL;
+  int *level = NULL;
+  i64 st_reach = 0, st_levels = 0, st_touched = 0, st_maxtouched = 0, st_maxreach = 0;
+  if (want_stats) {
+    level = spasm_calloc(U->n + 1, sizeof(int));
+    for (int i = 0; i < U->n; i++)
+      for (i64 px = Up[i] + 1; px < Up[i + 1]; px++) {
+        int i2 = qinv[U->j[px]];
+        if (i2 >= 0 && level[i2] < level[i] + 1) level[i2] = level[i] + 1;
+      }
+  }
+#pragma omp parallel reduction(+ : bytes, macs, st_reach, st_levels, st_touched) reduction(max : st_maxtouched, st_maxreach)
   {
     int tid = spasm_get_thread_num();
     spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
     int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
     int *cols = spasm_malloc((i64)m * sizeof(int));
+    int *levseen = want_stats ? spasm_calloc(U->n + 2, sizeof(int)) : NULL;
 #pragma omp for schedule(dynamic, 64)
     for (int k = 0; k < n; k++) {
       int i = p[k];
       int top = spasm_sparse_triangular_solve(U, A, i, xj, x, qinv);
       int nc = 0, nl = 0;
       bytes += 8 * (A->p[i + 1] - A->p[i]) + 8;
+      if (want_stats) {
+        i64 reach = 0, nlev = 0;
+        for (int px = top; px < m; px++) {
+          int j = xj[px];
+          if (qinv[j] >= 0 && x[j] != 0) {
+            reach++;
+            if (levseen[level[qinv[j]]] != k + 1) levseen[level[qinv[j]]] = k + 1, nlev++;
+          }
+        }
+        st_reach += reach, st_levels += nlev, st_touched += m - top;
+        if (m - top > st_maxtouched) st_maxtouched = m - top;
+        if (reach > st_maxreach) st_maxreach = reach;
+      }
       for (int px = top; px < m; px++) {
         int j = xj[px];
         if (x[j] == 0) continue;
@@ -963,6 +999,17 @@ struct spasm_csr *spasm_schur(const struct spasm_csr *A, const int *p, int n, co
     free(x);
     free(xj);
     free(cols);
+    free(levseen);
+  }
+  if (want_stats && n > 0) {
+    int maxlev = 0;
+    for (int i = 0; i < U->n; i++)
+      if (level[i] > maxlev) maxlev = level[i];
+    fprintf(stderr, "[oracle/schur stats] rows %d, U rows %d (%d levels, avg len %.1f); per row: reached pivots avg %.1f max %" PRId64
+            ", distinct levels avg %.1f, touched columns avg %.1f max %" PRId64 "\n",
+            n, U->n, maxlev + 1, (double)Up[U->n] / (U->n > 0 ? U->n : 1), (double)st_reach / n, st_maxreach, (double)st_levels / n,
+            (double)st_touched / n, st_maxtouched);
+    free(level);
   }
   i64 snz = 0;
   for (int k = 0; k < n; k++) snz += cnt[k];

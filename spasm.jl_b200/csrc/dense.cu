@@ -719,6 +719,12 @@ __global__ void k_gather_pivot_cols_T(const uint32_t *__restrict__ Dt, long long
     if (k < nk && s < rr) Pt[(long long)k * ldp + s] = tile[threadIdx.x][y];
   }
 }
+// Dt[pivcol[s]][kbase + k] = 0: the columns pivoted by this panel are dead on every remaining row (the trailing
+// products skip them), and later panels read R = T . Dt over all columns
+__global__ void k_zero_pivot_cols(uint32_t *__restrict__ Dt, long long ld, const int *__restrict__ pivcol, int rr, long long kbase, int nk) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (k < nk && s < rr) Dt[(long long)pivcol[s] * ld + kbase + k] = 0u;
+}
 // out[s][u] = in[idx[s]][u], u < cols
 __global__ void k_gather_rows_ld(const uint32_t *__restrict__ in, long long ldi, const int *__restrict__ idx, int rows, int cols,
                                  uint32_t *__restrict__ out, long long ldo) {
@@ -1036,6 +1042,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         Pt.alloc((size_t)nk * ldk);
         k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
         k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt.p, ldk);
+        k_zero_pivot_cols<<<dim3(cdiv(nk, 256), rr), 256, 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk);
         tick(3, t1);
         if (nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F, cand.p);
         tick(4, t1);
@@ -1046,6 +1053,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt_b, LDK);
         if (rr16 > rr) CK(cudaMemset2DAsync(Rt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, Sm0, s));  // zero pad columns: the pad of Pt may hold anything
         k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt_b, LDK);
+        k_zero_pivot_cols<<<dim3(cdiv(nk, 256), rr), 256, 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk);
         if (rr16 > rr) CK(cudaMemset2DAsync(Pt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, nk, s));  // and the pad of Pt: no garbage x 0
         if (Kacc > 0 && fe < n_local) {
           // the far rows of these pivot columns still miss the pending updates

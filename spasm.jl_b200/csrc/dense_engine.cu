@@ -19,39 +19,9 @@ __global__ void k_pivcol_of_rows(const long long *__restrict__ Up, const int *__
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < r) pivcol[i] = Uj[Up[i]];
 }
-static constexpr int RELAX_SWEEPS = 8;
-// level[i] = 1 + max level of the rows i' != i that hold column pc_i (they must be final first)
-__global__ void k_level_relax(const long long *__restrict__ Tp, const int *__restrict__ Tj, const int *__restrict__ pivcol, int r,
-                              int *__restrict__ level, int *__restrict__ changed) {
-  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= r) return;
-  const int c = pivcol[i];
-  // several sweeps per launch: the iteration is monotone (levels only grow towards the longest-path
-  // fixpoint), so re-evaluating against whatever the neighbours hold right now is safe, and a launch
-  // in which nobody changed anything proves the fixpoint.  Cuts the number of launches of this
-  // latency-bound loop (thousands of levels) by the sweep count.
-  for (int sweep = 0; sweep < RELAX_SWEEPS; sweep++) {
-    int h = 0;
-    for (long long e = Tp[c] + lane; e < Tp[c + 1]; e += 32) {
-      int i2 = Tj[e];
-      if (i2 != i) h = max(h, ((volatile int *)level)[i2] + 1);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
-    if (lane == 0 && h > ((volatile int *)level)[i]) {
-      ((volatile int *)level)[i] = h;
-      *changed = 1;
-    }
-    __syncwarp();
-  }
-}
 __global__ void k_iota_int(int *a, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = i;
-}
-__global__ void k_hist(const int *__restrict__ level, int r, int *__restrict__ hist) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < r) atomicAdd(&hist[level[i]], 1);
 }
 __global__ void k_scatter_rows_T(const long long *__restrict__ Ap, const int *__restrict__ Aj, const uint32_t *__restrict__ Ax,
                                  const int *__restrict__ rows, int k0, int kc, const int *__restrict__ qinv,
@@ -108,6 +78,84 @@ __global__ void __launch_bounds__(256) k_sptrsm(const long long *__restrict__ Tp
   }
 }
 
+// ---- pivot part without any level schedule.  Right-hand sides are independent, and U row i only holds pivot
+// columns of LATER rows, so the multiplier of pivot i depends on rows i' < i only: a thread that walks the pivots in
+// row order i = 0, 1, ... for ITS right-hand side reads values it wrote itself — no barrier of any kind.  One warp
+// owns 32 consecutive right-hand sides (coalesced 128-byte accesses of Vp[i][kk..kk+31]) and streams the
+// "program" (for each pivot i: the pairs (i', -U[i'][pc_i])), prefetched 32 entries per coalesced load.
+// This replaces the level-scheduled loop (thousands of launches on deep pivot DAGs).
+__global__ void k_prog_count(const long long *__restrict__ Tp, const int *__restrict__ pivcol, int r, int *__restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < r) {
+    const int c = pivcol[i];
+    cnt[i] = (int)(Tp[c + 1] - Tp[c]) - 1;  // every entry of column pc_i except the unit pivot of row i itself
+  }
+  if (i == r) cnt[i] = 0;
+}
+__global__ void k_prog_fill(const long long *__restrict__ Tp, const int *__restrict__ Tj, const uint32_t *__restrict__ Tx,
+                            const int *__restrict__ pivcol, int r, const long long *__restrict__ Pp, int2 *__restrict__ prog, Fp F) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= r) return;
+  const int c = pivcol[i];
+  const long long a = Tp[c], b = Tp[c + 1];
+  long long w = Pp[i];
+  for (long long e0 = a; e0 < b; e0 += 32) {
+    const long long e = e0 + lane;
+    const bool ok = e < b && Tj[e] != i;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (ok) prog[w + __popc(bal & ((1u << lane) - 1u))] = make_int2(Tj[e], (int)negmod(Tx[e], F));
+    w += __popc(bal);
+  }
+}
+template <bool SMALL>
+__global__ void __launch_bounds__(128) k_sptrsm_seq(const long long *__restrict__ Pp, const int2 *__restrict__ prog, int r,
+                                                    uint32_t *__restrict__ Vp, long long ldv, int kc, Fp F) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int kk = wid * 32 + lane;
+  if (wid * 32 >= kc) return;
+  const bool live = kk < kc;
+  const int kq = live ? kk : 0;
+  for (int i0 = 0; i0 < r; i0 += 32) {
+    const int nb = min(32, r - i0);
+    const long long myP0 = (lane < nb) ? Pp[i0 + lane] : 0, myP1 = (lane < nb) ? Pp[i0 + lane + 1] : 0;
+    // first chunk of the first pivot of this group
+    long long a = __shfl_sync(FULL, myP0, 0), b = __shfl_sync(FULL, myP1, 0);
+    int2 ent = (a + lane < b) ? __ldg(&prog[a + lane]) : make_int2(0, 0);
+    for (int t = 0; t < nb; t++) {
+      const int i = i0 + t;
+      // prefetch the first chunk of the next pivot while this one is computed
+      long long na = 0, nbb = 0;
+      int2 nent = make_int2(0, 0);
+      if (t + 1 < nb) {
+        na = __shfl_sync(FULL, myP0, t + 1), nbb = __shfl_sync(FULL, myP1, t + 1);
+        if (na + lane < nbb) nent = __ldg(&prog[na + lane]);
+      }
+      if (b > a) {
+        uint32_t *out = Vp + (long long)i * ldv + kq;
+        unsigned long long acc = *out;
+        uint32_t accm = (uint32_t)acc;
+        for (long long e0 = a; e0 < b; e0 += 32) {
+          if (e0 > a) ent = (e0 + lane < b) ? __ldg(&prog[e0 + lane]) : make_int2(0, 0);
+          const int cnt = (int)min((long long)32, b - e0);
+          for (int u = 0; u < cnt; u++) {
+            const int i2 = __shfl_sync(FULL, ent.x, u);
+            const uint32_t cf = (uint32_t)__shfl_sync(FULL, ent.y, u);
+            const uint32_t y = Vp[(long long)i2 * ldv + kq];
+            if (SMALL)
+              acc += (unsigned long long)(cf * y);
+            else
+              accm = addmod(accm, mulmod<false>(cf, y, F), F);
+          }
+        }
+        if (live) *out = SMALL ? red64(acc, F) : accm;
+      }
+      a = na, b = nbb, ent = nent;
+    }
+  }
+}
+
 void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U, const int *Uqinv, const Fp &F, DenseSchur &D) {
   build_dense_schur_raw(A.p.p, A.j.p, A.x.p, A.m, rows, nrows, U, Uqinv, F, D, false);
 }
@@ -133,37 +181,18 @@ void build_dense_schur_raw(const long long *Ap, const int *Aj, const uint32_t *A
   // transpose of U and the level schedule
   DCsr Ut;
   transpose_csr(U, Ut);
-  DBuf<int> pivcol(std::max(r, 1)), level(std::max(r, 1)), order(std::max(r, 1)), order2(std::max(r, 1)), lev2(std::max(r, 1)), chg(1);
-  int maxlev = 0;
-  std::vector<int> hist_h(1, 0);
+  DBuf<int> pivcol(std::max(r, 1)), pcnt(std::max(r, 1) + 1);
+  DBuf<long long> Pp(std::max(r, 1) + 1);
+  DBuf<int2> prog;
   if (r > 0) {
+    // the elimination program of the pivot part, in U row order (a topological order of the pivot DAG)
     k_pivcol_of_rows<<<cdiv(r, 256), 256, 0, s>>>(U.p.p, U.j.p, r, pivcol.p);
-    level.zero();
-    for (int it = 0;; it += 4) {
-      chg.zero();
-      for (int rep = 0; rep < 4; rep++) k_level_relax<<<cdiv((long long)r * 32, 256), 256, 0, s>>>(Ut.p.p, Ut.j.p, pivcol.p, r, level.p, chg.p);
-      if (fetch(chg.p) == 0) break;
-      if (it > r + 8) throw Error("dense engine: U is not triangular");
-    }
-    DBuf<int> mx(1);
-    size_t tmp = 0;
-    cub::DeviceReduce::Max(nullptr, tmp, level.p, mx.p, r, s);
-    DBuf<char> t1(tmp);
-    cub::DeviceReduce::Max(t1.p, tmp, level.p, mx.p, r, s);
-    maxlev = fetch(mx.p);
-    k_iota_int<<<cdiv(r, 256), 256, 0, s>>>(order.p, r);
-    int bits = 1;
-    while ((1LL << bits) <= maxlev) bits++;
-    tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, level.p, lev2.p, order.p, order2.p, r, 0, bits, s);
-    DBuf<char> t2(tmp);
-    cub::DeviceRadixSort::SortPairs(t2.p, tmp, level.p, lev2.p, order.p, order2.p, r, 0, bits, s);
-    DBuf<int> hist(maxlev + 1);
-    hist.zero();
-    k_hist<<<cdiv(r, 256), 256, 0, s>>>(level.p, r, hist.p);
-    hist_h.resize(maxlev + 1);
-    hist.download(hist_h.data(), maxlev + 1);
-    sync();
+    k_prog_count<<<cdiv(r + 1, 256), 256, 0, s>>>(Ut.p.p, pivcol.p, r, pcnt.p);
+    exclusive_scan_i32_to_i64(pcnt.p, Pp.p, r + 1);
+    const long long plen = fetch(Pp.p + r);
+    prog.alloc(std::max<long long>(plen, 1));
+    k_prog_fill<<<cdiv((long long)r * 32, 256), 256, 0, s>>>(Ut.p.p, Ut.j.p, Ut.x.p, pivcol.p, r, Pp.p, prog.p, F);
+    g_launches += 4;
   }
   // chunk the right-hand sides so that the pivot part fits comfortably
   size_t avail = dev_free_bytes();
@@ -183,16 +212,12 @@ void build_dense_schur_raw(const long long *Ap, const int *Aj, const uint32_t *A
     if (r > 0) CK(cudaMemsetAsync(Vp.p, 0, (size_t)r * kc_max * 4, s));
     k_scatter_rows_T<<<cdiv((long long)kc * 32, 256), 256, 0, s>>>(Ap, Aj, Ax, rows, (int)k0, kc, Uqinv, qpos.p, Vp.p, kc_max, D.Dt.p, D.ld);
     const int ktiles = cdiv(kc, 256);
-    int off = r > 0 ? hist_h[0] : 0;
-    for (int L = 1; L <= maxlev; L++) {
-      const int cnt = hist_h[L];
-      if (cnt == 0) continue;
-      dim3 grid(cnt, ktiles);
+    if (r > 0) {
+      const int warps = cdiv(kc, 32);
       if (F.small)
-        k_sptrsm<true, true><<<grid, 256, 0, s>>>(Ut.p.p, Ut.j.p, Ut.x.p, order2.p + off, pivcol.p, Vp.p, kc_max, D.Dt.p, D.ld, (int)k0, kc, F);
+        k_sptrsm_seq<true><<<cdiv(warps, 4), 128, 0, s>>>(Pp.p, prog.p, r, Vp.p, kc_max, kc, F);
       else
-        k_sptrsm<false, true><<<grid, 256, 0, s>>>(Ut.p.p, Ut.j.p, Ut.x.p, order2.p + off, pivcol.p, Vp.p, kc_max, D.Dt.p, D.ld, (int)k0, kc, F);
-      off += cnt;
+        k_sptrsm_seq<false><<<cdiv(warps, 4), 128, 0, s>>>(Pp.p, prog.p, r, Vp.p, kc_max, kc, F);
       g_launches += 1;
     }
     if (r > 0) {
@@ -204,7 +229,7 @@ void build_dense_schur_raw(const long long *Ap, const int *Aj, const uint32_t *A
     }
     CK(cudaGetLastError());
   }
-  D.levels = maxlev + 1;
+  D.levels = 0;  // no level schedule any more (k_sptrsm_seq)
   if (keep_pivot_part) {
     D.ldv = kc_max;
     D.Vp = std::move(Vp);

@@ -121,31 +121,88 @@ static void add_L_entries(Echelon &E, const SolveResult &R, const std::vector<in
 }
 
 // ------------------------------------------------------------------ GPLU tail
-// Row-by-row semantics (README.md:34-36) reproduced by speculative batches: a batch of rows is
-// reduced against the current U in parallel; one warp then walks the batch in order and accepts
-// rows until it meets one that holds a column pivoted earlier in the same batch (that row needs
-// the new pivot row, so it and everything after it is re-solved in the next batch).
+// Row-by-row semantics (README.md:34-36) reproduced by speculative batches: a batch of rows is reduced against
+// the current U in parallel; one warp then walks the batch IN ORDER and decides every row:
+//   * a row that reduced to zero is final whatever happens before it (it stays zero against any larger U);
+//   * a non-zero row is accepted as the next pivot row unless it holds a column pivoted earlier in this batch;
+//   * from the first such conflict on, every non-zero row is DEFERRED: it is solved again in the next batch, in
+//     the same relative order, against the enlarged U (its value, or the order in which pivots enter U, could
+//     depend on the rows deferred before it).
+// On rank-deficient tails (most rows vanish) almost nothing is deferred and the batches stay large.
+// decision[t]: 0 zero row, 1 + k pivot number k of this batch, -1 deferred.
 __global__ void k_gplu_commit(const long long *__restrict__ Rp, const int *__restrict__ Rj, int wn, unsigned char *__restrict__ newpiv,
-                              int urows, int m, int *__restrict__ out /* [0]=ncommit [1]=npivots */, int *__restrict__ pivt) {
+                              int urows, int m, int *__restrict__ out /* [0]=ndeferred [1]=npivots */, int *__restrict__ pivt,
+                              int *__restrict__ decision) {
+  constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x;
-  int np = 0, t = 0;
-  for (; t < wn; t++) {
-    if (urows + np == m) break;  // every column is pivotal: the remaining rows reduce to zero
-    const long long a = Rp[t], b = Rp[t + 1];
-    int conflict = 0;
-    for (long long e = a + lane; e < b; e += 32) conflict |= newpiv[Rj[e]];
-    if (__any_sync(0xffffffffu, conflict)) break;
-    if (b > a) {
-      if (lane == 0) {
-        newpiv[Rj[a]] = 1;  // entries are sorted: the first one is the leftmost column
-        pivt[np] = t;
+  int np = 0, nd = 0;
+  bool dirty = false;
+  for (int t0 = 0; t0 < wn; t0 += 32) {
+    const int tt = t0 + lane;
+    const long long ra = tt < wn ? Rp[tt] : 0, rb = tt < wn ? Rp[tt + 1] : 0;
+    const bool nonzero = tt < wn && rb > ra;
+    if (tt < wn && !nonzero) decision[tt] = 0;
+    unsigned todo = __ballot_sync(FULL, nonzero);
+    while (todo) {
+      const int u = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int t = t0 + u;
+      const long long a = __shfl_sync(FULL, ra, u), b = __shfl_sync(FULL, rb, u);
+      bool defer = dirty;
+      if (!defer && urows + np == m) {
+        // every column is pivotal: this row cannot be non-zero against the final U; solve it again (it will vanish)
+        defer = true;
       }
-      np++;
-      __syncwarp();
+      if (!defer) {
+        int conflict = 0;
+        for (long long e = a + lane; e < b; e += 32) conflict |= newpiv[Rj[e]];
+        if (__any_sync(FULL, conflict)) defer = true, dirty = true;
+      }
+      if (defer) {
+        if (lane == 0) decision[t] = -1;
+        nd++;
+      } else {
+        if (lane == 0) {
+          newpiv[Rj[a]] = 1;  // entries are sorted: the first one is the leftmost column
+          pivt[np] = t;
+          decision[t] = 1 + np;
+        }
+        np++;
+        __syncwarp();
+      }
     }
   }
-  if (urows + np == m) t = wn;
-  if (lane == 0) out[0] = t, out[1] = np;
+  if (lane == 0) out[0] = nd, out[1] = np;
+}
+// carry = the deferred rows of a batch in their REDUCED form (already eliminated against the U of that batch): the
+// next batch only has to eliminate them against the pivots that entered U since, instead of solving them again
+__global__ void k_carry_lens(const long long *__restrict__ Rp, const int *__restrict__ decision, int wn, int *__restrict__ flag,
+                             int *__restrict__ len) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < wn) {
+    const bool d = decision[t] == -1;
+    flag[t] = d;
+    len[t] = d ? (int)(Rp[t + 1] - Rp[t]) : 0;
+  }
+  if (t == wn) flag[t] = 0, len[t] = 0;
+}
+__global__ void k_carry_gather(const long long *__restrict__ Rp, const int *__restrict__ Rj, const uint32_t *__restrict__ Rx,
+                               const int *__restrict__ decision, int wn, const long long *__restrict__ rowpos,
+                               const long long *__restrict__ entpos, long long *__restrict__ Cp, int *__restrict__ Cj, uint32_t *__restrict__ Cx) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t > wn) return;
+  if (t == wn) {
+    if (lane == 0) Cp[rowpos[wn]] = entpos[wn];
+    return;
+  }
+  if (decision[t] != -1) return;
+  const long long a = Rp[t], b = Rp[t + 1], d = entpos[t];
+  if (lane == 0) Cp[rowpos[t]] = d;
+  for (long long e = a + lane; e < b; e += 32) Cj[d + (e - a)] = Rj[e], Cx[d + (e - a)] = Rx[e];
+}
+__global__ void k_shift_ptr(const long long *__restrict__ in, int n_plus_one, long long shift, long long *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_plus_one) out[i] = in[i] + shift;
 }
 __global__ void k_gplu_lens(const long long *__restrict__ Rp, const int *__restrict__ pivt, int np, int *__restrict__ len) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,71 +241,157 @@ static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, in
   logf("[echelonize/GPLU] processing matrix of dimension %d x %d\n", nrows, m);
   DBuf<unsigned char> newpiv(m);
   newpiv.zero();
-  DBuf<int> out(2), pivt, len;
-  DBuf<long long> pos;
+  DBuf<int> out(2), pivt, len, decision, cflag, clen;
+  DBuf<long long> pos, crow, cent;
   DBuf<PDesc> pdesc;
   DBuf<uint32_t> pivval;
+  DCsr carry;  // deferred rows, reduced against the U of the batch that deferred them
+  carry.n = 0, carry.m = m, carry.nnz = 0;
+  std::vector<int> carry_orig, hdec;
   int batch = 256;
-  for (int done = 0; done < nrows;) {
+  const bool prof = getenv("SPASM_B200_PROFILE") != nullptr;
+  int nbatches = 0;
+  long long solved = 0, npivots = 0;
+  double t_solve = 0;
+  struct ProfGuard {
+    const bool on;
+    int &nb;
+    long long &solved, &np;
+    double &ts;
+    int nrows;
+    ~ProfGuard() {
+      if (on) fprintf(stderr, "[GPLU] %d rows: %d batches, %lld row solves, %lld pivots, %.3fs in solve_rows\n", nrows, nb, solved, np, ts);
+    }
+  } prof_guard{prof, nbatches, solved, npivots, t_solve, nrows};
+  for (int done = 0; done < nrows || carry.n > 0;) {
     if (E.U.n == m) {
       logf("\n[echelonize/GPLU] full rank reached\n");
       break;
     }
-    const int wn = std::min(batch, nrows - done);
+    const int nc = carry.n;
+    const int wf = std::max(0, std::min(batch - nc, nrows - done));  // fresh rows of this batch
+    const int wn = nc + wf;
     build_pdesc_U(E.U, E.Uqinv.p, pdesc);
     SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m, &E.U, E.Uqinv.p};
-    SolveRows B{cur.p.p, cur.j.p, cur.x.p, rows_dev + done, wn, nullptr};
     SolveEmit Em;
     Em.want_L = (E.L != nullptr);
-    SolveResult R;
-    solve_rows(G, B, Em, E.F, R);
+    SolveResult R1, R2;
+    const double ts0 = spasm_wtime();
+    if (nc > 0) {
+      SolveRows B1{carry.p.p, carry.j.p, carry.x.p, nullptr, nc, nullptr};
+      solve_rows(G, B1, Em, E.F, R1);
+    }
+    if (wf > 0) {
+      SolveRows B2{cur.p.p, cur.j.p, cur.x.p, rows_dev + done, wf, nullptr};
+      solve_rows(G, B2, Em, E.F, R2);
+    }
+    t_solve += spasm_wtime() - ts0, nbatches++, solved += wn;
+    // one result list: the carried rows first (they come first in row order), then the fresh ones
+    SolveResult Rc;
+    SolveResult *R = nullptr;
+    if (nc > 0 && wf > 0) {
+      Rc.nnz = R1.nnz + R2.nnz;
+      Rc.p.alloc(wn + 1);
+      Rc.j.alloc(std::max<long long>(Rc.nnz, 1));
+      Rc.x.alloc(std::max<long long>(Rc.nnz, 1));
+      CK(cudaMemcpyAsync(Rc.p.p, R1.p.p, (size_t)nc * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+      k_shift_ptr<<<cdiv(wf + 1, 256), 256, 0, s>>>(R2.p.p, wf + 1, R1.nnz, Rc.p.p + nc);
+      if (R1.nnz) {
+        CK(cudaMemcpyAsync(Rc.j.p, R1.j.p, (size_t)R1.nnz * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(Rc.x.p, R1.x.p, (size_t)R1.nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      }
+      if (R2.nnz) {
+        CK(cudaMemcpyAsync(Rc.j.p + R1.nnz, R2.j.p, (size_t)R2.nnz * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(Rc.x.p + R1.nnz, R2.x.p, (size_t)R2.nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      }
+      R = &Rc;
+    } else
+      R = nc > 0 ? &R1 : &R2;
     pivt.alloc(wn);
-    k_gplu_commit<<<1, 32, 0, s>>>(R.p.p, R.j.p, wn, newpiv.p, E.U.n, m, out.p, pivt.p);
+    decision.alloc(wn);
+    k_gplu_commit<<<1, 32, 0, s>>>(R->p.p, R->j.p, wn, newpiv.p, E.U.n, m, out.p, pivt.p, decision.p);
     int h[2];
     out.download(h, 2);
     sync();
-    const int ncommit = h[0], np = h[1];
+    const int nd = h[0], np = h[1];
+    npivots += np;
+    if (prof && (nbatches <= 40 || nbatches % 50 == 0))
+      fprintf(stderr, "[GPLU] batch %d: %d carried + %d fresh rows, %d deferred, %d pivots; fresh: light %lld global %lld dense %lld, %.1f + %.1f ms\n",
+              nbatches, nc, wf, nd, np, R2.stats.light, R2.stats.medium, R2.stats.heavy, R1.stats.ms, R2.stats.ms);
     const int urow0 = E.U.n;
     if (np > 0) {
       len.alloc(np + 1);
       pos.alloc(np + 1);
       pivval.alloc(np);
-      k_gplu_lens<<<cdiv(np + 1, 256), 256, 0, s>>>(R.p.p, pivt.p, np, len.p);
+      k_gplu_lens<<<cdiv(np + 1, 256), 256, 0, s>>>(R->p.p, pivt.p, np, len.p);
       exclusive_scan_i32_to_i64(len.p, pos.p, np + 1);
       const long long add = fetch(pos.p + np);
       csr_reserve(E.U, E.U.nnz + add, E.U.n + np);
       if (E.F.small)
-        k_gplu_append<true><<<cdiv((long long)np * 32, 256), 256, 0, s>>>(R.p.p, R.j.p, R.x.p, pivt.p, np, pos.p, E.U.nnz, E.U.n, E.U.p.p,
+        k_gplu_append<true><<<cdiv((long long)np * 32, 256), 256, 0, s>>>(R->p.p, R->j.p, R->x.p, pivt.p, np, pos.p, E.U.nnz, E.U.n, E.U.p.p,
                                                                          E.U.j.p, E.U.x.p, E.Uqinv.p, newpiv.p, pivval.p, E.F);
       else
-        k_gplu_append<false><<<cdiv((long long)np * 32, 256), 256, 0, s>>>(R.p.p, R.j.p, R.x.p, pivt.p, np, pos.p, E.U.nnz, E.U.n, E.U.p.p,
+        k_gplu_append<false><<<cdiv((long long)np * 32, 256), 256, 0, s>>>(R->p.p, R->j.p, R->x.p, pivt.p, np, pos.p, E.U.nnz, E.U.n, E.U.p.p,
                                                                           E.U.j.p, E.U.x.p, E.Uqinv.p, newpiv.p, pivval.p, E.F);
       CK(cudaGetLastError());
       E.U.nnz += add;
       E.U.n += np;
     }
-    if (E.L != nullptr) {
-      // multipliers of the committed rows, then the pivot entries
-      std::vector<long long> lp(wn + 1);
-      std::vector<int> lj(R.lnnz), ht(std::max(np, 1));
-      std::vector<uint32_t> lx(R.lnnz), hv(std::max(np, 1));
-      R.lp.download(lp.data(), wn + 1);
-      if (R.lnnz) R.lj.download(lj.data(), R.lnnz), R.lx.download(lx.data(), R.lnnz);
-      if (np) pivt.download(ht.data(), np), pivval.download(hv.data(), np);
-      sync();
-      int kp = 0;
-      for (int t = 0; t < ncommit; t++) {
-        const int i_orig = orig_rows[done + t];
-        for (long long e = lp[t]; e < lp[t + 1]; e++) spasm_add_entry(E.L, i_orig, lj[e], (i64)lx[e]);
-        if (kp < np && ht[kp] == t) {
-          E.Lp[urow0 + kp] = i_orig;
-          spasm_add_entry(E.L, i_orig, urow0 + kp, (i64)hv[kp]);
-          kp++;
+    const bool need_dec = (E.L != nullptr);
+    if (need_dec) {
+      hdec.resize(wn);
+      decision.download(hdec.data(), wn);
+      // multipliers found in this batch (final for decided AND deferred rows: later pivots never touch them), then
+      // the pivot entries
+      std::vector<int> new_carry_orig;
+      std::vector<uint32_t> hv(std::max(np, 1));
+      if (np) pivval.download(hv.data(), np);
+      for (int part = 0; part < 2; part++) {
+        SolveResult &Rp_ = part == 0 ? R1 : R2;
+        const int cnt = part == 0 ? nc : wf, base = part == 0 ? 0 : nc;
+        if (cnt == 0) continue;
+        std::vector<long long> lp(cnt + 1);
+        std::vector<int> lj(Rp_.lnnz);
+        std::vector<uint32_t> lx(Rp_.lnnz);
+        Rp_.lp.download(lp.data(), cnt + 1);
+        if (Rp_.lnnz) Rp_.lj.download(lj.data(), Rp_.lnnz), Rp_.lx.download(lx.data(), Rp_.lnnz);
+        sync();
+        for (int t = 0; t < cnt; t++) {
+          const int i_orig = part == 0 ? carry_orig[t] : orig_rows[done + t];
+          for (long long e = lp[t]; e < lp[t + 1]; e++) spasm_add_entry(E.L, i_orig, lj[e], (i64)lx[e]);
+          const int d = hdec[base + t];
+          if (d > 0) {
+            E.Lp[urow0 + d - 1] = i_orig;
+            spasm_add_entry(E.L, i_orig, urow0 + d - 1, (i64)hv[d - 1]);
+          } else if (d < 0)
+            new_carry_orig.push_back(i_orig);
         }
       }
+      carry_orig.swap(new_carry_orig);
     }
-    done += ncommit;
-    batch = (ncommit == wn) ? std::min(batch * 2, 16384) : std::max(32, std::min(batch, 2 * ncommit + 32));
+    // the deferred rows, reduced, become the carry of the next batch
+    DCsr next;
+    next.n = nd, next.m = m, next.nnz = 0;
+    if (nd > 0) {
+      cflag.alloc(wn + 1);
+      clen.alloc(wn + 1);
+      crow.alloc(wn + 1);
+      cent.alloc(wn + 1);
+      k_carry_lens<<<cdiv(wn + 1, 256), 256, 0, s>>>(R->p.p, decision.p, wn, cflag.p, clen.p);
+      exclusive_scan_i32_to_i64(cflag.p, crow.p, wn + 1);
+      exclusive_scan_i32_to_i64(clen.p, cent.p, wn + 1);
+      next.nnz = fetch(cent.p + wn);
+      next.p.alloc(nd + 1);
+      next.j.alloc(std::max<long long>(next.nnz, 1));
+      next.x.alloc(std::max<long long>(next.nnz, 1));
+      k_carry_gather<<<cdiv((long long)(wn + 1) * 32, 256), 256, 0, s>>>(R->p.p, R->j.p, R->x.p, decision.p, wn, crow.p, cent.p, next.p.p, next.j.p,
+                                                                       next.x.p);
+      CK(cudaGetLastError());
+    }
+    sync();
+    carry = std::move(next);
+    done += wf;
+    batch = (2 * nd <= wn) ? std::min(batch * 2, 16384) : std::max(64, std::min(batch, 2 * (wn - nd) + 64));
   }
 }
 

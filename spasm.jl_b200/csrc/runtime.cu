@@ -94,17 +94,33 @@ void *dmalloc_bytes(size_t bytes) {
   }
   void *p = nullptr;
   cudaError_t e = cudaMallocAsync(&p, bytes, g_stream);
-  if (e != cudaSuccess && !g_big_free.empty()) {  // give the cached blocks back and retry
+  if (e != cudaSuccess) {  // give the cached blocks and the idle part of the pool back to the driver and retry
     cudaGetLastError();
     big_trim();
     cudaStreamSynchronize(g_stream);
+    cudaMemPool_t pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     e = cudaMallocAsync(&p, bytes, g_stream);
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
     size_t f = 0, t = 0;
     cudaMemGetInfo(&f, &t);
-    throw Error("spasm_b200: device allocation of " + std::to_string(bytes >> 20) + " MiB failed (" + std::to_string(f >> 20) + " MiB free): " +
+    uint64_t reserved = 0, used = 0;
+    cudaMemPool_t pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    size_t live = 0;
+    for (auto &b : g_big_live) live += b.bytes;
+    throw Error("spasm_b200: device allocation of " + std::to_string(bytes >> 20) + " MiB failed (" + std::to_string(f >> 20) + " MiB free of " +
+                std::to_string(t >> 20) + "; pool reserved " + std::to_string(reserved >> 20) + " / in use " + std::to_string(used >> 20) +
+                " MiB; large blocks in use " + std::to_string(live >> 20) + " MiB in " + std::to_string(g_big_live.size()) + "): " +
                 cudaGetErrorString(e));
   }
   if (bytes >= BIG) g_big_live.push_back({p, bytes});

@@ -27,6 +27,12 @@ namespace sb {
 static constexpr int EMPTY = -1;
 static constexpr int ST_OK = 0, ST_TABLE = 1, ST_SLAB = 2;
 
+struct __align__(16) PRow {
+  long long start;
+  int len;
+  int pad;
+};
+
 struct KArgs {
   SolveSystem G;
   SolveRows B;
@@ -57,6 +63,18 @@ struct KArgs {
   uint32_t *gvals;       // [groups][width]
   unsigned *gbitmap;     // [groups][nprio/32+1]
   int nprio;
+  // global tier (k_solve_global)
+  const int2 *G2;            // entries of G relabelled (slot id, value), same offsets as Gj / Gx
+  const int *col2sid;        // [width] column -> slot id: pivotal columns their prio, the others nprio + rank among the non-pivotal
+  const int *sid2col;        // [width]
+  const PRow *prow;          // [nprio] row of G that eliminates the pivot of that prio
+  const unsigned *classbit;  // optional [nwords]: bit set at the first prio of every class of mutually independent pivots
+  int nwords;                // words of the pending bitmap
+  int gw;                    // slots per row: nprio + number of non-pivotal columns
+  int pop_budget;            // > 0: a row that needs more elimination steps gives up (status ST_TABLE: next tier)
+  unsigned long long *gsum;  // [slots][width] unreduced sums; all zero between rows
+  int *gtouched;             // [slots][width] slot ids touched by the current row
+  unsigned *gpending;        // [slots][nwords] pending pivots of the current row; all zero between rows
 };
 
 template <int T>
@@ -580,6 +598,363 @@ __global__ void __launch_bounds__(T) k_solve_heavy(KArgs a, const int *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// GLOBAL tier: one warp per row, THOUSANDS of rows in flight.  Rows that do not fit the shared-memory table
+// (hundreds to tens of thousands of touched columns, hundreds of pivots reached) are latency-bound: every
+// elimination step is a chain of dependent L2 round trips, so throughput comes from concurrency, not from
+// a faster step.  The accumulator is therefore a direct-indexed array in global memory — no probing, no
+// capacity tiers — at 16 warps per SM (2368 rows in flight on a B200):
+//   * slot id: pivotal columns are addressed by their prio, the others by nprio + rank, so the multiplier of a
+//     pending pivot and the pending bitmap share one index and G is read as ONE 8-byte (slot, value) stream;
+//   * sum[slot] is an UNREDUCED 64-bit sum of residues, updated with atomicAdd (several rows of G are merged
+//     in the same warp step, so two lanes may hit one slot); every addend is a non-zero residue, hence
+//     "old == 0" detects the first touch exactly once: that lane logs the slot and sets its pending bit;
+//   * pending pivots live in a bitmap over prio, scanned 32 words per step from a monotone cursor; with
+//     `classbit` all pending pivots of one independence class inside a word are eliminated together
+//     (their rows are flattened over the 32 lanes); the sums are reduced mod p only when read;
+//   * emission walks the touched log (reduce, filter, write, zero the slot); rows come out unsorted and are
+//     sorted by k_sort_rows (normalisation N1).
+// Any valid topological order gives bit-identical values (exact arithmetic), so this tier, the shared-memory
+// tier and the oracle agree.  Zero multipliers are skipped (no structural mode here).
+template <bool SMALL>
+__global__ void __launch_bounds__(128) k_solve_global(KArgs a) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const size_t slot = (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  unsigned long long *__restrict__ sum = a.gsum + slot * (size_t)a.gw;
+  int *__restrict__ touched = a.gtouched + slot * (size_t)a.gw;
+  unsigned *__restrict__ pending = a.gpending + slot * (size_t)a.nwords;
+  const Fp F = a.F;
+  const int nprio = a.nprio;
+  const int2 *__restrict__ G2 = a.G2;
+
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(a.work_counter, 1);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= a.ntodo) break;
+    const int k = a.todo ? a.todo[t] : t;
+    const int brow = a.B.rows ? a.B.rows[k] : k;
+    const int masksid = a.B.mask ? a.col2sid[a.B.mask[k]] : -1;
+    int nt = 0, wmin = a.nwords;
+    unsigned long long bytes = 0, macs = 0;
+
+    // one warp step: `valid` lanes add delta to sum[sid]; first touches are logged and made pending
+    auto merge = [&](bool valid, int sid, uint32_t delta) {
+      bool first = false;
+      if (valid) first = atomicAdd(&sum[sid], (unsigned long long)delta) == 0ULL;
+      const unsigned fb = __ballot_sync(FULL, first);
+      int myw = 0x7fffffff;
+      if (first) {
+        touched[nt + __popc(fb & lt_mask)] = sid;
+        if (sid < nprio && sid != masksid) {
+          atomicOr(&pending[sid >> 5], 1u << (sid & 31));
+          myw = sid >> 5;
+        }
+      }
+      nt += __popc(fb);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) myw = min(myw, __shfl_xor_sync(FULL, myw, o));
+      wmin = min(wmin, myw);
+    };
+
+    // ---- B[k]
+    {
+      const long long b0 = a.B.Bp[brow], b1 = a.B.Bp[brow + 1];
+      bytes += 8 * (b1 - b0) + 8;
+      for (long long e0 = b0; e0 < b1; e0 += 32) {
+        const long long e = e0 + lane;
+        bool valid = e < b1;
+        int sid = 0;
+        uint32_t v = 0;
+        if (valid) {
+          v = a.B.Bx[e];
+          sid = a.col2sid[a.B.Bj[e]];
+          valid = v != 0;
+        }
+        merge(valid, sid, v);
+      }
+    }
+    __syncwarp();
+    // ---- eliminate the pending pivots by increasing prio, one class (inside one word) per step
+    int cw = wmin, steps = 0;
+    bool gave_up = false;
+    while (cw < a.nwords) {
+      if (a.pop_budget > 0 && ++steps > a.pop_budget) {
+        gave_up = true;
+        break;
+      }
+      const unsigned bw = (cw + lane < a.nwords) ? __ldcg(&pending[cw + lane]) : 0u;
+      const unsigned nz = __ballot_sync(FULL, bw != 0);
+      if (nz == 0) {
+        cw += 32;
+        continue;
+      }
+      const int f = __ffs(nz) - 1;
+      const unsigned w0 = __shfl_sync(FULL, bw, f);
+      const int wi = cw + f;
+      const int bit0 = __ffs(w0) - 1;
+      unsigned mw = 1u << bit0;
+      if (a.classbit != nullptr) {
+        const unsigned cb = __ldg(&a.classbit[wi]);
+        const unsigned above = (bit0 == 31) ? 0u : (cb & ~((2u << bit0) - 1u));  // class starts strictly after bit0
+        const int end = above ? (__ffs(above) - 1) : 32;
+        const unsigned upto = (end == 32) ? 0xffffffffu : ((1u << end) - 1u);
+        mw = w0 & upto & ~((1u << bit0) - 1u);
+      }
+      const int nm = __popc(mw);
+      if (lane == 0) atomicAnd(&pending[wi], ~mw);
+      int mprio = -1, mlen = 0;
+      long long mstart = 0;
+      uint32_t coef = 0;
+      if (lane < nm) {
+        mprio = wi * 32 + (int)__fns(mw, 0, lane + 1);
+        const uint32_t mult = red64(__ldcg(&sum[mprio]), F);
+        if (mult != 0) {
+          const PRow pr = a.prow[mprio];
+          mstart = pr.start, mlen = pr.len, coef = F.p - mult;
+        }
+      }
+      int incl = mlen;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int excl_mine = incl - mlen;
+      const int total = __shfl_sync(FULL, incl, 31);
+      const int nzm = __popc(__ballot_sync(FULL, mlen > 0));
+      macs += total, bytes += 8ULL * total + 8ULL * nzm;
+      for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        int lo = 0, hi = 31;  // smallest member whose inclusive prefix exceeds idx
+#pragma unroll
+        for (int s_ = 0; s_ < 5; s_++) {
+          const int mid = (lo + hi) >> 1;
+          const int v = __shfl_sync(FULL, incl, mid);
+          if (v > idx)
+            hi = mid;
+          else
+            lo = mid + 1;
+        }
+        const int ex = __shfl_sync(FULL, excl_mine, lo);
+        const long long st = __shfl_sync(FULL, mstart, lo);
+        const uint32_t cf = __shfl_sync(FULL, coef, lo);
+        const int mp = __shfl_sync(FULL, mprio, lo);
+        bool valid = idx < total;
+        int sid = 0;
+        uint32_t delta = 0;
+        if (valid) {
+          const int2 ent = __ldg(&G2[st + (idx - ex)]);
+          sid = ent.x;
+          if (sid == mp)
+            valid = false;  // the unit pivot entry: sum[prio] keeps the multiplier
+          else
+            delta = mulmod<SMALL>(cf, (uint32_t)ent.y, F);
+        }
+        merge(valid, sid, delta);
+      }
+      __syncwarp();
+      cw = wi;
+    }
+
+    if (gave_up) {
+      // a chain this long belongs to the column-major engine: leave the accumulator and the bitmap clean
+      for (int t0 = 0; t0 < nt; t0 += 32) {
+        const int i = t0 + lane;
+        if (i < nt) {
+          const int sid = __ldcg(&touched[i]);
+          sum[sid] = 0ULL;
+          if (sid < nprio) atomicAnd(&pending[sid >> 5], ~(1u << (sid & 31)));
+        }
+      }
+      if (lane == 0) {
+        a.status[k] = ST_TABLE;
+        atomicAdd(&a.stats[2], 1ULL);
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- emit.  pass 1: count
+    int nout = 0, nl = 0;
+    for (int t0 = 0; t0 < nt; t0 += 32) {
+      const int i = t0 + lane;
+      const bool valid = i < nt;
+      const int sid = valid ? __ldcg(&touched[i]) : 0;
+      const uint32_t v = valid ? red64(__ldcg(&sum[sid]), F) : 0u;
+      const bool piv = valid && sid < nprio && sid != masksid;
+      const bool pass = valid && v != 0 && sid != masksid && (a.all_columns || !piv);
+      const bool lpass = a.want_L && v != 0 && piv;
+      nout += __popc(__ballot_sync(FULL, pass));
+      nl += __popc(__ballot_sync(FULL, lpass));
+    }
+    const int npre = a.prefix_col ? 1 : 0;
+    unsigned long long o = 0, lo_ = 0;
+    int st = ST_OK;
+    if (lane == 0) {
+      a.cnt[k] = nout + npre;
+      if (a.want_L) a.lcnt[k] = nl;
+      atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
+      atomicAdd(&a.stats[1], macs);
+      if (!a.count_only) {
+        o = atomicAdd(a.cursor, (unsigned long long)(nout + npre));
+        if (o + nout + npre > a.cap) st = ST_SLAB;
+        if (a.want_L) {
+          lo_ = atomicAdd(a.lcursor, (unsigned long long)nl);
+          if (lo_ + nl > a.lcap) st = ST_SLAB;
+        }
+        if (st == ST_SLAB) {
+          atomicAdd(&a.stats[3], 1ULL);
+          atomicAdd(&a.stats[4], (unsigned long long)(nout + npre));
+          atomicAdd(&a.stats[5], (unsigned long long)nl);
+        }
+        a.off[k] = (a.slab_id << 56) | o;
+        if (a.want_L) a.loff[k] = (a.slab_id << 56) | lo_;
+      }
+      a.status[k] = st;
+    }
+    st = __shfl_sync(FULL, st, 0);
+    o = __shfl_sync(FULL, o, 0);
+    lo_ = __shfl_sync(FULL, lo_, 0);
+    const bool write = !a.count_only && st == ST_OK;
+    if (write && npre && lane == 0) {
+      a.oj[o] = a.prefix_col[k];
+      a.ox[o] = a.prefix_val;
+    }
+    // pass 2: write (unsorted: k_sort_rows orders them) and give the slots back as zeros
+    int wo = 0, wl = 0;
+    for (int t0 = 0; t0 < nt; t0 += 32) {
+      const int i = t0 + lane;
+      const bool valid = i < nt;
+      const int sid = valid ? __ldcg(&touched[i]) : 0;
+      const uint32_t v = valid ? red64(__ldcg(&sum[sid]), F) : 0u;
+      const bool piv = valid && sid < nprio && sid != masksid;
+      const bool pass = valid && v != 0 && sid != masksid && (a.all_columns || !piv);
+      const bool lpass = a.want_L && v != 0 && piv;
+      const unsigned pb = __ballot_sync(FULL, pass), lb = __ballot_sync(FULL, lpass);
+      if (valid) sum[sid] = 0ULL;
+      if (write && pass) {
+        const unsigned long long d = o + npre + wo + __popc(pb & lt_mask);
+        a.oj[d] = a.sid2col[sid];
+        a.ox[d] = v;
+      }
+      if (write && lpass) {
+        const unsigned long long d = lo_ + wl + __popc(lb & lt_mask);
+        a.lj[d] = sid;
+        a.lx[d] = v;
+      }
+      wo += __popc(pb), wl += __popc(lb);
+    }
+    __syncwarp();
+  }
+}
+
+// rows written by the global tier: sort (oj, ox)[off+npre, off+cnt) by column and the L stream by prio.
+// One CTA per row; rows of at most SORT_CAP entries are sorted in shared memory, longer ones in place.
+static constexpr int SORT_CAP = 4096;
+// bitonic network for an arbitrary length n: every compare-exchange is ascending (the first step of each merge
+// pairs i with its mirror image), so the virtual +inf elements at positions >= n never move
+__device__ void bitonic_any(int *kk, uint32_t *vv, int n) {
+  int N = 1;
+  while (N < n) N <<= 1;
+  auto cmpx = [&](int lo, int hi) {
+    if (hi < n) {
+      const int ka = kk[lo], kb = kk[hi];
+      if (ka > kb) {
+        kk[lo] = kb, kk[hi] = ka;
+        const uint32_t tv = vv[lo];
+        vv[lo] = vv[hi], vv[hi] = tv;
+      }
+    }
+  };
+  for (int size = 2; size <= N; size <<= 1) {
+    const int half = size >> 1;
+    for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
+      const int blk = i / half, o = i - blk * half;
+      cmpx(blk * size + o, blk * size + size - 1 - o);
+    }
+    __syncthreads();
+    for (int stride = size >> 2; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        cmpx(lo, lo | stride);
+      }
+      __syncthreads();
+    }
+  }
+}
+__device__ void sort_segment(int *gj, uint32_t *gx, int n, int *sk, uint32_t *sv) {
+  if (n <= 1) return;
+  if (n <= SORT_CAP) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = gj[i], sv[i] = gx[i];
+    __syncthreads();
+    bitonic_any(sk, sv, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) gj[i] = sk[i], gx[i] = sv[i];
+    __syncthreads();
+  } else {
+    __syncthreads();
+    bitonic_any(gj, gx, n);  // in place in global memory (rare: rows with more than SORT_CAP entries)
+  }
+}
+__global__ void __launch_bounds__(256) k_sort_rows(const int *__restrict__ todo, int ntodo, const int *__restrict__ status, const int *__restrict__ cnt,
+                                                    const unsigned long long *__restrict__ off, int npre, int *__restrict__ oj,
+                                                    uint32_t *__restrict__ ox, unsigned long long slab_id, const int *__restrict__ lcnt,
+                                                    const unsigned long long *__restrict__ loff, int *__restrict__ lj, uint32_t *__restrict__ lx) {
+  __shared__ int sk[SORT_CAP];
+  __shared__ uint32_t sv[SORT_CAP];
+  for (int t = blockIdx.x; t < ntodo; t += gridDim.x) {
+    const int k = todo ? todo[t] : t;
+    if (status[k] != ST_OK) continue;
+    const unsigned long long o = off[k];
+    if ((o >> 56) != slab_id) continue;
+    const unsigned long long base = o & ((1ULL << 56) - 1);
+    sort_segment(oj + base + npre, ox + base + npre, cnt[k] - npre, sk, sv);
+    if (lcnt != nullptr) {
+      const unsigned long long lb = loff[k] & ((1ULL << 56) - 1);
+      sort_segment(lj + lb, lx + lb, lcnt[k], sk, sv);
+    }
+  }
+}
+
+// slot ids of the global tier
+__global__ void k_sys_extent(const PDesc *__restrict__ pdesc, int width, unsigned long long *__restrict__ out /* [0] nprio, [1] nnz(G) */,
+                             int *__restrict__ isfree) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > width) return;
+  if (c == width) {
+    isfree[c] = 0;
+    return;
+  }
+  const PDesc d = pdesc[c];
+  isfree[c] = d.len < 0;
+  if (d.len >= 0) {
+    atomicMax(&out[0], (unsigned long long)d.prio + 1ULL);
+    atomicMax(&out[1], (unsigned long long)(d.start + d.len));
+  }
+}
+__global__ void k_build_sid(const PDesc *__restrict__ pdesc, const long long *__restrict__ pos, int width, int nprio, int *__restrict__ col2sid,
+                            int *__restrict__ sid2col, PRow *__restrict__ prow) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  const PDesc d = pdesc[c];
+  int sid;
+  if (d.len >= 0) {
+    sid = d.prio;
+    PRow r;
+    r.start = d.start, r.len = d.len, r.pad = c;
+    prow[sid] = r;
+  } else
+    sid = nprio + (int)pos[c];
+  col2sid[c] = sid;
+  sid2col[sid] = c;
+}
+__global__ void k_relabel_G2(const int *__restrict__ Gj, const uint32_t *__restrict__ Gx, long long nnz, const int *__restrict__ col2sid,
+                             int2 *__restrict__ G2) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e < nnz) G2[e] = make_int2(col2sid[Gj[e]], (int)Gx[e]);
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void k_collect_status(const int *__restrict__ status, const int *__restrict__ todo, int ntodo, int want,
                                  int *__restrict__ out, int *__restrict__ nout) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -681,10 +1056,34 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
   DBuf<unsigned> gbitmap;
   int nprio = 0;
 
-  for (int tier = 0; tier < 4 && ntodo > 0; tier++) {
+  // global tier state (built on first use)
+  DBuf<int> col2sid, sid2col, isfree, gtouched;
+  DBuf<long long> fpos;
+  DBuf<PRow> prow;
+  DBuf<int2> G2;
+  DBuf<unsigned long long> gsum, ext(2);
+  DBuf<unsigned> gpending;
+  int gslots = 0;
+  // rows that overflow tier 0: SPASM_B200_SCHUR_DENSE=0 always the global tier (row at a time); default (1): batches of
+  // at least DENSE_MIN rows of an x.U = b solve go through the column-major SpTRSM engine all at once — rows that reach
+  // hundreds of pivots are a dependent chain of L2 round trips in any row-at-a-time engine
+  static const int dense_policy = getenv("SPASM_B200_SCHUR_DENSE") ? atoi(getenv("SPASM_B200_SCHUR_DENSE")) : 1;
+  constexpr int DENSE_MIN = 128;
+
+  // Stages.  SMEM: warp per row, shared-memory hash (rows with at most ~400 touched columns).  Rows that overflow it:
+  //  * x.U = b solves (Schur complement, GPLU batches): at least DENSE_MIN rows go to the column-major SpTRSM engine
+  //    all at once; fewer rows go through the GLOBAL tier with a step budget, and rows whose elimination chain is
+  //    longer than the budget (thousands of dependent steps) are handed to the SpTRSM engine as well;
+  //  * other systems (kernel, rref, L solves): GLOBAL tier without a budget;
+  //  * structural mode (triangular-solve ABI): the CTA-per-row heavy kernel.
+  enum Stage { SMEM, GLOBAL, HEAVY };
+  const bool dense_ok = dense_policy == 1 && G.U_dense != nullptr && E.prefix_col == nullptr && B.mask == nullptr && !E.structural && !E.all_columns;
+  constexpr int GLOBAL_BUDGET = 1536;
+
+  // one kernel stage over the current todo list, with exact-slab retries; returns with status[] final for the stage
+  auto run_stage = [&](Stage stage, int budget) {
     long long need = guess, lneed = guess;
     for (int attempt = 0; attempt < 4 && ntodo > 0; attempt++) {
-      // fresh slab for this launch
       unsigned long long h_ctrs[8];
       if (!E.count_only) {
         if (slabs_j.size() >= 60) throw Error("solve_rows: too many slabs");
@@ -704,7 +1103,7 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
       counter.zero();
       a.todo = todo, a.ntodo = ntodo;
       const int sms = sm_count();
-      if (tier == 0) {
+      if (stage == SMEM) {
         constexpr int H = 512, PC = 256;
         size_t smem = 8 * (size_t)(2 * H + 3 * PC) * 4 + 32 * 8 + 64 * 4;
         int blocks = std::min(cdiv(ntodo, 8), sms * 4);
@@ -715,38 +1114,59 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
           CK(cudaFuncSetAttribute(k_solve_smem<32, H, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_solve_smem<32, H, PC, false><<<blocks, 256, smem, stream()>>>(a);
         }
-        R.stats.light += ntodo;
-      } else if (tier == 1) {
-        // still one warp per row, 4x the table: rows with a few hundred to ~1700 distinct columns
-        constexpr int H = 2048, PC = 512;
-        size_t smem = 8 * (size_t)(2 * H + 3 * PC) * 4 + 32 * 8 + 64 * 4;
-        int blocks = std::min(cdiv(ntodo, 8), sms);
-        if (F.small) {
-          CK(cudaFuncSetAttribute(k_solve_smem<32, H, PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_solve_smem<32, H, PC, true><<<blocks, 256, smem, stream()>>>(a);
-        } else {
-          CK(cudaFuncSetAttribute(k_solve_smem<32, H, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_solve_smem<32, H, PC, false><<<blocks, 256, smem, stream()>>>(a);
+        if (attempt == 0) R.stats.light += ntodo;
+      } else if (stage == GLOBAL) {
+        if (gslots == 0) {
+          // slot ids, the relabelled copy of G, and the per-warp accumulators
+          ext.zero();
+          isfree.alloc(G.width + 1);
+          fpos.alloc(G.width + 1);
+          k_sys_extent<<<cdiv(G.width + 1, 256), 256, 0, stream()>>>(G.pdesc, G.width, ext.p, isfree.p);
+          exclusive_scan_i32_to_i64(isfree.p, fpos.p, G.width + 1);
+          unsigned long long hx[2];
+          ext.download(hx, 2);
+          const long long nfree = fetch(fpos.p + G.width);
+          nprio = (int)hx[0];
+          const long long gnnz = (long long)hx[1];
+          a.nprio = nprio;
+          a.gw = nprio + (int)nfree;
+          a.nwords = (nprio + 31) / 32 + 1;
+          col2sid.alloc(G.width);
+          sid2col.alloc(std::max(a.gw, 1));
+          sid2col.fill_ff();
+          prow.alloc(std::max(nprio, 1));
+          k_build_sid<<<cdiv(G.width, 256), 256, 0, stream()>>>(G.pdesc, fpos.p, G.width, nprio, col2sid.p, sid2col.p, prow.p);
+          G2.alloc(std::max<long long>(gnnz, 1));
+          if (gnnz) k_relabel_G2<<<cdiv(gnnz, 256), 256, 0, stream()>>>(G.Gj, G.Gx, gnnz, col2sid.p, G2.p);
+          const size_t per = (size_t)a.gw * 12 + (size_t)a.nwords * 4;
+          long long slots = std::min<long long>(((long long)ntodo + 3) / 4 * 4, 16LL * sms);
+          const size_t budget_bytes = dev_free_bytes() / 3;
+          while (slots > 4 && (size_t)slots * per > budget_bytes) slots = (slots / 2 + 3) / 4 * 4;
+          gslots = (int)slots;
+          gsum.alloc((size_t)gslots * a.gw);
+          gsum.zero();
+          gtouched.alloc((size_t)gslots * a.gw);
+          gpending.alloc((size_t)gslots * a.nwords);
+          gpending.zero();
+          a.G2 = G2.p, a.col2sid = col2sid.p, a.sid2col = sid2col.p, a.prow = prow.p, a.classbit = G.classbit;
+          a.gsum = gsum.p, a.gtouched = gtouched.p, a.gpending = gpending.p;
+          CK(cudaGetLastError());
+          g_launches += 4;
         }
-        R.stats.light += 0;
-        R.stats.medium += ntodo;
-      } else if (tier == 2) {
-        constexpr int H = 16384, PC = 4096;
-        size_t smem = (size_t)(2 * H + 3 * PC) * 4 + 32 * 8 + 64 * 4;
-        int blocks = std::min(ntodo, sms);
-        if (F.small) {
-          CK(cudaFuncSetAttribute(k_solve_smem<256, H, PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_solve_smem<256, H, PC, true><<<blocks, 256, smem, stream()>>>(a);
-        } else {
-          CK(cudaFuncSetAttribute(k_solve_smem<256, H, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_solve_smem<256, H, PC, false><<<blocks, 256, smem, stream()>>>(a);
-        }
-        R.stats.medium += ntodo;
+        a.pop_budget = budget;
+        const int blocks = std::min(gslots / 4, cdiv(ntodo, 4));
+        if (F.small)
+          k_solve_global<true><<<blocks, 128, 0, stream()>>>(a);
+        else
+          k_solve_global<false><<<blocks, 128, 0, stream()>>>(a);
+        if (!E.count_only)
+          k_sort_rows<<<std::min(ntodo, sms * 8), 256, 0, stream()>>>(todo, ntodo, status.p, R.cnt.p, off.p, E.prefix_col ? 1 : 0, a.oj, a.ox, a.slab_id,
+                                                                       E.want_L ? R.lcnt.p : nullptr, loff.p, a.lj, a.lx);
+        g_launches += 1;
+        if (attempt == 0) R.stats.medium += ntodo;
       } else {
         int blocks = std::min(ntodo, sms * 2);
         if (gkeys.p == nullptr) {
-          // nprio = 1 + max prio: the number of pivotal columns
-          DBuf<int> tmp(1);
           nprio = G.width;  // upper bound on the number of pivots
           prio2col.alloc(nprio + 1);
           prio2col.fill_ff();
@@ -767,85 +1187,87 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
           k_solve_heavy<256, true><<<blocks, 256, 0, stream()>>>(a, prio2col.p);
         else
           k_solve_heavy<256, false><<<blocks, 256, 0, stream()>>>(a, prio2col.p);
-        R.stats.heavy += ntodo;
+        if (attempt == 0) R.stats.heavy += ntodo;
       }
       CK(cudaGetLastError());
       g_launches += 1;
       ctrs.download(h_ctrs, 8);
       sync();
-      const long long n_tbl = (long long)h_ctrs[2], n_slab = (long long)h_ctrs[3];
-      if (n_tbl == 0 && n_slab == 0) {
-        ntodo = 0;
-        break;
-      }
-      // rows that overflowed the slab are retried in this tier with an exact slab
+      const long long n_slab = (long long)h_ctrs[3];
+      if (n_slab == 0) break;
+      // rows that did not fit the slab are retried in this stage with an exactly sized slab (rows that overflowed
+      // the stage itself keep status ST_TABLE and are collected by the caller)
       DBuf<int> &dst = (todo == todoA.p) ? todoB : todoA;
-      if (n_slab > 0) {
-        dst.alloc(ntodo);
-        ntodo_d.zero();
-        k_collect_status<<<cdiv(ntodo, 256), 256, 0, stream()>>>(status.p, todo, ntodo, ST_SLAB, dst.p, ntodo_d.p);
-        // table-overflow rows of this attempt must not be lost: collect them after the retries
-        // by re-scanning all rows at the tier boundary (status stays ST_TABLE)
-        todo = dst.p;
-        ntodo = fetch(ntodo_d.p);
-        need = (long long)h_ctrs[4] + 16;
-        lneed = (long long)h_ctrs[5] + 16;
-        continue;
-      }
-      ntodo = 0;
-      break;
+      dst.alloc(ntodo);
+      ntodo_d.zero();
+      k_collect_status<<<cdiv(ntodo, 256), 256, 0, stream()>>>(status.p, todo, ntodo, ST_SLAB, dst.p, ntodo_d.p);
+      todo = dst.p;
+      ntodo = fetch(ntodo_d.p);
+      need = (long long)h_ctrs[4] + 16;
+      lneed = (long long)h_ctrs[5] + 16;
+      if (attempt == 3 && ntodo > 0) throw Error("solve_rows: slab retries exhausted");
     }
-    // next tier: every row whose status is ST_TABLE
+  };
+  auto collect_overflow = [&]() {
     DBuf<int> &dst = (todo == todoA.p) ? todoB : todoA;
     dst.alloc(nrows);
     ntodo_d.zero();
     k_collect_status<<<cdiv(nrows, 256), 256, 0, stream()>>>(status.p, nullptr, nrows, ST_TABLE, dst.p, ntodo_d.p);
     todo = dst.p;
     ntodo = fetch(ntodo_d.p);
-    if (ntodo > 0) {
-      // mark them pending so a later tier's collect does not see stale states
-      guess = std::max<long long>(guess, 1024LL * ntodo);
-    }
-    if (tier == 1 && ntodo >= 2048 && G.U_dense != nullptr &&  // (a small batch does not amortise the transpose + level schedule)
-        E.prefix_col == nullptr && B.mask == nullptr && !E.structural && !E.all_columns) {
-      // ---- heavy rows of an x.U = b solve: all at once through the SpTRSM engine, in chunks that fit
-      const DCsr &U = *G.U_dense;
-      const int Sm0 = G.width - U.n, r = U.n;
-      DBuf<int> rows_sel(ntodo);
-      k_gather_rows_sel<<<cdiv(ntodo, 256), 256, 0, stream()>>>(B.rows, todo, ntodo, rows_sel.p);
-      const size_t per_row = ((size_t)Sm0 + (size_t)std::max(r, 1)) * 4 + 64;
-      long long ch = (long long)(dev_free_bytes() * 2 / 5 / per_row);
-      ch = std::max<long long>(256, std::min<long long>(ch / 256 * 256, ntodo));
-      DBuf<int> ident;
-      for (int off2 = 0; off2 < ntodo; off2 += (int)ch) {
-        const int nr = (int)std::min<long long>(ch, ntodo - off2);
-        DenseSchur D;
-        build_dense_schur_raw(B.Bp, B.Bj, B.Bx, G.width, rows_sel.p + off2, nr, U, G.qinv_dense, F, D, E.want_L);
-        if (E.count_only) {
-          DBuf<int> oj0;
-          DBuf<uint32_t> ox0;
-          dense_rows_to_sparse(D.Dt.p, D.ld, D.Sm0, D.q0.p, nr, todo, off2, R.cnt.p, off.p, 0, oj0, ox0);
-        } else {
-          if (slabs_j.size() >= 60) throw Error("solve_rows: too many slabs");
-          slabs_j.emplace_back();
-          slabs_x.emplace_back();
-          const unsigned long long sid = slabs_j.size() - 1;
-          if (E.want_L) slabs_lj.emplace_back(), slabs_lx.emplace_back();
-          dense_rows_to_sparse(D.Dt.p, D.ld, D.Sm0, D.q0.p, nr, todo, off2, R.cnt.p, off.p, sid << 56, slabs_j.back(), slabs_x.back());
-          SP.j[sid] = slabs_j.back().p, SP.x[sid] = slabs_x.back().p;
-          if (E.want_L) {
-            dense_rows_to_sparse(D.Vp.p, D.ldv, r, nullptr, nr, todo, off2, R.lcnt.p, loff.p, sid << 56, slabs_lj.back(), slabs_lx.back());
-            LSP.j[sid] = slabs_lj.back().p, LSP.x[sid] = slabs_lx.back().p;
-          }
+    if (ntodo > 0) guess = std::max<long long>(guess, 1024LL * ntodo);
+  };
+  auto run_dense = [&]() {
+    // ---- rows of an x.U = b solve, all at once through the SpTRSM engine, in chunks that fit
+    const DCsr &U = *G.U_dense;
+    const int Sm0 = G.width - U.n, r = U.n;
+    DBuf<int> rows_sel(ntodo);
+    k_gather_rows_sel<<<cdiv(ntodo, 256), 256, 0, stream()>>>(B.rows, todo, ntodo, rows_sel.p);
+    const size_t per_row = ((size_t)Sm0 + (size_t)std::max(r, 1)) * 4 + 64;
+    long long ch = (long long)(dev_free_bytes() * 2 / 5 / per_row);
+    ch = std::max<long long>(256, std::min<long long>(ch / 256 * 256, ntodo));
+    for (int off2 = 0; off2 < ntodo; off2 += (int)ch) {
+      const int nr = (int)std::min<long long>(ch, ntodo - off2);
+      DenseSchur D;
+      build_dense_schur_raw(B.Bp, B.Bj, B.Bx, G.width, rows_sel.p + off2, nr, U, G.qinv_dense, F, D, E.want_L);
+      if (E.count_only) {
+        DBuf<int> oj0;
+        DBuf<uint32_t> ox0;
+        dense_rows_to_sparse(D.Dt.p, D.ld, D.Sm0, D.q0.p, nr, todo, off2, R.cnt.p, off.p, 0, oj0, ox0);
+      } else {
+        if (slabs_j.size() >= 60) throw Error("solve_rows: too many slabs");
+        slabs_j.emplace_back();
+        slabs_x.emplace_back();
+        const unsigned long long sid = slabs_j.size() - 1;
+        if (E.want_L) slabs_lj.emplace_back(), slabs_lx.emplace_back();
+        dense_rows_to_sparse(D.Dt.p, D.ld, D.Sm0, D.q0.p, nr, todo, off2, R.cnt.p, off.p, sid << 56, slabs_j.back(), slabs_x.back());
+        SP.j[sid] = slabs_j.back().p, SP.x[sid] = slabs_x.back().p;
+        if (E.want_L) {
+          dense_rows_to_sparse(D.Vp.p, D.ldv, r, nullptr, nr, todo, off2, R.lcnt.p, loff.p, sid << 56, slabs_lj.back(), slabs_lx.back());
+          LSP.j[sid] = slabs_lj.back().p, LSP.x[sid] = slabs_lx.back().p;
         }
-        R.stats.heavy += nr;
-        g_launches += 8;
       }
-      ntodo = 0;
-      break;
+      R.stats.heavy += nr;
+      g_launches += 8;
+    }
+    ntodo = 0;
+  };
+
+  run_stage(SMEM, 0);
+  collect_overflow();
+  if (ntodo > 0) {
+    if (E.structural) {
+      run_stage(HEAVY, 0);
+      collect_overflow();
+    } else if (dense_ok && ntodo >= DENSE_MIN) {
+      run_dense();
+    } else {
+      run_stage(GLOBAL, dense_ok ? GLOBAL_BUDGET : 0);
+      collect_overflow();
+      if (ntodo > 0 && dense_ok) run_dense();
     }
   }
-  if (ntodo > 0) throw Error("solve_rows: rows left unsolved after the heavy tier");
+  if (ntodo > 0) throw Error("solve_rows: rows left unsolved after the last tier");
 
   unsigned long long h_ctrs[8];
   ctrs.download(h_ctrs, 8);

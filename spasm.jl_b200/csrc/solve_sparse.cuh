@@ -25,6 +25,10 @@ struct SolveSystem {
   // column-major SpTRSM engine (dense_engine.cu) and converted back to sorted sparse rows
   const DCsr *U_dense = nullptr;
   const int *qinv_dense = nullptr;
+  // optional, [nprio/32 + 1] words: bit set at the first prio of every class of mutually independent pivots
+  // (consecutive prios; e.g. the structural pivots of one round that have the same height in the pivot DAG).
+  // The global tier eliminates all pending pivots of a class in one step.  nullptr: one pivot per step.
+  const unsigned *classbit = nullptr;
 };
 
 struct SolveRows {
