@@ -937,7 +937,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   const int B16 = (Bmax + 15) / 16 * 16;
   int kcap = 4096;
   if (const char *e = getenv("SPASM_B200_LAZY_K")) kcap = atoi(e);
-  kcap = std::max(0, std::min(kcap, 16384 - B16));
+  kcap = std::max(0, std::min(kcap, gemm_max_k(F) - B16));
   while (kcap >= 2 * B16 && (size_t)(Sm0 + n_local + B16) * (size_t)(kcap + B16) * 4 > dev_free_bytes() / 4) kcap /= 2;  // keep the two factor buffers small
   const bool lazy = kcap >= 2 * B16 && n_local > 2 * block_size;
   const int group = lazy ? std::max(1, kcap / std::max(block_size, 1)) : 1;
@@ -1140,7 +1140,7 @@ void echelonize_lowrank_device(const DCsr &A, const int *rows, int nrows, DCsr &
   DBuf<unsigned char> colpiv(std::max(Sm0, 1));
   colpiv.zero();
   k_iota2<<<cdiv(B, 256), 256, 0, s>>>(ident.p, B);
-  const int KCH = 16384;  // the tensor-core GEMM takes K <= 16384 per call
+  const int KCH = gemm_max_k(F);  // depth one tensor-core launch takes (int32 accumulator bound of the limb kernel)
   for (unsigned long long blk = 0;; blk++) {
     if (U.n == A.m) break;
     // ---- coefficients and the combined block  Blk[c][t] = sum_k Dt[c][k] * Coef[t][k]

@@ -32,6 +32,9 @@ void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U,
 void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
              bool subtract, const Fp &F, const int *rowmap = nullptr);
 
+// largest K one tcgen05 launch takes for this prime (int32 accumulator bound of the 2 / 3 / 4 limb kernels)
+int gemm_max_k(const Fp &F);
+
 // eliminate the rows `rows` of A against U block by block, RREF each block, append to U
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);
 // low-rank / tall-and-skinny mode: blocks of random combinations of ALL remaining rows

@@ -21,11 +21,21 @@
 
 namespace sb {
 
-static constexpr int TILE = 128;   // output tile M = N = 128
+static constexpr int TILE = 128;   // output tile M = 128 rows
 static constexpr int BK = 128;     // bytes (= int8 elements) of K per stage: one 128B swizzle row
-static constexpr int STAGES = 3;
-static constexpr int STAGE_BYTES = 4 * TILE * BK;  // A0 A1 B0 B1
 static constexpr int MMA_THREADS = 192;
+// Limb configurations.  L = 2 (p < 2^16): N = 128, 3 accumulators, 3 stages.  L = 3 (p < 2^24) and L = 4 (p < 2^32,
+// the reference admits primes up to 4294967291, src/SpaSM.jl:74): N = 64 so that the 2L-1 int32 accumulators
+// (one per power 2^(8s), s = i + j) still fit the 512 TMEM columns; L^2 u8 x u8 MMAs per K step; 2 stages.
+// |acc_s| <= min(s+1, 2L-1-s) * 255^2 * K < 2^31 bounds K per launch (gemm_max_k).
+template <int L>
+struct LimbCfg {
+  static constexpr int TN = (L == 2) ? 128 : 64;
+  static constexpr int STAGES = (L == 2) ? 3 : 2;
+  static constexpr int NACC = 2 * L - 1;
+  static constexpr int STAGE_BYTES = L * TILE * BK + L * TN * BK;
+  static constexpr int MAXK = (L == 2) ? 16384 : (L == 3) ? 10880 : 8192;
+};
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,8 +94,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::i8, D = s32, A = B = u8, both K-major, M = 128, N = 128
-static constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+// kind::i8, D = s32, A = B = u8, both K-major, M = 128, N = TN
+__host__ __device__ constexpr uint32_t idesc_for(int tn) {
+  return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(tn >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+}
 
 // Tile order.  The CTAs in flight work on consecutive tile numbers, so the order decides what the L2 has to
 // hold: row-major order re-streams ALL of B (N x K limbs, up to 900 MB in the bench) for every row of tiles
@@ -93,36 +105,43 @@ static constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_
 // column groups of RASTER_GN tiles: inside a group the B tiles (16 x 128 rows x K, 16 MB at K = 4096) stay in
 // L2 while the rows of A stream past once.
 static constexpr int RASTER_GN = 16;
+template <int TN>
 __device__ __forceinline__ void tile_origin(long long tile, int tiles_m, int tiles_n, int &m0, int &n0) {
   const long long per_group = (long long)RASTER_GN * tiles_m;
   const int grp = (int)(tile / per_group);
   const int within = (int)(tile - (long long)grp * per_group);
   const int gw = min(RASTER_GN, tiles_n - grp * RASTER_GN);
   m0 = (within / gw) * TILE;
-  n0 = (grp * RASTER_GN + within % gw) * TILE;
+  n0 = (grp * RASTER_GN + within % gw) * TN;
 }
 
+struct TensorMaps {
+  CUtensorMap a[4], b[4];  // limb planes of A and B
+};
+
 struct __align__(8) MmaShared {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[3];
+  uint64_t empty[3];
   uint64_t tmem_full;
   uint64_t tmem_empty;
   uint32_t tmem_base;
 };
-static constexpr int HALF = TILE / 2;
+static constexpr int HALF = 64;                                 // columns of C handled per epilogue pass
 static constexpr int STAGE_SP = HALF + 1;                       // padded row of the epilogue staging tile
 static constexpr int STAGING_BYTES = TILE * STAGE_SP * 4;       // 128 x 65 words
 
 // PERSISTENT: gridDim.x CTAs (one per SM) loop over the output tiles.  Per tile: the producer streams
-// K through the 3-stage ring (it runs ahead into the next tile while the epilogue is busy), the MMA
-// thread accumulates hi/mid/lo in TMEM, the epilogue warps pull the whole accumulator into registers
+// K through the smem ring (it runs ahead into the next tile while the epilogue is busy), the MMA
+// thread accumulates the 2L-1 partial sums in TMEM, the epilogue warps pull the whole accumulator into registers
 // (reduced mod p), hand TMEM back at once (tmem_empty) so the next tile's MMAs start, and only then do
-// the read-modify-write of C through a padded staging tile, half a tile at a time.
-template <bool SUB>
+// the read-modify-write of C through a padded staging tile, 64 columns at a time.
+template <bool SUB, int L>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
-k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-              const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, uint32_t *__restrict__ C, long long ldc,
-              int M, int N, int nkb, int tiles_m, int tiles_n, const int *__restrict__ rowmap, Fp F) {
+k_gemm_i8limb(const __grid_constant__ TensorMaps maps, uint32_t *__restrict__ C, long long ldc, int M, int N, int nkb, int tiles_m, int tiles_n,
+              const int *__restrict__ rowmap, Fp F) {
+  using Cfg = LimbCfg<L>;
+  constexpr int TN = Cfg::TN, STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, NACC = Cfg::NACC;
+  constexpr uint32_t IDESC = idesc_for(TN);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *tiles = (uint8_t *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   uint32_t *stage = (uint32_t *)(tiles + STAGES * STAGE_BYTES);
@@ -138,10 +157,11 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     mbar_init(&sh->tmem_full, 1);
     mbar_init(&sh->tmem_empty, 4);  // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB0) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB1) : "memory");
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[l]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[l]) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512) : "memory");
@@ -157,17 +177,17 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       long long kbg = 0;  // k-blocks issued so far (ring position)
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int m0, n0;
-        tile_origin(tile, tiles_m, tiles_n, m0, n0);
+        tile_origin<TN>(tile, tiles_m, tiles_n, m0, n0);
         for (int kb = 0; kb < nkb; kb++, kbg++) {
           const int s = (int)(kbg % STAGES);
           const uint32_t ph = (uint32_t)((kbg / STAGES) & 1);
           mbar_wait(&sh->empty[s], ph ^ 1);
           uint8_t *st = tiles + s * STAGE_BYTES;
           mbar_expect_tx(&sh->full[s], STAGE_BYTES);
-          tma_load_2d(st + 0 * TILE * BK, &mapA0, kb * BK, m0, &sh->full[s]);
-          tma_load_2d(st + 1 * TILE * BK, &mapA1, kb * BK, m0, &sh->full[s]);
-          tma_load_2d(st + 2 * TILE * BK, &mapB0, kb * BK, n0, &sh->full[s]);
-          tma_load_2d(st + 3 * TILE * BK, &mapB1, kb * BK, n0, &sh->full[s]);
+#pragma unroll
+          for (int l = 0; l < L; l++) tma_load_2d(st + l * TILE * BK, &maps.a[l], kb * BK, m0, &sh->full[s]);
+#pragma unroll
+          for (int l = 0; l < L; l++) tma_load_2d(st + L * TILE * BK + l * TN * BK, &maps.b[l], kb * BK, n0, &sh->full[s]);
         }
       }
     }
@@ -184,16 +204,25 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
           mbar_wait(&sh->full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(tiles + s * STAGE_BYTES);
-          const uint64_t a0 = make_desc(base), a1 = make_desc(base + TILE * BK), b0 = make_desc(base + 2 * TILE * BK),
-                         b1 = make_desc(base + 3 * TILE * BK);
+          uint64_t ad[L], bd[L];
+#pragma unroll
+          for (int l = 0; l < L; l++) ad[l] = make_desc(base + l * TILE * BK), bd[l] = make_desc(base + L * TILE * BK + l * TN * BK);
 #pragma unroll
           for (int ks = 0; ks < BK / 32; ks++) {
             const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 32 bytes of K per instruction
-            const uint32_t acc = (kb | ks) ? 1u : 0u;
-            umma_i8(tmem + 0 * TILE, a0 + adv, b0 + adv, IDESC, acc);  // lo
-            umma_i8(tmem + 1 * TILE, a1 + adv, b0 + adv, IDESC, acc);  // mid
-            umma_i8(tmem + 1 * TILE, a0 + adv, b1 + adv, IDESC, 1u);   // mid
-            umma_i8(tmem + 2 * TILE, a1 + adv, b1 + adv, IDESC, acc);  // hi
+            const uint32_t cont = (kb | ks) ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < L; j++)
+#pragma unroll
+              for (int i = 0; i < L; i++) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int sidx = i + j;
+                // the first product issued for power s (smallest j) starts the accumulator of this tile
+                const int j_first = (sidx - (L - 1)) > 0 ? (sidx - (L - 1)) : 0;
+                const uint32_t acc = (j == j_first) ? cont : 1u;
+                umma_i8(tmem + sidx * TN, ad[i] + adv, bd[j] + adv, IDESC, acc);
+              }
           }
           umma_commit(&sh->empty[s]);  // frees the stage when these MMAs have read it
         }
@@ -202,7 +231,7 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     }
   } else {
     // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); each thread owns one output row in TMEM.
-    // The C values of a half tile (128 x 64) are PREFETCHED into registers as 16 coalesced 16-byte
+    // The C values of a 128 x 64 block are PREFETCHED into registers as 16 coalesced 16-byte
     // loads per thread before the accumulator is even ready, so no global-memory latency is exposed;
     // the reduced accumulator is transposed through the padded staging tile to meet them.
     const int q = warp & 3;
@@ -211,12 +240,13 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     const int e = warp - 2;
     const int sub = lane >> 4, l16 = lane & 15;  // two rows per warp instruction, 16 lanes x 16 B each
     const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
+    constexpr int NH = TN / HALF;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
       int m0, n0;
-        tile_origin(tile, tiles_m, tiles_n, m0, n0);
+      tile_origin<TN>(tile, tiles_m, tiles_n, m0, n0);
 #pragma unroll 1
-      for (int h = 0; h < 2; h++) {
+      for (int h = 0; h < NH; h++) {
         const int nh = n0 + h * HALF;
         uint4 cv[16];
         // interior tiles: 16 unconditional 16-byte loads (all in flight together).  Row r of the product is row
@@ -252,21 +282,34 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
           mbar_wait(&sh->tmem_full, it & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging free (previous half read out)
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging free (previous block read out)
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 16) {
-          uint32_t lo[16], mid[16], hi[16];
-          tmem_ld16(lane_base + 0 * TILE + h * HALF + c0, lo);
-          tmem_ld16(lane_base + 1 * TILE + h * HALF + c0, mid);
-          tmem_ld16(lane_base + 2 * TILE + h * HALF + c0, hi);
+          uint32_t acc[NACC][16];
+#pragma unroll
+          for (int sidx = 0; sidx < NACC; sidx++) tmem_ld16(lane_base + sidx * TN + h * HALF + c0, acc[sidx]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            unsigned long long v = ((unsigned long long)hi[j] << 16) + ((unsigned long long)mid[j] << 8) + lo[j];
-            stage[trow * STAGE_SP + c0 + j] = red64(v, F);
+            uint32_t r;
+            if (L == 2) {
+              const unsigned long long v = ((unsigned long long)acc[2][j] << 16) + ((unsigned long long)acc[1][j] << 8) + acc[0][j];
+              r = red64(v, F);
+            } else if (L == 3) {
+              // Horner in 64 bits: (a4 2^16 + a3 2^8 + a2) mod p, then (. 2^16 + a1 2^8 + a0) mod p
+              unsigned long long v = ((unsigned long long)acc[4][j] << 16) + ((unsigned long long)acc[3][j] << 8) + acc[2][j];
+              v = ((unsigned long long)red64(v, F) << 16) + ((unsigned long long)acc[1][j] << 8) + acc[0][j];
+              r = red64(v, F);
+            } else {
+              unsigned long long v = ((unsigned long long)acc[6][j] << 16) + ((unsigned long long)acc[5][j] << 8) + acc[4][j];
+              v = ((unsigned long long)red64(v, F) << 24) + ((unsigned long long)acc[3][j] << 16) + ((unsigned long long)acc[2][j] << 8) + acc[1][j];
+              v = ((unsigned long long)red64(v, F) << 8) + acc[0][j];
+              r = red64(v, F);
+            }
+            stage[trow * STAGE_SP + c0 + j] = r;
           }
         }
-        if (h == 1) {  // the accumulator is out of TMEM: the next tile's MMAs may start
+        if (h == NH - 1) {  // the accumulator is out of TMEM: the next tile's MMAs may start
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sh->tmem_empty)) : "memory");
@@ -316,22 +359,27 @@ k_gemm_i8limb(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
   }
 }
 
-// ------------------------------------------------------------------ limb split (u32 residues -> two K-major u8 planes, zero padded)
-__global__ void k_split_limbs(const uint32_t *__restrict__ in, long long ld, int rows, int K, uint8_t *__restrict__ lo, uint8_t *__restrict__ hi,
-                              int rows_pad, int Kpad, const int *__restrict__ rowmap) {
+// ------------------------------------------------------------------ limb split (u32 residues -> L K-major u8 planes, zero padded)
+struct PlanePtrs {
+  uint8_t *p[4];
+};
+template <int L>
+__global__ void k_split_limbs(const uint32_t *__restrict__ in, long long ld, int rows, int K, PlanePtrs planes, int rows_pad, int Kpad,
+                              const int *__restrict__ rowmap) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one thread per 4 k
   const int kq = Kpad >> 2;
   if (idx >= (long long)rows_pad * kq) return;
   const int r = (int)(idx / kq), k = (int)(idx % kq) * 4;
-  uchar4 l = make_uchar4(0, 0, 0, 0), h = make_uchar4(0, 0, 0, 0);
+  uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
   if (r < rows) {
     const uint32_t *src = in + (long long)(rowmap ? rowmap[r] : r) * ld + k;
-    uint32_t v0 = k + 0 < K ? src[0] : 0u, v1 = k + 1 < K ? src[1] : 0u, v2 = k + 2 < K ? src[2] : 0u, v3 = k + 3 < K ? src[3] : 0u;
-    l = make_uchar4(v0 & 255, v1 & 255, v2 & 255, v3 & 255);
-    h = make_uchar4(v0 >> 8, v1 >> 8, v2 >> 8, v3 >> 8);
+    v0 = k + 0 < K ? src[0] : 0u, v1 = k + 1 < K ? src[1] : 0u, v2 = k + 2 < K ? src[2] : 0u, v3 = k + 3 < K ? src[3] : 0u;
   }
-  *(uchar4 *)(lo + (long long)r * Kpad + k) = l;
-  *(uchar4 *)(hi + (long long)r * Kpad + k) = h;
+#pragma unroll
+  for (int l = 0; l < L; l++) {
+    const int sh = 8 * l;
+    *(uchar4 *)(planes.p[l] + (long long)r * Kpad + k) = make_uchar4((v0 >> sh) & 255, (v1 >> sh) & 255, (v2 >> sh) & 255, (v3 >> sh) & 255);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -349,11 +397,11 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-static CUtensorMap make_map(uint8_t *base, int rows_pad, int Kpad) {
+static CUtensorMap make_map(uint8_t *base, int rows_pad, int Kpad, int box_rows) {
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows_pad};
   cuuint64_t strides[1] = {(cuuint64_t)Kpad};
-  cuuint32_t box[2] = {BK, TILE};
+  cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -363,7 +411,8 @@ static CUtensorMap make_map(uint8_t *base, int rows_pad, int Kpad) {
 
 // statistics for the roofline (bench.py): int8 MACs issued and device time spent in the MMA kernel
 double g_mma_ms = 0;
-double g_mma_macs = 0;  // modular MACs (x4 int8 MACs)
+double g_mma_macs = 0;       // modular MACs
+double g_mma_int8_macs = 0;  // int8 MACs issued for them (x L^2: 4, 9 or 16)
 long long g_mma_calls = 0;
 static bool g_mma_disabled = false;
 
@@ -382,32 +431,33 @@ static void mma_collect_timings() {
   g_ev_pending.clear();
 }
 
-bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
-                 bool subtract, const Fp &F, const int *rowmap) {
-  if (g_mma_disabled || !F.small) return false;
-  if (K < 64 || K > 16384 || (long long)M * N < 4LL * TILE * TILE) return false;
-  static bool env_checked = false;
-  if (!env_checked) {
-    env_checked = true;
-    if (getenv("SPASM_B200_NO_MMA")) {
-      g_mma_disabled = true;
-      return false;
-    }
-  }
+template <int L>
+static void launch_limb_gemm(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
+                             bool subtract, const Fp &F, const int *rowmap) {
+  using Cfg = LimbCfg<L>;
+  constexpr int TN = Cfg::TN;
   cudaStream_t s = stream();
-  const int Mp = (M + TILE - 1) / TILE * TILE, Np = (N + TILE - 1) / TILE * TILE, Kp = (K + BK - 1) / BK * BK;
-  DBuf<uint8_t> a0((size_t)Mp * Kp), a1((size_t)Mp * Kp), b0((size_t)Np * Kp), b1((size_t)Np * Kp);
-  k_split_limbs<<<cdiv((long long)Mp * (Kp >> 2), 256), 256, 0, s>>>(A, lda, M, K, a0.p, a1.p, Mp, Kp, rowmap);
-  k_split_limbs<<<cdiv((long long)Np * (Kp >> 2), 256), 256, 0, s>>>(B, ldb, N, K, b0.p, b1.p, Np, Kp, nullptr);
-  CUtensorMap mA0 = make_map(a0.p, Mp, Kp), mA1 = make_map(a1.p, Mp, Kp), mB0 = make_map(b0.p, Np, Kp), mB1 = make_map(b1.p, Np, Kp);
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + sizeof(MmaShared) + 64;
+  const int Mp = (M + TILE - 1) / TILE * TILE, Np = (N + TN - 1) / TN * TN, Kp = (K + BK - 1) / BK * BK;
+  DBuf<uint8_t> pa((size_t)L * Mp * Kp), pb((size_t)L * Np * Kp);
+  PlanePtrs A_, B_;
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int l = 0; l < 4; l++) A_.p[l] = B_.p[l] = nullptr;
+  for (int l = 0; l < L; l++) {
+    A_.p[l] = pa.p + (size_t)l * Mp * Kp, B_.p[l] = pb.p + (size_t)l * Np * Kp;
+    maps.a[l] = make_map(A_.p[l], Mp, Kp, TILE);
+    maps.b[l] = make_map(B_.p[l], Np, Kp, TN);
+  }
+  k_split_limbs<L><<<cdiv((long long)Mp * (Kp >> 2), 256), 256, 0, s>>>(A, lda, M, K, A_, Mp, Kp, rowmap);
+  k_split_limbs<L><<<cdiv((long long)Np * (Kp >> 2), 256), 256, 0, s>>>(B, ldb, N, K, B_, Np, Kp, nullptr);
+  const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + STAGING_BYTES + 1024 + sizeof(MmaShared) + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_gemm_i8limb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_gemm_i8limb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_gemm_i8limb<true, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_gemm_i8limb<false, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int tiles_m = Mp / TILE, tiles_n = Np / TILE;
+  const int tiles_m = Mp / TILE, tiles_n = Np / TN;
   const int grid = (int)std::min<long long>((long long)tiles_m * tiles_n, sm_count());
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
   if (g_mma_timing) {
@@ -422,16 +472,42 @@ bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, lo
     CK(cudaEventRecord(ev.first, s));
   }
   if (subtract)
-    k_gemm_i8limb<true><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, rowmap, F);
+    k_gemm_i8limb<true, L><<<grid, MMA_THREADS, smem, s>>>(maps, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, rowmap, F);
   else
-    k_gemm_i8limb<false><<<grid, MMA_THREADS, smem, s>>>(mA0, mA1, mB0, mB1, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, rowmap, F);
+    k_gemm_i8limb<false, L><<<grid, MMA_THREADS, smem, s>>>(maps, C, ldc, M, N, Kp / BK, tiles_m, tiles_n, rowmap, F);
   CK(cudaGetLastError());
   if (g_mma_timing) {
     CK(cudaEventRecord(ev.second, s));
     g_ev_pending.push_back(ev);
   }
   g_mma_macs += (double)M * N * K;  // algorithmic (unpadded) modular MACs
+  g_mma_int8_macs += (double)M * N * K * L * L;
   g_mma_calls++;
+}
+
+int gemm_limbs(const Fp &F) { return F.p < (1u << 16) ? 2 : F.p < (1u << 24) ? 3 : 4; }
+int gemm_max_k(const Fp &F) {
+  const int L = gemm_limbs(F);
+  return L == 2 ? LimbCfg<2>::MAXK : L == 3 ? LimbCfg<3>::MAXK : LimbCfg<4>::MAXK;
+}
+
+bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
+                 bool subtract, const Fp &F, const int *rowmap) {
+  if (g_mma_disabled) return false;
+  static bool env_checked = false;
+  if (!env_checked) {
+    env_checked = true;
+    if (getenv("SPASM_B200_NO_MMA")) {
+      g_mma_disabled = true;
+      return false;
+    }
+  }
+  if (K < 64 || K > gemm_max_k(F) || (long long)M * N < 4LL * TILE * TILE) return false;
+  switch (gemm_limbs(F)) {
+    case 2: launch_limb_gemm<2>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F, rowmap); break;
+    case 3: launch_limb_gemm<3>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F, rowmap); break;
+    default: launch_limb_gemm<4>(C, ldc, M, N, A, lda, B, ldb, K, subtract, F, rowmap); break;
+  }
   return true;
 }
 
@@ -442,7 +518,7 @@ extern "C" void spasm_b200_mma_timing(int on) { sb::g_mma_timing = on != 0; }
 extern "C" void spasm_b200_mma_stats(double *out, int reset) {
   sb::mma_collect_timings();
   out[0] = sb::g_mma_ms, out[1] = sb::g_mma_macs, out[2] = (double)sb::g_mma_calls, out[3] = (double)sb::g_launches;
-  if (reset) sb::g_mma_ms = sb::g_mma_macs = 0, sb::g_mma_calls = 0, sb::g_launches = 0;
+  if (reset) sb::g_mma_ms = sb::g_mma_macs = sb::g_mma_int8_macs = 0, sb::g_mma_calls = 0, sb::g_launches = 0;
 }
 
 // ------------------------------------------------------------------ measured tensor-pipe peak

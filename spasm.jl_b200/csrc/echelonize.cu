@@ -248,7 +248,8 @@ static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, in
   DCsr carry;  // deferred rows, reduced against the U of the batch that deferred them
   carry.n = 0, carry.m = m, carry.nnz = 0;
   std::vector<int> carry_orig, hdec;
-  int batch = 256;
+  // speculation is cheap to undo (deferred rows are carried in reduced form), so the batches start large
+  int batch = 4096;
   const bool prof = getenv("SPASM_B200_PROFILE") != nullptr;
   int nbatches = 0;
   long long solved = 0, npivots = 0;
@@ -278,7 +279,7 @@ static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, in
     SolveResult R1, R2;
     const double ts0 = spasm_wtime();
     if (nc > 0) {
-      SolveRows B1{carry.p.p, carry.j.p, carry.x.p, nullptr, nc, nullptr};
+      SolveRows B1{carry.p.p, carry.j.p, carry.x.p, nullptr, nc, nullptr, true};
       solve_rows(G, B1, Em, E.F, R1);
     }
     if (wf > 0) {
@@ -391,7 +392,7 @@ static void echelonize_GPLU(Echelon &E, const DCsr &cur, const int *rows_dev, in
     sync();
     carry = std::move(next);
     done += wf;
-    batch = (2 * nd <= wn) ? std::min(batch * 2, 16384) : std::max(64, std::min(batch, 2 * (wn - nd) + 64));
+    batch = (2 * nd <= wn) ? std::min(batch * 2, 32768) : std::max(256, std::min(batch, 2 * (wn - nd) + 256));
   }
 }
 

@@ -13,6 +13,7 @@
 //    (reachability is monotone in the pivot set, so the continued closure equals the sequential
 //    one; a row that failed speculatively stays failed).
 //  * reorder: heights in the pivot DAG by relaxation, then a stable sort (normalisation N2).
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "pivots.cuh"
@@ -431,327 +432,57 @@ __global__ void __launch_bounds__(256) k_greedy_stream(GreedyArgs g) {
   }
 }
 
-// ------------------------------------------------------------------ greedy search, bit-parallel version
-// One warp per BATCH of 32 consecutive candidate rows.  Reachability is kept as 32-bit masks per
-// column (bit k = row k of the batch), so rows that share most of their closure — the normal case,
-// the pivot graph has one giant component — traverse it once instead of 32 times, and the marks of
-// a batch (12 B per column) stay in L2.  Same semantics as above: speculative multi-source BFS, then
-// batches are decided strictly in order, rows inside a batch in order; pivots published by earlier
-// rows are applied to every later row by continuing the (masked) BFS from the new pivot column.
-struct MsArgs {
-  const long long *Ap;
-  const int *Aj;
-  int n, m;
-  int *pinv, *qinv;
-  const int *cand;
-  int ncand;
-  unsigned *seen, *cnd, *pend;  // [B][m] each
-  int *queue;                   // [B][2][qcap]
-  int qcap;
-  int *ctl;     // [0] cursor (batches decided) [1] pivots published
-  int *done;    // [B]
-  int *newcol;  // [32 B]
-  int *npiv;
-};
-
-struct MsState {
-  unsigned *seen, *cnd, *pend;
-  int *q[2];
-  int cur, qn[2];
-  unsigned alive;      // rows of the batch that are undecided and still have a surviving candidate
-  int *s_surv;         // shared: surviving candidates per row
-};
-
-__device__ __forceinline__ void ms_push(MsState &S, int which, int jj, bool push, int lane) {
-  unsigned pm = __ballot_sync(0xffffffffu, push);
-  if (push) S.q[which][S.qn[which] + __popc(pm & ((1u << lane) - 1u))] = jj;
-  S.qn[which] += __popc(pm);
-}
-
-// lane-parallel visit of column jj with source mask M (all 32 lanes call; `valid` lanes act)
-__device__ __forceinline__ void ms_visit(const MsArgs &g, MsState &S, bool valid, int jj, unsigned M, int lane) {
-  bool push = false;
-  if (valid && M) {
-    unsigned nw = M & ~S.seen[jj];
-    if (nw) {
-      unsigned old = atomicOr(&S.seen[jj], nw);
-      nw &= ~old;
-    }
-    if (nw) {
-      unsigned kills = nw & S.cnd[jj];
-      while (kills) {
-        int k = __ffs(kills) - 1;
-        kills &= kills - 1;
-        atomicSub(&S.s_surv[k], 1);
-      }
-      if (__ldcg(&g.qinv[jj]) >= 0) {
-        unsigned oldp = atomicOr(&S.pend[jj], nw);
-        push = (oldp == 0);
-      }
-    }
-  }
-  ms_push(S, S.cur ^ 1, jj, push, lane);
-}
-
-__device__ __forceinline__ void ms_refresh_alive(MsState &S, unsigned undecided, int lane) {
-  __syncwarp();
-  S.alive = __ballot_sync(0xffffffffu, ((volatile int *)S.s_surv)[lane] > 0) & undecided;
-}
-
-// level-synchronous masked BFS until the frontier is empty or nobody is alive
-__device__ __forceinline__ void ms_bfs(const MsArgs &g, MsState &S, unsigned undecided, int lane) {
-  ms_refresh_alive(S, undecided, lane);
-  while (S.qn[S.cur] > 0 && S.alive) {
-    const int nq = S.qn[S.cur];
-    S.qn[S.cur ^ 1] = 0;
-    for (int h0 = 0; h0 < nq && S.alive; h0 += 32) {
-      const int nb = min(32, nq - h0);
-      long long a = 0;
-      int len = 0;
-      unsigned M = 0;
-      if (lane < nb) {
-        const int j = S.q[S.cur][h0 + lane];
-        M = atomicExch(&S.pend[j], 0u) & S.alive;
-        const int I = __ldcg(&g.qinv[j]);
-        if (I >= 0 && M) {
-          a = g.Ap[I];
-          len = (int)(g.Ap[I + 1] - a);
-        }
-      }
-      int inc = len;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, inc, 31);
-      for (int f0 = 0; f0 < total; f0 += 32) {
-        const int f = f0 + lane;
-        const int fc = min(f, total - 1);
-        int lo = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          int v = __shfl_sync(0xffffffffu, inc, lo + step - 1);
-          if (v <= fc) lo += step;
-        }
-        const int excl = __shfl_sync(0xffffffffu, inc - len, lo);
-        const long long base = __shfl_sync(0xffffffffu, a, lo);
-        const unsigned Msrc = __shfl_sync(0xffffffffu, M, lo);
-        const bool valid = f < total;
-        const int jj = valid ? g.Aj[base + (f - excl)] : 0;
-        ms_visit(g, S, valid, jj, Msrc, lane);
-      }
-      ms_refresh_alive(S, undecided, lane);
-    }
-    S.cur ^= 1;
-  }
-  if (!S.alive) {  // nobody left to serve: drop the frontier (pending masks must not leak into later work)
-    for (int w = 0; w < 2; w++)
-      for (int h = lane; h < S.qn[w]; h += 32) S.pend[S.q[w][h]] = 0;
-    S.qn[0] = S.qn[1] = 0;
-    __syncwarp();
-  }
-}
-
-// column jp (pivot of row ip) has just become pivotal: rows in `rows_mask` that touched it continue through it
-__device__ __forceinline__ void ms_apply_pivot(const MsArgs &g, MsState &S, int jp, unsigned rows_mask, unsigned undecided, int lane) {
-  unsigned touched = 0;
-  if (lane == 0) {
-    const unsigned sn = S.seen[jp], cd = S.cnd[jp];
-    touched = (sn | cd) & rows_mask & S.alive;
-    unsigned kills = cd & ~sn & touched;  // it was a surviving candidate of those rows: no longer one
-    while (kills) {
-      int k = __ffs(kills) - 1;
-      kills &= kills - 1;
-      atomicSub(&S.s_surv[k], 1);
-    }
-    if (touched) {
-      S.seen[jp] = sn | touched;
-      S.pend[jp] = touched;
-      S.q[S.cur][S.qn[S.cur]] = jp;
-    }
-  }
-  touched = __shfl_sync(0xffffffffu, touched, 0);
-  if (touched) {
-    S.qn[S.cur] += 1;
-    __syncwarp();
-    ms_bfs(g, S, undecided, lane);
-  } else
-    ms_refresh_alive(S, undecided, lane);
-}
-
-__global__ void __launch_bounds__(256) k_greedy_msbfs(MsArgs g, int w0, int nbatch) {
-  __shared__ int s_surv_all[8][32];
-  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= nbatch) return;
-  volatile int *ctl = g.ctl;
-  volatile int *done = g.done;
-  MsState S;
-  S.seen = g.seen + (size_t)b * g.m;
-  S.cnd = g.cnd + (size_t)b * g.m;
-  S.pend = g.pend + (size_t)b * g.m;
-  S.q[0] = g.queue + (size_t)b * 2 * g.qcap;
-  S.q[1] = S.q[0] + g.qcap;
-  S.cur = 0, S.qn[0] = S.qn[1] = 0;
-  S.s_surv = s_surv_all[wl];
-  S.s_surv[lane] = 0;
-  __syncwarp();
-  const int t0 = w0 + b * 32;                       // first candidate of this batch
-  const int nrow = min(32, g.ncand - t0);
-  const unsigned present = nrow >= 32 ? 0xffffffffu : ((1u << nrow) - 1u);
-  // ---- scatter the rows: candidates into cnd, pivotal entries into the frontier
-  for (int k = 0; k < nrow; k++) {
-    const int i = g.cand[t0 + k];
-    const unsigned bit = 1u << k;
-    const long long a = g.Ap[i], e1 = g.Ap[i + 1];
-    for (long long e0 = a; e0 < e1; e0 += 32) {
-      const long long e = e0 + lane;
-      bool push = false;
-      int j = 0;
-      if (e < e1) {
-        j = g.Aj[e];
-        if (__ldcg(&g.qinv[j]) < 0) {
-          unsigned old = atomicOr(&S.cnd[j], bit);
-          if (!(old & bit)) atomicAdd(&S.s_surv[k], 1);
-        } else {
-          unsigned old = atomicOr(&S.seen[j], bit);
-          if (!(old & bit)) {
-            unsigned oldp = atomicOr(&S.pend[j], bit);
-            push = (oldp == 0);
-          }
-        }
-      }
-      ms_push(S, S.cur, j, push, lane);
-    }
-  }
-  __syncwarp();
-  unsigned undecided = present;
-  S.alive = present;
-  ms_bfs(g, S, undecided, lane);
-
-  // ---- decide in order
-  int applied = 0;
-  unsigned backoff = 32;
-  for (;;) {
-    int cur = 0, nn = 0;
-    if (lane == 0) {
-      cur = ctl[0];
-      __threadfence();
-      nn = ctl[1];
-    }
-    cur = __shfl_sync(0xffffffffu, cur, 0);
-    nn = __shfl_sync(0xffffffffu, nn, 0);
-    if (S.alive && applied < nn) {
-      for (; applied < nn && S.alive; applied++) ms_apply_pivot(g, S, __ldcg(&g.newcol[applied]), undecided, undecided, lane);
-      backoff = 32;
-      continue;
-    }
-    if (!S.alive && cur != b) {  // every row of the batch is final: let the cursor skip us
-      if (lane == 0) {
-        done[b] = 1;
-        __threadfence();
-        cur = ctl[0];
-      }
-      cur = __shfl_sync(0xffffffffu, cur, 0);
-      if (cur != b) return;
-    }
-    if (cur != b) {
-      __nanosleep(backoff);
-      if (backoff < 1024) backoff <<= 1;
-      continue;
-    }
-    if (S.alive && applied < nn) continue;  // (re-read happened above; nn is final once it is our turn)
-    // ---- our turn: rows in order
-    for (int k = 0; k < nrow && S.alive; k++) {
-      const unsigned bit = 1u << k;
-      if (!(S.alive & bit)) {
-        undecided &= ~bit;
-        continue;
-      }
-      const int i = g.cand[t0 + k];
-      const long long a = g.Ap[i], e1 = g.Ap[i + 1];
-      int jp = -1;
-      for (long long e0 = a; e0 < e1 && jp < 0; e0 += 32) {
-        const long long e = e0 + lane;
-        const int j = e < e1 ? g.Aj[e] : -1;
-        const bool surv = j >= 0 && (S.cnd[j] & bit) && !(S.seen[j] & bit);
-        unsigned c = __ballot_sync(0xffffffffu, surv);
-        if (c) jp = __shfl_sync(0xffffffffu, j, __ffs(c) - 1);
-      }
-      undecided &= ~bit;
-      if (jp >= 0) {
-        if (lane == 0) {
-          g.pinv[i] = jp;
-          g.qinv[jp] = i;
-          g.newcol[nn] = jp;
-          atomicAdd(g.npiv, 1);
-          __threadfence();
-          ctl[1] = nn + 1;
-          __threadfence();
-        }
-        nn++;
-        applied = nn;
-        __syncwarp();
-        ms_apply_pivot(g, S, jp, undecided, undecided, lane);  // the later rows of this batch
-      } else
-        ms_refresh_alive(S, undecided, lane);
-    }
-    if (lane == 0) {
-      done[b] = 1;
-      __threadfence();
-    }
-    // advance the cursor over the following batches that are already final
-    int nxt = b + 1;
-    for (;;) {
-      for (;;) {
-        int tt = nxt + lane;
-        unsigned fin = __ballot_sync(0xffffffffu, tt < nbatch && done[tt] != 0);
-        int run = (fin == 0xffffffffu) ? 32 : __ffs(~fin) - 1;
-        nxt += run;
-        if (run < 32 || nxt >= nbatch) break;
-      }
-      if (nxt > nbatch) nxt = nbatch;
-      int cur2 = 0;
-      if (lane == 0) {
-        __threadfence();
-        int old = atomicMax(g.ctl, nxt);
-        cur2 = old > nxt ? old : nxt;
-        __threadfence();
-      }
-      cur2 = __shfl_sync(0xffffffffu, cur2, 0);
-      if (cur2 >= nbatch) break;
-      int d = 0;
-      if (lane == 0) d = done[cur2];
-      d = __shfl_sync(0xffffffffu, d, 0);
-      if (!d) break;
-      nxt = cur2;
-    }
-    return;
-  }
-}
-
 // ------------------------------------------------------------------ reorder (heights) + extraction
-__global__ void k_height_relax(const long long *__restrict__ Ap, const int *__restrict__ Aj, int n,
-                               const int *__restrict__ pinv, const int *__restrict__ qinv, int *__restrict__ height,
-                               int *__restrict__ changed) {
-  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= n) return;
-  const int jp = pinv[i];
-  if (jp < 0) return;
-  int h = 0;
+// Heights in the pivot DAG (height = longest chain of pivot rows below a row) by peeling from the sinks: a row is
+// final when every pivot row it references is final.  ONE CTA walks the levels; a level is usually a handful of
+// rows (the DAG of the banded benchmark matrices is tens of thousands of levels deep, three rows wide), so the cost
+// per level is a few dependent loads + a block barrier (~3 us) instead of a launch + host round trip per sweep.
+// T = A^T gives, for the pivot column of a finished row, the rows that were waiting for it.
+__global__ void k_out_degree(const long long *__restrict__ Ap, const int *__restrict__ Aj, const int *__restrict__ prow, int npiv,
+                             const int *__restrict__ pinv, const int *__restrict__ qinv, int *__restrict__ deg, int *__restrict__ queue,
+                             int *__restrict__ qtail) {
+  int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= npiv) return;
+  const int i = prow[k], jp = pinv[i];
+  int d = 0;
   for (long long e = Ap[i] + lane; e < Ap[i + 1]; e += 32) {
-    int j = Aj[e];
-    if (j == jp) continue;
-    int i2 = qinv[j];
-    if (i2 >= 0) h = max(h, ((volatile int *)height)[i2] + 1);
+    const int j = Aj[e];
+    d += (j != jp && qinv[j] >= 0);
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
-  if (lane == 0 && h > height[i]) {
-    height[i] = h;
-    *changed = 1;
+  for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if (lane == 0) {
+    deg[i] = d;
+    if (d == 0) queue[atomicAdd(qtail, 1)] = i;
   }
+}
+__global__ void __launch_bounds__(1024) k_height_peel(const long long *__restrict__ Tp, const int *__restrict__ Tj, const int *__restrict__ pinv,
+                                                       int *__restrict__ deg, int *__restrict__ height, int *__restrict__ queue,
+                                                       int *__restrict__ qtail /* in: size of level 0; out: rows finished */) {
+  __shared__ int s_begin, s_end, s_tail;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_begin = 0, s_end = *qtail, s_tail = *qtail;
+  __syncthreads();
+  for (;;) {
+    const int b = s_begin, e = s_end;
+    if (b == e) break;
+    for (int q = b + warp; q < e; q += nwarps) {
+      const int i2 = ((volatile int *)queue)[q];
+      const int h2 = ((volatile int *)height)[i2] + 1;
+      const int c = pinv[i2];
+      for (long long t = Tp[c] + lane; t < Tp[c + 1]; t += 32) {
+        const int i = Tj[t];
+        if (i == i2 || pinv[i] < 0) continue;
+        atomicMax(&height[i], h2);
+        if (atomicSub(&deg[i], 1) == 1) queue[atomicAdd(&s_tail, 1)] = i;
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (threadIdx.x == 0) s_begin = e, s_end = s_tail;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *qtail = s_tail;
 }
 __global__ void k_flag_rows(const int *__restrict__ pinv, int n, int want_pivotal, int *__restrict__ flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -866,34 +597,7 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
     if (ncand > 0) {
       cand.alloc(ncand);
       k_compact_rows<<<cdiv(n, 256), 256, 0, s>>>(flag.p, pos.p, n, cand.p);
-      if (getenv("SPASM_B200_GREEDY_MSBFS") != nullptr) {
-        // experimental: bit-parallel batches of 32 rows.  Exact, but level-synchronous, and the pivot DAG of the
-        // benchmark matrices is thousands of levels deep: measured 2.3x SLOWER than the per-row kernel below.
-        const int qcap = std::min(n, m) + 64;
-        const size_t per = (size_t)m * 12 + (size_t)qcap * 8;
-        size_t budget = std::min<size_t>(dev_free_bytes() / 3, (size_t)24 << 30);
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy_msbfs, 256, 0));
-        const int maxwarps = std::max(1, occ) * sm_count() * 8;
-        const int nb_all = (ncand + 31) / 32;
-        int WB = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxwarps, budget / per));
-        WB = std::min(WB, nb_all);
-        DBuf<unsigned> seen((size_t)WB * m), cnd((size_t)WB * m), pend((size_t)WB * m);
-        DBuf<int> queue((size_t)WB * 2 * qcap), ctl(4), done(WB), newcol((size_t)WB * 32);
-        ctr.zero();
-        MsArgs g{A.p.p, A.j.p, n, m, P.pinv.p, P.qinv.p, cand.p, ncand, seen.p, cnd.p, pend.p, queue.p, qcap, ctl.p, done.p, newcol.p, ctr.p};
-        for (int bb = 0; bb < nb_all; bb += WB) {
-          int nbatch = std::min(WB, nb_all - bb);
-          int w0 = bb * 32;
-          seen.zero(), cnd.zero(), pend.zero();
-          ctl.zero(), done.zero();
-          void *args[] = {&g, &w0, &nbatch};
-          CK(cudaLaunchCooperativeKernel((void *)k_greedy_msbfs, dim3(cdiv((long long)nbatch * 32, 256)), dim3(256), args, 0, s));
-          g_launches += 1;
-          P.greedy_windows++;
-        }
-        CK(cudaGetLastError());
-      } else {
+      {
       const int qcap = std::min(n, m) + 1 + 1024;
       const int mw = (((m + 15) >> 4) + 3) & ~3;
       const size_t per = (size_t)mw * 4 + (size_t)qcap * 4;
@@ -950,14 +654,16 @@ int find_structural_pivots(const DCsr &A, bool greedy, PivotSearch &P, int count
     if (npiv > 0) {
       DBuf<int> height(n);
       height.zero();
-      int iters = 0;
-      for (;;) {
-        CK(cudaMemsetAsync(ctr.p + 2, 0, sizeof(int), s));
-        for (int rep = 0; rep < 4; rep++)
-          k_height_relax<<<rowblocks, 256, 0, s>>>(A.p.p, A.j.p, n, P.pinv.p, P.qinv.p, height.p, ctr.p + 2);
-        iters += 4;
-        if (fetch(ctr.p + 2) == 0) break;
-        if (iters > n + 8) throw Error("structural pivots contain a cycle");
+      {
+        DCsr T;
+        transpose_csr(A, T);
+        DBuf<int> deg(n), queue(npiv), qtail(1);
+        qtail.zero();
+        k_out_degree<<<cdiv((long long)npiv * 32, 256), 256, 0, s>>>(A.p.p, A.j.p, prow.p, npiv, P.pinv.p, P.qinv.p, deg.p, queue.p, qtail.p);
+        k_height_peel<<<1, 1024, 0, s>>>(T.p.p, T.j.p, P.pinv.p, deg.p, height.p, queue.p, qtail.p);
+        CK(cudaGetLastError());
+        g_launches += 2;
+        if (fetch(qtail.p) != npiv) throw Error("structural pivots contain a cycle");
       }
       // max height
       DBuf<int> mx(1);

@@ -71,7 +71,7 @@ struct KArgs {
   const unsigned *classbit;  // optional [nwords]: bit set at the first prio of every class of mutually independent pivots
   int nwords;                // words of the pending bitmap
   int gw;                    // slots per row: nprio + number of non-pivotal columns
-  int pop_budget;            // > 0: a row that needs more elimination steps gives up (status ST_TABLE: next tier)
+  long long pop_budget;      // > 0: a row that has merged more entries of G than this gives up (status ST_TABLE: next stage)
   unsigned long long *gsum;  // [slots][width] unreduced sums; all zero between rows
   int *gtouched;             // [slots][width] slot ids touched by the current row
   unsigned *gpending;        // [slots][nwords] pending pivots of the current row; all zero between rows
@@ -677,10 +677,10 @@ __global__ void __launch_bounds__(128) k_solve_global(KArgs a) {
     }
     __syncwarp();
     // ---- eliminate the pending pivots by increasing prio, one class (inside one word) per step
-    int cw = wmin, steps = 0;
+    int cw = wmin;
     bool gave_up = false;
     while (cw < a.nwords) {
-      if (a.pop_budget > 0 && ++steps > a.pop_budget) {
+      if (a.pop_budget > 0 && (long long)macs > a.pop_budget) {
         gave_up = true;
         break;
       }
@@ -1078,10 +1078,10 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
   //  * structural mode (triangular-solve ABI): the CTA-per-row heavy kernel.
   enum Stage { SMEM, GLOBAL, HEAVY };
   const bool dense_ok = dense_policy == 1 && G.U_dense != nullptr && E.prefix_col == nullptr && B.mask == nullptr && !E.structural && !E.all_columns;
-  constexpr int GLOBAL_BUDGET = 1536;
+  constexpr long long GLOBAL_BUDGET = 1 << 16;  // entries of G merged into one row (a few milliseconds of dependent steps)
 
   // one kernel stage over the current todo list, with exact-slab retries; returns with status[] final for the stage
-  auto run_stage = [&](Stage stage, int budget) {
+  auto run_stage = [&](Stage stage, long long budget) {
     long long need = guess, lneed = guess;
     for (int attempt = 0; attempt < 4 && ntodo > 0; attempt++) {
       unsigned long long h_ctrs[8];
@@ -1259,7 +1259,7 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
     if (E.structural) {
       run_stage(HEAVY, 0);
       collect_overflow();
-    } else if (dense_ok && ntodo >= DENSE_MIN) {
+    } else if (dense_ok && ntodo >= DENSE_MIN && !B.few_pivots) {
       run_dense();
     } else {
       run_stage(GLOBAL, dense_ok ? GLOBAL_BUDGET : 0);

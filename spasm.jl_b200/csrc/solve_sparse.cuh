@@ -38,6 +38,7 @@ struct SolveRows {
   const int *rows = nullptr;  // [nrows] row indices into B (nullptr: 0..nrows-1)
   int nrows = 0;
   const int *mask = nullptr;  // [nrows] optional: column treated as non-pivotal for row k (rref)
+  bool few_pivots = false;    // hint: these rows reach only a handful of pivots (GPLU rows carried in reduced form): row-at-a-time tiers first
 };
 
 // what to emit for each solved row

@@ -22,7 +22,30 @@ def _gemm(gpu, prime, A, B, Cm, subtract, path):
     return out, used, ms.value
 
 
-@pytest.mark.parametrize("prime", [42013, 65521, 251])
+def _exact_product(A, B, prime):
+    """(A @ B^T) mod prime, exactly, for residues up to 2^32 (16-bit halves keep every partial sum below 2^63)"""
+    M, K = A.shape
+    prod = np.zeros((M, B.shape[0]), dtype=np.int64)
+    if prime < (1 << 16):
+        for k0 in range(0, K, 256):
+            prod = (prod + A[:, k0 : k0 + 256] @ B[:, k0 : k0 + 256].T) % prime
+        return prod
+    Ah, Al = A >> 16, A & 0xFFFF
+    for k0 in range(0, K, 256):
+        Bk = B[:, k0 : k0 + 256].T
+        Bh, Bl = Bk >> 16, Bk & 0xFFFF
+        hh = (Ah[:, k0 : k0 + 256] @ Bh) % prime
+        hl = (Ah[:, k0 : k0 + 256] @ Bl + Al[:, k0 : k0 + 256] @ Bh) % prime
+        ll = (Al[:, k0 : k0 + 256] @ Bl) % prime
+        w16 = (1 << 16) % prime
+        w32 = (w16 * w16) % prime
+        part = ((hh.astype(object) * w32 + hl.astype(object) * w16 + ll.astype(object)) % prime).astype(np.int64)
+        prod = (prod + part) % prime
+    return prod
+
+
+# 2 limbs (p < 2^16), 3 limbs (p < 2^24), 4 limbs (up to the largest prime the reference admits, src/SpaSM.jl:74)
+@pytest.mark.parametrize("prime", [42013, 65521, 251, 65537, 16777213, 2147483647, 4294967291])
 @pytest.mark.parametrize("shape", [(256, 256, 128), (300, 517, 200), (1000, 1024, 1000), (129, 2000, 64), (2048, 384, 999)])
 def test_gemm_mod_p(gpu, prime, shape):
     M, N, K = shape
@@ -33,9 +56,7 @@ def test_gemm_mod_p(gpu, prime, shape):
     # extremes: p-1 everywhere in one row/column stresses the accumulators
     A[0, :] = prime - 1
     B[0, :] = prime - 1
-    prod = np.zeros((M, N), dtype=np.int64)
-    for k0 in range(0, K, 256):
-        prod = (prod + A[:, k0 : k0 + 256] @ B[:, k0 : k0 + 256].T) % prime
+    prod = _exact_product(A, B, prime)
     for subtract in (False, True):
         want = (C0 - prod) % prime if subtract else prod
         got_core, used_core, _ = _gemm(gpu, prime, A, B, C0, subtract, 1)
