@@ -478,6 +478,40 @@ class SpaSM:
         return I, j.astype(np.int64) + 1, x.copy()
 
     # ---- src/SpaSM.jl:589
+    # ---- SMS files: "n m M" / "i j v" (1-based) / "0 0 0"  (src/SpaSM.jl:498-529)
+    @staticmethod
+    def _fopen(path, mode):
+        libc = C.CDLL(None)
+        libc.fopen.restype = C.c_void_p
+        libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+        f = libc.fopen(os.fsencode(str(path)), mode.encode())
+        if not f:
+            raise OSError(f"cannot open {path}")
+        libc.fclose.argtypes = [C.c_void_p]
+        return libc, f
+
+    def load(self, path, prime=PRIME0) -> CSR:
+        """fileio_load(...; csr = true) (src/SpaSM.jl:506-512): spasm_triplet_load + spasm_compress"""
+        libc, f = self._fopen(path, "r")
+        try:
+            T = self.lib.spasm_triplet_load(f, prime, None)
+        finally:
+            libc.fclose(f)
+        if not T:
+            raise ValueError(f"{path}: not an SMS file")
+        try:
+            return CSR(self, self.lib.spasm_compress(T))
+        finally:
+            self.lib.spasm_triplet_free(T)
+
+    def save(self, path, A: CSR):
+        """fileio_save(f, A::CSR) (src/SpaSM.jl:523-529): spasm_csr_save"""
+        libc, f = self._fopen(path, "w")
+        try:
+            self.lib.spasm_csr_save(A.data, f)
+        finally:
+            libc.fclose(f)
+
     def transpose(self, A: CSR) -> CSR:
         return CSR(self, self.lib.spasm_transpose(A.data))
 

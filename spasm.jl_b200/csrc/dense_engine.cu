@@ -139,14 +139,22 @@ __global__ void __launch_bounds__(128) k_sptrsm_seq(const long long *__restrict_
         for (long long e0 = a; e0 < b; e0 += 32) {
           if (e0 > a) ent = (e0 + lane < b) ? __ldg(&prog[e0 + lane]) : make_int2(0, 0);
           const int cnt = (int)min((long long)32, b - e0);
-          for (int u = 0; u < cnt; u++) {
-            const int i2 = __shfl_sync(FULL, ent.x, u);
-            const uint32_t cf = (uint32_t)__shfl_sync(FULL, ent.y, u);
-            const uint32_t y = Vp[(long long)i2 * ldv + kq];
-            if (SMALL)
-              acc += (unsigned long long)(cf * y);
-            else
-              accm = addmod(accm, mulmod<false>(cf, y, F), F);
+          // 8 independent loads in flight per step (an entry beyond the list has coefficient 0 and reads row 0)
+          for (int u = 0; u < cnt; u += 8) {
+            uint32_t y[8], cf[8];
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+              const int i2 = __shfl_sync(FULL, ent.x, (u + v) & 31);
+              cf[v] = (uint32_t)__shfl_sync(FULL, ent.y, (u + v) & 31);
+              y[v] = Vp[(long long)i2 * ldv + kq];
+            }
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+              if (SMALL)
+                acc += (unsigned long long)(cf[v] * y[v]);
+              else
+                accm = addmod(accm, mulmod<false>(cf[v], y[v], F), F);
+            }
           }
         }
         if (live) *out = SMALL ? red64(acc, F) : accm;

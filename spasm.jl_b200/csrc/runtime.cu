@@ -260,34 +260,104 @@ spasm_csr *download_csr(const DCsr &D, int64_t prime, const Fp &F) {
 }
 
 // ------------------------------------------------------------------ transpose
-// T = A^T with every row of T sorted by original row index (the order a stable counting sort
-// produces — same as the oracle's, src/SpaSM.jl:589).  Stable LSD radix sort of the nnz entries by
-// column: keys = column (log2 m bits), payload = entry index; rows are recovered from a row-id
-// expansion.  16 B/nnz algorithmic traffic (read j,x; write row,x) + 8(n+m+2).
-__global__ void k_expand_rows(const long long *__restrict__ p, int n, int *__restrict__ rowid) {
-  // one warp per row
-  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n) return;
-  long long a = p[w], b = p[w + 1];
-  for (long long e = a + lane; e < b; e += 32) rowid[e] = w;
-}
+// T = A^T with every row of T sorted by original row index (the order a stable counting sort produces — same as
+// the oracle's, src/SpaSM.jl:589).  Hand-written counting sort: (1) histogram of the columns, (2) exclusive scan =
+// row pointers of T, (3) scatter with one atomic cursor per column (order inside a column is arbitrary),
+// (4) every row of T sorted by original row index in shared memory (rows are short: the column weights of A).
+// Traffic: read j,x once, write (row, x) once = 16 B per non-zero + 8 (n + m + 2), plus the in-place sort of (4)
+// which touches each entry once more; no multi-pass radix sort over the whole matrix.
 __global__ void k_count_cols(const int *__restrict__ j, long long nnz, int *__restrict__ cnt) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < nnz) atomicAdd(&cnt[j[i]], 1);
 }
-__global__ void k_gather_t(const long long *__restrict__ perm, const int *__restrict__ rowid,
-                           const uint32_t *__restrict__ x, long long nnz, int *__restrict__ Tj,
-                           uint32_t *__restrict__ Tx) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < nnz) {
-    long long e = perm[i];
-    Tj[i] = rowid[e];
-    Tx[i] = x[e];
+__global__ void k_scatter_t(const long long *__restrict__ Ap, const int *__restrict__ Aj, const uint32_t *__restrict__ Ax, int n,
+                            const long long *__restrict__ Tp, int *__restrict__ cursor, int *__restrict__ Tj, uint32_t *__restrict__ Tx) {
+  // one warp per row of A
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  for (long long e = Ap[w] + lane; e < Ap[w + 1]; e += 32) {
+    const int c = Aj[e];
+    const long long d = Tp[c] + atomicAdd(&cursor[c], 1);
+    Tj[d] = w;
+    Tx[d] = Ax[e];
   }
 }
-__global__ void k_iota(long long *a, long long n) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) a[i] = i;
+// rows of T by increasing original row index.  Short rows (<= 32 entries): one warp per row, rank by counting;
+// longer rows: one CTA per row, bitonic network in shared memory (or in place beyond its capacity).
+static constexpr int TSORT_CAP = 2048;
+__device__ void t_bitonic(int *kk, uint32_t *vv, int n) {
+  int N = 1;
+  while (N < n) N <<= 1;
+  auto cmpx = [&](int lo, int hi) {
+    if (hi < n) {
+      const int ka = kk[lo], kb = kk[hi];
+      if (ka > kb) {
+        kk[lo] = kb, kk[hi] = ka;
+        const uint32_t tv = vv[lo];
+        vv[lo] = vv[hi], vv[hi] = tv;
+      }
+    }
+  };
+  for (int size = 2; size <= N; size <<= 1) {
+    const int half = size >> 1;
+    for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
+      const int blk = i / half, o = i - blk * half;
+      cmpx(blk * size + o, blk * size + size - 1 - o);
+    }
+    __syncthreads();
+    for (int stride = size >> 2; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        cmpx(lo, lo | stride);
+      }
+      __syncthreads();
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_sort_t_rows_short(const long long *__restrict__ Tp, int m, int *__restrict__ Tj, uint32_t *__restrict__ Tx) {
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= m) return;
+  const long long a = Tp[c];
+  const int len = (int)(Tp[c + 1] - a);
+  if (len <= 1 || len > 32) return;
+  const int key = lane < len ? Tj[a + lane] : 0x7fffffff;
+  const uint32_t val = lane < len ? Tx[a + lane] : 0u;
+  int rank = 0;  // keys are distinct unless a row of A stores a column twice: ties are broken by position
+  for (int u = 0; u < len; u++) {
+    const int ku = __shfl_sync(0xffffffffu, key, u);
+    rank += (ku < key) || (ku == key && u < lane);
+  }
+  __syncwarp();
+  if (lane < len) Tj[a + rank] = key, Tx[a + rank] = val;
+}
+__global__ void __launch_bounds__(256) k_sort_t_rows_long(const long long *__restrict__ Tp, const int *__restrict__ list, int nlist,
+                                                           int *__restrict__ Tj, uint32_t *__restrict__ Tx) {
+  __shared__ int sk[TSORT_CAP];
+  __shared__ uint32_t sv[TSORT_CAP];
+  for (int t = blockIdx.x; t < nlist; t += gridDim.x) {
+    const int c = list[t];
+    const long long a = Tp[c];
+    const int len = (int)(Tp[c + 1] - a);
+    if (len <= TSORT_CAP) {
+      for (int i = threadIdx.x; i < len; i += blockDim.x) sk[i] = Tj[a + i], sv[i] = Tx[a + i];
+      __syncthreads();
+      t_bitonic(sk, sv, len);
+      for (int i = threadIdx.x; i < len; i += blockDim.x) Tj[a + i] = sk[i], Tx[a + i] = sv[i];
+      __syncthreads();
+    } else {
+      __syncthreads();
+      t_bitonic(Tj + a, Tx + a, len);
+    }
+  }
+}
+__global__ void k_flag_long_rows(const long long *__restrict__ Tp, int m, int *__restrict__ flag) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < m) flag[c] = (Tp[c + 1] - Tp[c]) > 32;
+  if (c == m) flag[c] = 0;
+}
+__global__ void k_compact_long(const int *__restrict__ flag, const long long *__restrict__ pos, int m, int *__restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < m && flag[c]) out[pos[c]] = c;
 }
 
 void transpose_csr(const DCsr &A, DCsr &T) {
@@ -300,18 +370,20 @@ void transpose_csr(const DCsr &A, DCsr &T) {
   if (A.nnz) k_count_cols<<<cdiv(A.nnz, 256), 256, 0, g_stream>>>(A.j.p, A.nnz, cnt.p);
   exclusive_scan_i32_to_i64(cnt.p, T.p.p, A.m + 1);
   if (A.nnz == 0) return;
-  DBuf<int> rowid(A.nnz), keys_out(A.nnz);
-  DBuf<long long> idx(A.nnz), perm(A.nnz);
-  k_expand_rows<<<cdiv((long long)A.n * 32, 256), 256, 0, g_stream>>>(A.p.p, A.n, rowid.p);
-  k_iota<<<cdiv(A.nnz, 256), 256, 0, g_stream>>>(idx.p, A.nnz);
-  int bits = 1;
-  while ((1LL << bits) < A.m) bits++;
-  size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, A.j.p, keys_out.p, idx.p, perm.p, A.nnz, 0, bits, g_stream);
-  DBuf<char> t(tmp);
-  cub::DeviceRadixSort::SortPairs(t.p, tmp, A.j.p, keys_out.p, idx.p, perm.p, A.nnz, 0, bits, g_stream);
-  k_gather_t<<<cdiv(A.nnz, 256), 256, 0, g_stream>>>(perm.p, rowid.p, A.x.p, A.nnz, T.j.p, T.x.p);
+  cnt.zero();  // now the scatter cursors
+  k_scatter_t<<<cdiv((long long)A.n * 32, 256), 256, 0, g_stream>>>(A.p.p, A.j.p, A.x.p, A.n, T.p.p, cnt.p, T.j.p, T.x.p);
+  k_sort_t_rows_short<<<cdiv((long long)A.m * 32, 256), 256, 0, g_stream>>>(T.p.p, A.m, T.j.p, T.x.p);
+  DBuf<int> flag(A.m + 1), list(std::max(A.m, 1));
+  DBuf<long long> pos(A.m + 1);
+  k_flag_long_rows<<<cdiv(A.m + 1, 256), 256, 0, g_stream>>>(T.p.p, A.m, flag.p);
+  exclusive_scan_i32_to_i64(flag.p, pos.p, A.m + 1);
+  const int nlong = (int)fetch(pos.p + A.m);
+  if (nlong > 0) {
+    k_compact_long<<<cdiv(A.m, 256), 256, 0, g_stream>>>(flag.p, pos.p, A.m, list.p);
+    k_sort_t_rows_long<<<std::min(nlong, g_sms * 8), 256, 0, g_stream>>>(T.p.p, list.p, nlong, T.j.p, T.x.p);
+  }
   CK(cudaGetLastError());
+  g_launches += 6;
 }
 
 }  // namespace sb
