@@ -261,6 +261,10 @@ def run_ours(args):
     lib.spasm_b200_set_cache(1)   # same-shaped calls in a loop: keep the device blocks between calls (opt-in; default is to return them)
     if world > 1:
         dist_init(lib, dist, rank, world)
+        # the factor stays distributed: the owner of every dense panel materialises and downloads ITS rows of U
+        # (a complete factor on rank 0 is the library's default; see csrc/dist.cuh)
+        lib.spasm_b200_dist_shard_factor.argtypes = [C.c_int]
+        lib.spasm_b200_dist_shard_factor(1)
 
     n = args.rows or FULL_N
     p, j, x = make_input(n)
@@ -293,6 +297,7 @@ def run_ours(args):
     barrier()
     t_wall = time.perf_counter()
     dev_ms, ranks_seen = [], set()
+    step_ms_all = dev_ms
     with ClockSampler(local) as clk:
         for _ in range(K):
             r, ms = resident_step()
@@ -320,9 +325,14 @@ def run_ours(args):
     # ---- end to end through the C ABI on host structs (upload + download of the factor inside)
     e2e_steps = max(1, args.e2e_steps)
     lu = gpu.echelonize(A)  # warm-up (page cache of the host allocator, pinned bounce buffers)
-    u_nnz = lu.U.nnz()
+    u_nnz = lu.U.nnz()  # this rank's share when the factor is distributed
     assert lu.r == rank_found
     del lu
+    u_nnz_all = u_nnz
+    if dist is not None:
+        t = torch.tensor([u_nnz], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        u_nnz_all = int(t.item())
     barrier()
     e2e_t = []
     for _ in range(e2e_steps):
@@ -451,16 +461,18 @@ def run_ours(args):
         "ms_per_step": 1e3 * my, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 residues mod p; dense tail on u8 limbs with int32 tensor-core accumulation", "data": "synthetic",
         "config": {"workload": f"random sparse {n}x{n}, {NNZ_ROW} nnz/row, echelonize+rank mod {PRIME} (BASELINE configs[1])",
-                   "rank": rank_found, "nnz": nnz, "U_nnz": int(u_nnz), "l2": "flushed between iterations (256 MiB write)",
+                   "rank": rank_found, "nnz": nnz, "U_nnz": int(u_nnz_all), "l2": "flushed between iterations (256 MiB write)",
                    "parallelism": "single GPU" if world == 1 else
-                   f"structural pivots replicated; dense tail sharded block-cyclically over {world} ranks, one NCCL broadcast per panel; factor materialised on rank 0"},
-        "e2e": {"value": e2e, "unit": "s", "steps": e2e_steps, "h2d_bytes_per_step": csr_bytes(n, nnz),
-                "d2h_bytes_per_step": int(8 * (rank_found + 1) + 8 * u_nnz + 4 * n)},
+                   f"structural pivots replicated; dense tail sharded block-cyclically over {world} ranks, one NCCL broadcast per panel; "
+                   f"every rank materialises and downloads the rows of U of its own panels (spasm_b200_dist_shard_factor)"},
+        "e2e": {"value": e2e, "unit": "s", "steps": e2e_steps, "h2d_bytes_per_step": csr_bytes(n, nnz) * world,
+                "d2h_bytes_per_step": int(world * (8 * (rank_found + 1) + 4 * n) + 8 * u_nnz_all)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "secondary": secondary,
+        "step_s": [round(v / 1e3, 4) for v in step_ms_all],
         "phases_last_step_s": phases,
         "wall_s_timed_region": wall,
     }

@@ -70,6 +70,8 @@ struct spasm_triplet {
 struct spasm_lu {
   int r;
   bool complete;
+  unsigned char partial; /* spasm_b200 only (padding byte 5 of libspasm's struct, which never reads it): non-zero when this
+                            process holds only SOME rows of U (multi-GPU run): kernel / rref / solve refuse such a factor */
   struct spasm_csr *L; /* NULL unless opts->L */
   struct spasm_csr *U; /* r x m, unit pivots, pivot entry stored first in each row */
   int *qinv; /* [m] column -> U row, or -1 */

@@ -1639,6 +1639,7 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
   fact->Ltmp = L;
   fact->r = 0;
   fact->complete = 0;
+  fact->partial = 0;
 
   int *p = spasm_malloc((i64)(n > 0 ? n : 1) * sizeof(int));
   for (int i = 0; i < n; i++) p[i] = i;

@@ -70,6 +70,7 @@ class _LU(C.Structure):  # src/SpaSM.jl:262-270
     _fields_ = [
         ("r", C.c_int32),
         ("complete", C.c_uint8),
+        ("partial", C.c_uint8),  # spasm_b200: padding byte of the reference struct (include/spasm_b200.h)
         ("L", C.POINTER(_CSR)),
         ("U", C.POINTER(_CSR)),
         ("qinv", C.POINTER(C.c_int32)),
@@ -345,6 +346,11 @@ class LU:
     @property
     def r(self):
         return int(self.data.contents.r)
+
+    @property
+    def partial(self):
+        """multi-GPU runs: True when this process only holds some rows of U (include/spasm_b200.h)"""
+        return bool(self.data.contents.partial)
 
     @property
     def complete(self):

@@ -30,6 +30,9 @@ void build_pdesc_U(const DCsr &U, const int *qinv, DBuf<PDesc> &pdesc) {
 }
 
 void DevFactor::upload(const spasm_lu *fact) {
+  if (fact->partial)
+    throw Error("this factor is partial: the rows of U are held by other ranks of the multi-GPU run (rank 0 holds the complete factor "
+                "unless spasm_b200_dist_shard_factor(1) was requested)");
   prime = fact->U->field->p;
   F = make_field(prime);
   upload_csr(fact->U, U, F);

@@ -886,7 +886,9 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   cudaStream_t s = stream();
   const Dist &dd = dist();
   const int me = dd.rank, NR = dd.nranks;
-  const bool emit_rows = (me == 0);
+  // who materialises the rows of U of panel b: rank 0 (complete factor on rank 0) or the panel's owner (sharded factor)
+  auto emits = [&](long long b) { return NR == 1 || (dd.shard_factor ? panel_owner(b, NR) == me : me == 0); };
+  const bool emit_rows = NR == 1 || dd.shard_factor || me == 0;  // this rank materialises at least some panels
   const int Sm0 = D.Sm0;
   const long long ld = D.ld;
   const bool prof = getenv("SPASM_B200_PROFILE") != nullptr;
@@ -903,7 +905,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     long long ub = 0, left = Sm0;
     for (long long k0 = 0; k0 < nrows && left > 0; k0 += block_size) {
       long long sn = std::min<long long>(block_size, nrows - k0), rr = std::min(sn, left);
-      ub += rr * left;
+      if (emits(k0 / block_size)) ub += rr * left;
       left -= rr;
     }
     if ((size_t)ub * 8 < dev_free_bytes() / 2) csr_reserve(U, U.nnz + ub, U.n + std::min(nrows, Sm0));
@@ -1011,7 +1013,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pivcol.p, rr, colpiv.p);
       refresh_live();
       nlive -= rr;
-      if (emit_rows) {
+      if (emits(b)) {
         // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
         DBuf<int> cnt(rr + 1);
         DBuf<long long> rpos(rr + 1);

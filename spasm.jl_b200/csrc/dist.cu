@@ -85,13 +85,16 @@ int spasm_b200_dist_init(int rank, int nranks, const unsigned char *id128) {
     memcpy(&id, id128, 128);
     ncclComm_t comm;
     NCK(nccl().CommInitRank(&comm, nranks, id, rank));
-    dist().rank = rank, dist().nranks = nranks, dist().comm = comm;
+    const bool keep = dist().shard_factor;
+    dist().rank = rank, dist().nranks = nranks, dist().comm = comm, dist().shard_factor = keep;
     return 0;
   } catch (const std::exception &e) {
     errf("[spasm_b200] spasm_b200_dist_init failed: %s\n", e.what());
     return -1;
   }
 }
+// 0 (default): rank 0 returns the complete factor; 1: every rank returns the rows of U it owns (see dist.cuh)
+void spasm_b200_dist_shard_factor(int on) { dist().shard_factor = on != 0; }
 void spasm_b200_dist_finalize(void) {
   if (dist().comm) nccl().CommDestroy((ncclComm_t)dist().comm);
   dist() = Dist();

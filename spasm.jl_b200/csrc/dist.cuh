@@ -8,6 +8,10 @@ namespace sb {
 struct Dist {
   int rank = 0, nranks = 1;
   void *comm = nullptr;  // ncclComm_t
+  // false: rank 0 materialises every row of U (the other ranks return a factor flagged `partial` that only carries
+  // r and qinv).  true: the owner of each dense panel materialises (and downloads) its rows — the factor is
+  // distributed over the ranks, every rank's struct is flagged `partial`, and the download scales with 1/N.
+  bool shard_factor = false;
 };
 Dist &dist();
 void dist_broadcast(void *dev_buf, size_t bytes, int root);  // on the library stream

@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "dense.cuh"
+#include "dist.cuh"
 #include "pivots.cuh"
 #include "sink.cuh"
 
@@ -610,6 +611,10 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
   g_timings[9] = spasm_wtime() - t_dl;
   fact->r = E.U.n;
   fact->complete = 0;
+  {
+    const Dist &dd = dist();
+    fact->partial = (dd.nranks > 1 && (dd.shard_factor || dd.rank != 0)) ? 1 : 0;
+  }
   fact->L = nullptr;
   fact->p = E.Lp;
   fact->Ltmp = nullptr;

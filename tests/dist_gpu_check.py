@@ -52,6 +52,29 @@ for idx, (n, m, k, prime, seed, kw) in enumerate(cases):
         K1, K2 = gpu.kernel(f), ora.kernel(ora.echelonize(A, **kw))
         for a, b in zip(K1.arrays(), K2.arrays()):
             assert np.array_equal(a, b)
+# ---- sharded factor: every rank materialises the rows of the dense panels it owns (plus the structural rows);
+# together the ranks hold exactly the single-GPU factor, and kernel / solve refuse a partial factor
+gpu.lib.spasm_b200_dist_shard_factor.argtypes = [C.c_int]
+gpu.lib.spasm_b200_dist_shard_factor(1)
+for idx, (n, m, k, prime, seed, kw) in enumerate(cases):
+    p, j, x = synth.random_rows(n, m, k, prime, seed)
+    A = gpu.from_arrays(n, m, p, j, x, prime)
+    f = gpu.echelonize(A, **kw)
+    assert f.partial and f.r == single[idx]["r"]
+    Up, Uj, Ux = f.U.arrays()
+    sp, sj, sx = single[idx]["Up"], single[idx]["Uj"], single[idx]["Ux"]
+    have = np.diff(Up) > 0
+    for i in np.nonzero(have)[0]:
+        assert np.array_equal(Uj[Up[i] : Up[i + 1]], sj[sp[i] : sp[i + 1]]) and np.array_equal(Ux[Up[i] : Up[i + 1]], sx[sp[i] : sp[i + 1]]), (rank, idx, i)
+    cover = torch.tensor(have.astype(np.int32), device="cuda")
+    dist.all_reduce(cover)
+    assert int(cover.min().item()) >= 1, f"case {idx}: some row of U is held by no rank"
+    try:
+        gpu.kernel(f)
+        raise SystemExit("kernel() accepted a partial factor")
+    except (RuntimeError, ValueError, AssertionError):
+        pass
+gpu.lib.spasm_b200_dist_shard_factor(0)
 dist.barrier()
 gpu.lib.spasm_b200_dist_finalize()
 dist.destroy_process_group()
