@@ -429,6 +429,44 @@ def run_ours(args):
             "hbm_peak_gbps": hbm_gbs,
             "phases_s": {k: round(v, 5) for k, v in ph.items() if v}}
         del fs, As
+        # the sparse row engine alone (SPASM_B200_SCHUR_DENSE=0 is read once per process: measured by tools/sparse_probe.py, see profiles/)
+
+        # ---- BASELINE configs[4] scaled 1/100 (the full 500k x 1M kernel basis has ~2e11 non-zeros = 1.7 TB): rectangular
+        # 5000 x 10000, 8 nnz/row: echelonize(L=true), kernel basis, 16 solvable + 4 random right-hand sides in ONE gesv
+        import numpy as np
+        import scipy.sparse as sp
+
+        n4, m4 = 5000, 10000
+        p4, j4, x4 = synth.random_rows(n4, m4, 8, PRIME, 0x5A5A0005)
+        A4 = gpu.from_arrays(n4, m4, p4, j4, x4, PRIME)
+        gpu.echelonize(A4, L=True)
+        t = time.perf_counter()
+        f4 = gpu.echelonize(A4, L=True)
+        t_ech = time.perf_counter() - t
+        t = time.perf_counter()
+        K4 = gpu.kernel(f4)
+        t_ker = time.perf_counter() - t
+        lib.spasm_b200_last_stats(Ls)
+        rng = np.random.default_rng(5)
+        Ad = sp.csr_matrix((x4.astype(np.int64) % PRIME, j4, p4), shape=(n4, m4))
+        X0 = sp.csr_matrix(rng.integers(0, PRIME, size=(16, n4)))
+        Bs = sp.vstack([sp.csr_matrix((X0 @ Ad).toarray() % PRIME), sp.csr_matrix(rng.integers(0, PRIME, size=(4, m4)))]).tocsr()
+        B4 = gpu.from_arrays(20, m4, Bs.indptr.astype(np.int64), Bs.indices.astype(np.int32), synth.balanced(Bs.data, PRIME), PRIME)
+        gpu.gesv(f4, B4)
+        t = time.perf_counter()
+        X4, ok4 = gpu.gesv(f4, B4)
+        t_sol = time.perf_counter() - t
+        assert list(ok4[:16]) == [True] * 16, "a solvable system was rejected"
+        Xd = sp.csr_matrix((X4.arrays()[2].astype(np.int64) % PRIME, X4.arrays()[1], X4.arrays()[0]), shape=(20, n4))
+        assert not (((Xd[:16] @ Ad).toarray() - Bs[:16].toarray()) % PRIME).any(), "x.A != b"
+        secondary["configs4_scaled"] = {
+            "workload": f"random {n4}x{m4}, 8 nnz/row mod {PRIME} (BASELINE configs[4] at 1/100): echelonize(L=true) + kernel basis + gesv of 20 right-hand sides "
+                        "(16 in the row space, checked x.A == b; 4 random)",
+            "rank": f4.r, "echelonize_L_s": t_ech, "kernel_s": t_ker, "kernel_nnz": int(K4.nnz()), "gesv_20_rhs_s": t_sol,
+            "solvable": int(sum(bool(v) for v in ok4)),
+            "kernel_solve_algorithmic_gbps": (Ls[0] / (Ls[6] * 1e-6) / 1e9) if Ls[6] > 0 else None,
+            "kernel_out_gbps_e2e": 8.0 * K4.nnz() / t_ker / 1e9}
+        del f4, K4, A4, X4, B4
 
     # ---- CPU baseline: the oracle on a bounded sample, rank 0 only, with the SAME sample through the CUDA library
     cpu = None

@@ -725,6 +725,17 @@ __global__ void k_zero_pivot_cols(uint32_t *__restrict__ Dt, long long ld, const
   const int k = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
   if (k < nk && s < rr) Dt[(long long)pivcol[s] * ld + kbase + k] = 0u;
 }
+// the factored panel on the wire: live columns only (dead columns of R are zero), 16 bits per entry when p < 2^16
+template <class T>
+__global__ void k_pack_R(const uint32_t *__restrict__ R, long long ldr, const int *__restrict__ cand, int nlive, int rr, T *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (t < nlive && s < rr) out[(long long)s * nlive + t] = (T)R[(long long)s * ldr + cand[t]];
+}
+template <class T>
+__global__ void k_unpack_R(const T *__restrict__ in, const int *__restrict__ cand, int nlive, int rr, uint32_t *__restrict__ R, long long ldr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (t < nlive && s < rr) R[(long long)s * ldr + cand[t]] = (uint32_t)in[(long long)s * nlive + t];
+}
 // out[s][u] = in[idx[s]][u], u < cols
 __global__ void k_gather_rows_ld(const uint32_t *__restrict__ in, long long ldi, const int *__restrict__ idx, int rows, int cols,
                                  uint32_t *__restrict__ out, long long ldo) {
@@ -944,7 +955,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   const bool lazy = kcap >= 2 * B16 && n_local > 2 * block_size;
   const int group = lazy ? std::max(1, kcap / std::max(block_size, 1)) : 1;
   const long long LDK = lazy ? (long long)kcap + B16 : 0;
-  DBuf<uint32_t> Rt_acc, Pt_acc, Rsel;
+  DBuf<uint32_t> Rt_acc, Pt_acc, Rsel, wire;
   if (lazy) Rt_acc.alloc((size_t)Sm0 * LDK), Pt_acc.alloc((size_t)n_local * LDK), Rsel.alloc((size_t)B16 * LDK);
   int Kacc = 0;                                         // depth of the pending product
   long long gend = (long long)group * block_size;       // my local rows [.., gend) are always up to date
@@ -1005,7 +1016,25 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       rr = fetch(hdr.p);
       if (rr > 0) {
         dist_broadcast(pivcol.p, (size_t)rr * sizeof(int), owner);
-        dist_broadcast(R.p, (size_t)rr * Sm0 * sizeof(uint32_t), owner);
+        // R_b travels packed: the nlive columns that were live before this panel (all others are zero), u16 when p < 2^16
+        const size_t esz = F.small ? 2 : 4;
+        wire.alloc(((size_t)rr * nlive * esz + 3) / 4);
+        const dim3 pg(cdiv(nlive, 256), rr);
+        if (owner == me) {
+          if (F.small)
+            k_pack_R<unsigned short><<<pg, 256, 0, s>>>(R.p, Sm0, cand.p, nlive, rr, (unsigned short *)wire.p);
+          else
+            k_pack_R<uint32_t><<<pg, 256, 0, s>>>(R.p, Sm0, cand.p, nlive, rr, wire.p);
+        }
+        dist_broadcast(wire.p, (size_t)rr * nlive * esz, owner);
+        if (owner != me) {
+          CK(cudaMemsetAsync(R.p, 0, (size_t)rr * Sm0 * sizeof(uint32_t), s));
+          if (F.small)
+            k_unpack_R<unsigned short><<<pg, 256, 0, s>>>((const unsigned short *)wire.p, cand.p, nlive, rr, R.p, Sm0);
+          else
+            k_unpack_R<uint32_t><<<pg, 256, 0, s>>>(wire.p, cand.p, nlive, rr, R.p, Sm0);
+        }
+        CK(cudaGetLastError());
       }
       tick(6, t1);
     }

@@ -916,6 +916,17 @@ __global__ void __launch_bounds__(256) k_sort_rows(const int *__restrict__ todo,
   }
 }
 
+// every row of a device CSR sorted by column (rows of arbitrary length; used by the batched gesv)
+__global__ void __launch_bounds__(256) k_sort_csr_rows(const long long *__restrict__ p, int n, int *__restrict__ j, uint32_t *__restrict__ x) {
+  __shared__ int sk[SORT_CAP];
+  __shared__ uint32_t sv[SORT_CAP];
+  for (int r = blockIdx.x; r < n; r += gridDim.x) sort_segment(j + p[r], x + p[r], (int)(p[r + 1] - p[r]), sk, sv);
+}
+void sort_csr_rows(const long long *p, int n, int *j, uint32_t *x) {
+  if (n > 0) k_sort_csr_rows<<<std::min(n, sm_count() * 8), 256, 0, stream()>>>(p, n, j, x);
+  CK(cudaGetLastError());
+}
+
 // slot ids of the global tier
 __global__ void k_sys_extent(const PDesc *__restrict__ pdesc, int width, unsigned long long *__restrict__ out /* [0] nprio, [1] nnz(G) */,
                              int *__restrict__ isfree) {

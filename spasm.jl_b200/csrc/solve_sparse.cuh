@@ -71,5 +71,7 @@ struct SolveResult {
 // heavy rows (more distinct columns than the shared-memory tiers hold) are delegated to this
 // callback: it must fill cnt/j/x for the listed k (dense engine, solve_dense.cu)
 void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, const Fp &F, SolveResult &R);
+// every row of a device CSR sorted by column index
+void sort_csr_rows(const long long *p, int n, int *j, uint32_t *x);
 
 }  // namespace sb

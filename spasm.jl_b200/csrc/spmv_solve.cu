@@ -161,6 +161,40 @@ static void backward(const LSystem &S, const std::vector<int> &diagrow_h, const 
   }
 }
 
+// batched gesv helpers.  okflag[k] = 1 iff row k of the forward solve has no entry on a non-pivotal column; its column
+// indices are replaced by U row indices on the fly (the second solve reads them as a row over the U rows)
+__global__ void k_gesv_check(const long long *__restrict__ Zp, int *__restrict__ Zj, int nb, const int *__restrict__ qinv, int *__restrict__ okflag) {
+  int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k > nb) return;
+  if (k == nb) {
+    if (lane == 0) okflag[nb] = 0;
+    return;
+  }
+  int bad = 0;
+  for (long long e = Zp[k] + lane; e < Zp[k + 1]; e += 32) {
+    const int i = qinv[Zj[e]];
+    if (i < 0)
+      bad = 1;
+    else
+      Zj[e] = i;
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) okflag[k] = !bad;
+}
+__global__ void k_gesv_list(const int *__restrict__ okflag, const long long *__restrict__ pos, int nb, int *__restrict__ list) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nb && okflag[k]) list[pos[k]] = k;
+}
+template <bool SMALL>
+__global__ void k_gesv_finish(int *__restrict__ Xj, uint32_t *__restrict__ Xx, long long nnz, const int *__restrict__ diagrow,
+                              const uint32_t *__restrict__ dinv, Fp F) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int k = Xj[e];
+  Xx[e] = mulmod<SMALL>(Xx[e], dinv[k], F);
+  Xj[e] = diagrow[k];
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -255,39 +289,75 @@ bool spasm_solve(const struct spasm_lu *fact, const spasm_ZZp *b, spasm_ZZp *x) 
   }
 }
 
+// ALL right-hand sides at once (src/SpaSM.jl:915-923): the rows of B go through the row engine in one batch for
+// z.U = b, the solvable ones in a second batch for x.L = z; nothing but ok[] and the result crosses PCIe.
 struct spasm_csr *spasm_gesv(const struct spasm_lu *fact, const struct spasm_csr *B, bool *ok) {
   try {
     ApiCall api_scope_;
     if (fact->L == nullptr) throw Error("spasm_gesv needs a factorisation computed with L=true");
     DevFactor f;
     f.upload(fact);
-    const int m = f.U.m, r = f.U.n, n = fact->L->n;
-    std::vector<int> qinv(fact->qinv, fact->qinv + m);
+    const int m = f.U.m, r = f.U.n, n = fact->L->n, nb = B->n;
+    cudaStream_t s = stream();
     DBuf<PDesc> pdesc;
     build_pdesc_U(f.U, f.qinv.p, pdesc);
     LSystem S;
     build_Lsystem(fact->L, fact->p, f.F, S);
-    std::vector<int> dr(fact->p, fact->p + r);
-    std::vector<long long> Xp(B->n + 1, 0);
-    std::vector<int> Xj;
-    std::vector<spasm_ZZp> Xx;
-    std::vector<spasm_ZZp> b(m), x(std::max(n, 1));
-    for (int k = 0; k < B->n; k++) {
-      std::fill(b.begin(), b.end(), 0);
-      for (i64 e = B->p[k]; e < B->p[k + 1]; e++) b[B->j[e]] = B->x[e];
-      std::vector<uint32_t> z;
-      ok[k] = forward(f, pdesc, qinv, b.data(), z);
-      if (ok[k]) {
-        backward(S, dr, f.F, z, n, x.data());
-        for (int i = 0; i < n; i++)
-          if (x[i] != 0) Xj.push_back(i), Xx.push_back(x[i]);
+    DCsr dB;
+    upload_csr(B, dB, f.F);
+    // ---- z.U = b for every row of B
+    SolveSystem GU{f.U.j.p, f.U.x.p, pdesc.p, m};
+    SolveRows RB{dB.p.p, dB.j.p, dB.x.p, nullptr, nb, nullptr};
+    SolveEmit Em;
+    Em.all_columns = true;
+    SolveResult Z;
+    solve_rows(GU, RB, Em, f.F, Z);
+    // solvable <=> nothing is left on a non-pivotal column; the multipliers become a row over the U rows
+    DBuf<int> okflag(std::max(nb, 1) + 1), oklist(std::max(nb, 1));
+    DBuf<long long> okpos(std::max(nb, 1) + 1);
+    k_gesv_check<<<cdiv((long long)nb * 32 + 32, 256), 256, 0, s>>>(Z.p.p, Z.j.p, nb, f.qinv.p, okflag.p);
+    exclusive_scan_i32_to_i64(okflag.p, okpos.p, nb + 1);
+    const int nok = (int)fetch(okpos.p + nb);
+    std::vector<int> hok(std::max(nb, 1));
+    if (nb) okflag.download(hok.data(), nb);
+    if (nok) k_gesv_list<<<cdiv(nb, 256), 256, 0, s>>>(okflag.p, okpos.p, nb, oklist.p);
+    sync();
+    for (int k = 0; k < nb; k++) ok[k] = hok[k] != 0;
+    // ---- x.L = z for the solvable ones
+    SolveResult X;
+    if (nok > 0) {
+      SolveSystem GL{S.L.j.p, S.scaled.p, S.pdesc.p, S.r};
+      SolveRows RZ{Z.p.p, Z.j.p, Z.x.p, oklist.p, nok, nullptr};
+      solve_rows(GL, RZ, Em, f.F, X);
+      // (k, v) -> (row of A that holds the k-th diagonal, v / diagonal), then by increasing row index
+      if (X.nnz) {
+        if (f.F.small)
+          k_gesv_finish<true><<<cdiv(X.nnz, 256), 256, 0, s>>>(X.j.p, X.x.p, X.nnz, S.diagrow.p, S.dinv.p, f.F);
+        else
+          k_gesv_finish<false><<<cdiv(X.nnz, 256), 256, 0, s>>>(X.j.p, X.x.p, X.nnz, S.diagrow.p, S.dinv.p, f.F);
+        sort_csr_rows(X.p.p, nok, X.j.p, X.x.p);
       }
-      Xp[k + 1] = (long long)Xj.size();
     }
-    spasm_csr *X = spasm_csr_alloc(B->n, n, (i64)Xj.size(), B->field->p, true);
-    for (int k = 0; k <= B->n; k++) X->p[k] = Xp[k];
-    if (!Xj.empty()) memcpy(X->j, Xj.data(), Xj.size() * sizeof(int)), memcpy(X->x, Xx.data(), Xx.size() * sizeof(spasm_ZZp));
-    return X;
+    // ---- host CSR: one row per right-hand side (empty when not solvable)
+    std::vector<long long> xp(nok + 1, 0);
+    if (nok > 0) X.p.download(xp.data(), nok + 1);
+    sync();
+    const long long xnz = nok > 0 ? xp[nok] : 0;
+    spasm_csr *R = spasm_csr_alloc(nb, n, xnz, B->field->p, true);
+    if (xnz) {
+      X.j.download(R->j, xnz);
+      convert_to_balanced(X.x.p, (int *)X.x.p, xnz, f.F);
+      CK(cudaMemcpyAsync(R->x, X.x.p, (size_t)xnz * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    sync();
+    // rows of solvable systems are consecutive in X: row k of R starts where its X row starts
+    int t = 0;
+    for (int k = 0; k < nb; k++) {
+      R->p[k] = xp[t];
+      if (hok[k]) t++;
+    }
+    R->p[nb] = xp[nok];
+    return R;
   } catch (const std::exception &e) {
     errf("[spasm_b200] spasm_gesv failed: %s\n", e.what());
     return nullptr;

@@ -164,6 +164,41 @@ def test_solve_gesv_spmv(gpu, oracle, prime):
         assert np.array_equal(a, b2)
 
 
+def test_gesv_many_right_hand_sides(gpu, oracle):
+    """the batched gesv (all right-hand sides through the row engine at once): 40 systems, solvable ones, random ones,
+    a zero row and a repeated row, against the oracle's one-at-a-time loop — ok[] and X bit for bit, and x.A == b"""
+    import scipy.sparse as sp
+
+    prime, n, m = 42013, 500, 800
+    p, j, x = synth.random_rows(n, m, 5, prime, 33)
+    A = gpu.from_arrays(n, m, p, j, x, prime)
+    fo, fg = oracle.echelonize(A, L=True), gpu.echelonize(A, L=True)
+    Ad = checks.dense_of(gpu, A)
+    rng = np.random.default_rng(8)
+    rows = []
+    for t in range(40):
+        if t % 5 == 4:
+            rows.append(rng.integers(0, prime, size=m))  # almost surely not in the row space
+        elif t == 7:
+            rows.append(np.zeros(m, dtype=np.int64))
+        else:
+            x0 = np.zeros(n, dtype=np.int64)
+            idx = rng.choice(n, size=1 + t % 17, replace=False)
+            x0[idx] = rng.integers(1, prime, size=len(idx))
+            rows.append(checks.mm(x0, Ad, prime))
+    rows[11] = rows[10].copy()
+    Bd = np.vstack(rows)
+    B = gpu.CSR(sp.csc_matrix(Bd.T), prime)
+    Xo, oko = oracle.gesv(fo, B)
+    Xg, okg = gpu.gesv(fg, B)
+    assert np.array_equal(oko, okg) and okg.sum() >= 30
+    for a, b2 in zip(Xo.arrays(), Xg.arrays()):
+        assert np.array_equal(a, b2)
+    Xd = checks.dense_of(gpu, Xg)
+    good = np.nonzero(okg)[0]
+    assert np.array_equal(checks.mm(Xd[good], Ad, prime), Bd[good] % prime)
+
+
 def test_medium_scale_c1_like(gpu, oracle):
     """a down-scaled configs[0] (random 5 nnz/row, mod 42013): echelonize + kernel, bit-exact"""
     n = m = 3000
