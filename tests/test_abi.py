@@ -27,6 +27,24 @@ def test_header_symbols_exported(pkg, product_lib):
     assert set(pkg.ABI) == set(syms), set(pkg.ABI) ^ set(syms)
 
 
+def test_extension_header_symbols_exported(product_lib):
+    """include/spasm_b200_ext.h: the entry points libspasm does not have (memory policy, multi-GPU, instrumentation)"""
+    text = (ROOT / "include" / "spasm_b200_ext.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(spasm_b200_[A-Za-z0-9_]+)\s*\(", text)))
+    assert len(syms) >= 20
+    lib = C.CDLL(str(product_lib), mode=C.RTLD_LOCAL)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/spasm_b200_ext.h but not exported"
+    # and nothing is exported that no header declares
+    import subprocess
+
+    out = subprocess.run(["nm", "-D", "--defined-only", str(product_lib)], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T spasm_" in l}
+    declared = set(syms) | set(_declared_symbols())
+    assert exported <= declared, exported - declared
+
+
 def test_oracle_exports_same_abi(pkg, oracle):
     for s in _declared_symbols():
         assert hasattr(oracle.lib, s)

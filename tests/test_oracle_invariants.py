@@ -200,3 +200,18 @@ def test_low_rank_mode_oracle(oracle, prime, kw):
     checks.check_rank_and_rowspace(oracle, A, fact)
     K = oracle.kernel(fact)
     checks.check_kernel(oracle, A, fact, K)
+
+
+@pytest.mark.parametrize("case", [(1500, 1500, 5, 42013, 3, {}), (900, 1300, 4, 65521, 12, dict(dense_block_size=64)),
+                                  (700, 650, 4, 4294967291, 13, dict(dense_block_size=100)), (1600, 1500, 10, 42013, 6, dict(dense_block_size=300)),
+                                  (800, 800, 5, 3, 2, dict(dense_block_size=50))])
+def test_blocked_dense_equals_rowwise(oracle, case, monkeypatch):
+    """the blocked OpenMP dense tail of the oracle (delayed-reduction products, sub-blocked RREF) against its own
+    row-by-row form (one sparse triangular solve per row, textbook Gauss-Jordan): every array of the factor, bit for bit"""
+    n, m, k, prime, seed, kw = case
+    p, j, x = synth.random_rows(n, m, k, prime, seed)
+    A = oracle.from_arrays(n, m, p, j, x, prime)
+    blocked = checks.lu_arrays(oracle.echelonize(A, **kw))
+    monkeypatch.setenv("SPASM_ORACLE_ROWWISE", "1")
+    rowwise = checks.lu_arrays(oracle.echelonize(A, **kw))
+    checks.assert_same(rowwise, blocked, "blocked vs row-wise: ")
