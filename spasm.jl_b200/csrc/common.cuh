@@ -122,6 +122,11 @@ __device__ inline uint32_t dev_inv(uint32_t a, uint32_t p) {  // extended Euclid
 // ------------------------------------------------------------------ device memory
 // stream-ordered allocations from the default pool (no cudaFree synchronisation)
 void *dmalloc_bytes(size_t bytes);
+// cache mode only: pinned host blocks for large result arrays (runtime.cu); nullptr = use malloc
+bool cache_enabled();
+void *host_big_alloc(size_t bytes);
+size_t host_big_capacity(const void *p);
+bool host_big_release(void *p);
 void dfree(void *p);
 size_t dev_free_bytes();
 

@@ -211,7 +211,6 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
 // counters of the deferred trailing updates since the last reset (tests assert that the far-row path ran):
 // [0] far flushes with far rows  [1] multiplier-correction GEMMs  [2] far rows x depth flushed  [3] near updates
 long long g_tail_stats[4] = {0, 0, 0, 0};
-long long g_tile_fallbacks = 0;  // tiles of the panel factorisation that needed the per-pivot kernel
 
 void make_free_columns(const int *qinv, int m, int *flag, long long *pos, int *q, int *qpos) {
   cudaStream_t s = stream();
@@ -613,191 +612,6 @@ k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long
   cluster.sync();  // nobody leaves while its shared memory may still be written remotely
 }
 
-// BLOCK version of the tile Gauss-Jordan: ONE cluster barrier per tile instead of two per pivot.
-// The pivot of column cc is the first row (by index) among the rows that are not pivots yet whose entry on cc, after
-// the eliminations of the tile so far, is non-zero.  Those rows are searched in index order, so the pivots of a tile
-// are found among the first NCAND rows that are not pivots yet — in a dense panel practically always the first 32.
-// Every CTA therefore runs the sequential Gauss-Jordan on that small candidate block [W | G] (NCAND x 64, shared
-// memory, block barriers only; the work is replicated, it is tiny), which yields the pivot rows in their FINAL,
-// mutually reduced form; every other row r is then finished in one independent step,
-//     G_r = - sum_s W_r[pivot column s] * G_pivot_s
-// (the multiplier of pivot s is the row's ORIGINAL entry, because the pivot rows are reduced among themselves).
-// The result equals the per-pivot kernel's (the reduced echelon form for a given pivot sequence is unique).
-// If some column finds no pivot inside the candidate block while more unpivoted rows exist beyond it, the true
-// pivot may lie there: the kernel changes nothing and raises ctl->pad[0]; the host runs the per-pivot kernel.
-static constexpr int NCAND = 64;
-__global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(GRP)
-k_tile_block(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long ldw, int *__restrict__ ispiv, int *__restrict__ pivrow,
-             int *__restrict__ pivcol, uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
-             const int *__restrict__ cand, Fp F) {
-  namespace cgx = cooperative_groups;
-  cgx::cluster_group cluster = cgx::this_cluster();
-  __shared__ uint32_t Wc[NCAND][33], Gq[NCAND][33];
-  __shared__ int crow[NCAND];          // candidate rows, increasing
-  __shared__ int cpiv[NCAND];          // candidate already a pivot of this tile?
-  __shared__ int prow_i[PB], pcol_l[PB];  // pivot s of the tile: candidate index, local column
-  __shared__ int s_cnt[GRP / 32], s_pick[2], s_misc[4];
-  const int cta = (int)cluster.block_rank();
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int r = cta * GRP + tid;  // my row in the final pass
-  const bool live = r < Sn;
-  const int c0 = ctl->c0, npiv0 = ctl->npiv;
-  if (npiv0 >= Sn || c0 >= Sm0 || ctl->pad[0] != 0) {  // panel finished, or waiting for the per-pivot kernel: no-op
-    if (cta == 0 && tid == 0 && ctl->pad[0] == 0) ctl->found = 0, ctl->consumed = 0;
-    return;
-  }
-  const int wc = min(32, Sm0 - c0);
-  // ---- the first NCAND rows that are not pivots yet (every CTA computes the same list)
-  int ncand = 0, nfree_total = 0;
-  for (int base = 0; base < Sn; base += GRP) {
-    const int rr_ = base + tid;
-    const bool fr = rr_ < Sn && ispiv[rr_] == 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, fr);
-    if (lane == 0) s_cnt[wid] = __popc(bal);
-    __syncthreads();
-    int before = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < GRP / 32; w++) {
-      if (w < wid) before += s_cnt[w];
-      tot += s_cnt[w];
-    }
-    const int pos = ncand + before + __popc(bal & ((1u << lane) - 1u));
-    if (fr && pos < NCAND) crow[pos] = rr_;
-    ncand += tot;
-    __syncthreads();
-  }
-  nfree_total = ncand;
-  ncand = min(ncand, NCAND);
-  // ---- candidate block: W (the K slices summed) and G = 0
-  for (int idx = tid; idx < NCAND * 32; idx += GRP) {
-    const int i = idx >> 5, c = idx & 31;
-    uint32_t v = 0;
-    if (i < ncand && c < wc) {
-      const int row = crow[i];
-      for (int z = 0; z < WKS; z++) v += Wt[((long long)z * 32 + c) * ldw + row];
-      v %= F.p;
-    }
-    Wc[i][c] = v;
-    Gq[i][c] = 0;
-  }
-  if (tid < NCAND) cpiv[tid] = 0;
-  cluster.sync();  // every CTA has read ispiv / ctl: CTA 0 may update them at the end
-  // ---- sequential Gauss-Jordan among the candidates
-  int npiv = npiv0, found = 0, cc = 0;
-  bool bail = false;
-  for (; cc < wc && found < PB && npiv < Sn; cc++) {
-    // first candidate (by index) that is not a pivot yet with a non-zero entry on column cc
-    if (tid < 64) {
-      const bool ok = tid < ncand && !cpiv[tid] && Wc[tid][cc] != 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) s_pick[wid] = bal ? (wid * 32 + __ffs(bal) - 1) : 0x7fffffff;
-    }
-    __syncthreads();
-    const int pi = min(s_pick[0], s_pick[1]);
-    if (pi == 0x7fffffff) {
-      if (nfree_total > ncand) {  // the pivot of this column may be a row beyond the candidate block
-        bail = true;
-        break;
-      }
-      __syncthreads();
-      continue;  // no pivot on this column (exact: every unpivoted row is a candidate)
-    }
-    const uint32_t alpha = dev_inv_small(Wc[pi][cc], F);
-    __syncthreads();
-    // scale the pivot row: W columns cc..wc and G columns 0..found (its own slot starts as 1)
-    if (tid < 64) {
-      const int k = tid;
-      if (k < 32) {
-        if (k >= cc && k < wc) Wc[pi][k] = mulmod<true>(alpha, Wc[pi][k], F);
-      } else {
-        const int sx = k - 32;
-        if (sx < found)
-          Gq[pi][sx] = mulmod<true>(alpha, Gq[pi][sx], F);
-        else if (sx == found)
-          Gq[pi][sx] = alpha;  // alpha * 1
-      }
-    }
-    if (tid == 0) cpiv[pi] = 1, prow_i[found] = pi, pcol_l[found] = cc;
-    __syncthreads();
-    // eliminate column cc from every other candidate (earlier pivots of the tile included)
-    for (int idx = tid; idx < ncand * 64; idx += GRP) {
-      const int i = idx >> 6, k = idx & 63;
-      if (i == pi) continue;
-      const uint32_t f = Wc[i][cc];
-      if (f == 0) continue;
-      const uint32_t nf = F.p - f;
-      if (k < 32) {
-        if (k > cc && k < wc) {
-          const uint32_t t = Wc[i][k] + mulmod<true>(nf, Wc[pi][k], F);
-          Wc[i][k] = t >= F.p ? t - F.p : t;
-        }
-      } else {
-        const int sx = k - 32;
-        if (sx <= found) {
-          const uint32_t t = Gq[i][sx] + mulmod<true>(nf, Gq[pi][sx], F);
-          Gq[i][sx] = t >= F.p ? t - F.p : t;
-        }
-      }
-    }
-    __syncthreads();
-    // column cc itself is cleared last (it held the multipliers during the pass above)
-    for (int i = tid; i < ncand; i += GRP)
-      if (i != pi) Wc[i][cc] = 0;
-    found++, npiv++;
-    __syncthreads();
-  }
-  if (bail) {
-    if (cta == 0 && tid == 0) ctl->pad[0] = 1, ctl->found = 0, ctl->consumed = 0;
-    return;
-  }
-  // ---- every row of the panel: G_r
-  if (live && found > 0) {
-    // is my row a candidate?
-    int ci = -1;
-    for (int i = 0; i < ncand; i++)
-      if (crow[i] == r) ci = i;
-    if (ci >= 0) {
-      for (int sx = 0; sx < found; sx++) Gc[(long long)sx * ldw + r] = Gq[ci][sx];
-    } else {
-      uint32_t g[PB];
-#pragma unroll
-      for (int sx = 0; sx < PB; sx++) g[sx] = 0;
-      for (int sp = 0; sp < found; sp++) {
-        const int c = pcol_l[sp];
-        uint32_t f = 0;
-        for (int z = 0; z < WKS; z++) f += Wt[((long long)z * 32 + c) * ldw + r];
-        f %= F.p;
-        if (f == 0) continue;
-        const uint32_t nf = F.p - f;
-        const int pi = prow_i[sp];
-#pragma unroll
-        for (int sx = 0; sx < PB; sx++) {
-          if (sx < found) {
-            const uint32_t t = g[sx] + mulmod<true>(nf, Gq[pi][sx], F);
-            g[sx] = t >= F.p ? t - F.p : t;
-          }
-        }
-      }
-#pragma unroll
-      for (int sx = 0; sx < PB; sx++)
-        if (sx < found) Gc[(long long)sx * ldw + r] = g[sx];
-    }
-  }
-  if (cta == 0) {
-    if (tid < found) {
-      const int row = crow[prow_i[tid]];
-      ispiv[row] = 1;
-      pivrow[npiv0 + tid] = row;
-      pivcol[npiv0 + tid] = cand[c0 + pcol_l[tid]];
-      tilepiv[tid] = row;
-    }
-    if (tid == 0) {
-      ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc, ctl->c0 = c0 + cc;
-      if (found < PB / 2 && npiv < Sn) ctl->low += 1;
-    }
-  }
-}
-
 // Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]  for a narrow tile (c < wc <= 32): one CTA per 32 rows r
 template <bool SMALL>
 __global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt_panel, long long ld, const uint32_t *__restrict__ T, int Sn, int Sm0,
@@ -966,7 +780,6 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
   k_set_identity<<<cdiv((long long)Sn * Sn, 256), 256, 0, s>>>(T, Sn);
   const bool fast = F.small && Sn <= 1024;
   static const bool use_cluster = getenv("SPASM_B200_NO_CLUSTER") == nullptr;
-  static const bool use_block = use_cluster && getenv("SPASM_B200_NO_TILE_BLOCK") == nullptr;
   static bool attr = false;
   const size_t gsm = (size_t)(32 + PB) * 1024 * sizeof(unsigned short);
   if (fast && !attr) {
@@ -985,9 +798,7 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
   while (fast && h.npiv < Sn && h.c0 < Sm0 && h.low == 0) {
     for (int g = 0; g < 8; g++) {
       k_wtile<true><<<dim3(cdiv(Sn, 32), 4, WKS), 256, 0, s>>>(Dt + k0, ld, T, Sn, Sm0, ctl.p, cand, Wt.p, ldw, F);
-      if (use_block)
-        k_tile_block<<<GC, GRP, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
-      else if (use_cluster)
+      if (use_cluster)
         k_tile_gauss_cluster<<<GC, GRP, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
       else
         k_tile_gauss_smem<<<1, 1024, gsm, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
@@ -996,17 +807,6 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
     CK(cudaGetLastError());
     g_launches += 32;
     h = fetch(ctl.p);
-    if (h.pad[0] != 0) {
-      // a pivot may lie beyond the candidate block of k_tile_block: this one tile goes through the per-pivot kernel
-      CK(cudaMemsetAsync(&ctl.p->pad[0], 0, sizeof(int), s));
-      k_wtile<true><<<dim3(cdiv(Sn, 32), 4, WKS), 256, 0, s>>>(Dt + k0, ld, T, Sn, Sm0, ctl.p, cand, Wt.p, ldw, F);
-      k_tile_gauss_cluster<<<GC, GRP, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
-      apply_T();
-      CK(cudaGetLastError());
-      g_launches += 4;
-      g_tile_fallbacks++;
-      h = fetch(ctl.p);
-    }
   }
   // ---- sparse phase (few pivots per tile, or a prime / panel the fast path does not take): adaptive width
   int w = 32;
@@ -1332,8 +1132,8 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     for (auto &e_ : evs) cudaEventDestroy(e_.second);
   }
   if (prof)
-    fprintf(stderr, "[dense] rank %d/%d blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs trailing=%.3fs bcast=%.3fs\n", me, NR, (int)tp[5],
-            tp[0], tp[1], tp[2], tp[3], tp[4], tp[6]);
+    fprintf(stderr, "[dense] rank %d/%d blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs trailing=%.3fs bcast=%.3fs\n", me, NR,
+            (int)tp[5], tp[0], tp[1], tp[2], tp[3], tp[4], tp[6]);
 }
 
 }  // namespace sb

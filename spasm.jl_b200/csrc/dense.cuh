@@ -20,8 +20,9 @@ struct DenseSchur {
   DBuf<uint32_t> Vp;  // optional: multipliers Vp[i][k] of U row i (kept when asked), leading dimension ldv
   long long ldv = 0;
 };
+// work (optional, device): [0] += algorithmic bytes, [1] += multiply-adds of the row eliminations this stands for
 void build_dense_schur_raw(const long long *Ap, const int *Aj, const uint32_t *Ax, int m, const int *rows, int nrows, const DCsr &U,
-                           const int *Uqinv, const Fp &F, DenseSchur &D, bool keep_pivot_part);
+                           const int *Uqinv, const Fp &F, DenseSchur &D, bool keep_pivot_part, unsigned long long *work = nullptr);
 // columns of M (nvec vectors of length nrows, leading dimension ld) -> sorted sparse rows for the rows todo[off..off+nrows)
 void dense_rows_to_sparse(const uint32_t *M, long long ld, int nvec, const int *label, int nrows, const int *todo, int off, int *cnt,
                           unsigned long long *offs, unsigned long long slab_tag, DBuf<int> &oj, DBuf<uint32_t> &ox);

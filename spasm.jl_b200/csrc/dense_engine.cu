@@ -164,12 +164,34 @@ __global__ void __launch_bounds__(128) k_sptrsm_seq(const long long *__restrict_
   }
 }
 
+// algorithmic work of the eliminations this engine stands for (the oracle's count): every pivot i with a
+// non-zero multiplier on right-hand side k costs one use of U row i: 8 nnz(U_i) + 8 bytes, nnz(U_i) multiply-adds
+__global__ void __launch_bounds__(256) k_dense_work(const uint32_t *__restrict__ Vp, long long ldv, int r, int kc, const long long *__restrict__ Up,
+                                                     unsigned long long *__restrict__ work) {
+  __shared__ int red[8];
+  for (int i = blockIdx.x; i < r; i += gridDim.x) {
+    int c = 0;
+    for (int kk = threadIdx.x; kk < kc; kk += blockDim.x) c += Vp[(long long)i * ldv + kk] != 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; w++) tot += red[w];
+      const unsigned long long len = (unsigned long long)(Up[i + 1] - Up[i]);
+      if (tot) atomicAdd(&work[0], (unsigned long long)tot * (8ULL * len + 8ULL)), atomicAdd(&work[1], (unsigned long long)tot * len);
+    }
+    __syncthreads();
+  }
+}
+
 void build_dense_schur(const DCsr &A, const int *rows, int nrows, const DCsr &U, const int *Uqinv, const Fp &F, DenseSchur &D) {
   build_dense_schur_raw(A.p.p, A.j.p, A.x.p, A.m, rows, nrows, U, Uqinv, F, D, false);
 }
 
 void build_dense_schur_raw(const long long *Ap, const int *Aj, const uint32_t *Ax, int m_, const int *rows, int nrows, const DCsr &U,
-                           const int *Uqinv, const Fp &F, DenseSchur &D, bool keep_pivot_part) {
+                           const int *Uqinv, const Fp &F, DenseSchur &D, bool keep_pivot_part, unsigned long long *work) {
   cudaStream_t s = stream();
   const int m = m_, r = U.n;
   D.n_rem = nrows;
@@ -227,6 +249,7 @@ void build_dense_schur_raw(const long long *Ap, const int *Aj, const uint32_t *A
       else
         k_sptrsm_seq<false><<<cdiv(warps, 4), 128, 0, s>>>(Pp.p, prog.p, r, Vp.p, kc_max, kc, F);
       g_launches += 1;
+      if (work != nullptr) k_dense_work<<<std::min(r, sm_count() * 8), 256, 0, s>>>(Vp.p, kc_max, r, kc, U.p.p, work);
     }
     if (r > 0) {
       dim3 grid(D.Sm0, ktiles);

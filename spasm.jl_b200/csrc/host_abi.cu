@@ -8,6 +8,8 @@
 
 #include <cinttypes>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 extern "C" {
@@ -122,9 +124,26 @@ struct spasm_csr *spasm_csr_alloc(int n, int m, i64 nzmax, i64 prime, bool with_
   A->p[0] = 0;
   return A;
 }
+// arrays handed out by host_big_alloc (cache mode) keep their capacity; growing them moves to a malloc'ed array
+static void *regrow(void *old, i64 new_bytes, i64 keep_bytes) {
+  const size_t cap = sb::host_big_capacity(old);
+  if (cap == 0) return spasm_realloc(old, new_bytes);
+  if ((size_t)new_bytes <= cap) return old;
+  void *q = spasm_malloc(new_bytes);
+  memcpy(q, old, (size_t)std::min<i64>(keep_bytes, new_bytes));
+  sb::host_big_release(old);
+  return q;
+}
 void spasm_csr_realloc(struct spasm_csr *A, i64 nzmax) {
   if (nzmax < 0) nzmax = spasm_nnz(A);
   if (nzmax == A->nzmax) return;
+  if (sb::host_big_capacity(A->j) != 0 || (A->x && sb::host_big_capacity(A->x) != 0)) {
+    const i64 keep = std::min(nzmax, A->nzmax) * (i64)sizeof(int);
+    A->j = (int *)regrow(A->j, nzmax * (i64)sizeof(int), keep);
+    if (A->x) A->x = (spasm_ZZp *)regrow(A->x, nzmax * (i64)sizeof(spasm_ZZp), keep);
+    A->nzmax = nzmax;
+    return;
+  }
   A->j = (int *)spasm_realloc(A->j, nzmax * (i64)sizeof(int));
   if (A->x) A->x = (spasm_ZZp *)spasm_realloc(A->x, nzmax * (i64)sizeof(spasm_ZZp));
   A->nzmax = nzmax;
@@ -139,7 +158,10 @@ void spasm_csr_resize(struct spasm_csr *A, int n, int m) {
 }
 void spasm_csr_free(struct spasm_csr *A) {
   if (!A) return;
-  free(A->p), free(A->j), free(A->x), free(A);
+  free(A->p);
+  if (!sb::host_big_release(A->j)) free(A->j);
+  if (!sb::host_big_release(A->x)) free(A->x);
+  free(A);
 }
 struct spasm_triplet *spasm_triplet_alloc(int n, int m, i64 nzmax, i64 prime, bool with_values) {
   auto *T = (struct spasm_triplet *)spasm_malloc(sizeof(struct spasm_triplet));

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -78,6 +79,64 @@ ApiCall::ApiCall() {
 }
 ApiCall::~ApiCall() {
   if (--g_api_depth == 0 && !g_keep_cache) release_cached(POOL_KEEP_BYTES);
+}
+
+// ---- large HOST arrays of results, cache mode only.  A factor of tens of GB written into freshly mmap'ed pageable
+// memory costs seconds of page faults per call; when the host keeps the caches (spasm_b200_set_cache(1)) the big
+// result arrays are PINNED blocks that the library hands out and takes back in spasm_csr_free (the reference frees
+// every object through the library's own free functions, src/SpaSM.jl:148,275,451,463), so the device writes into
+// them directly and repeated calls touch no new page.  Without cache mode nothing changes: plain malloc'ed arrays.
+static std::mutex g_hb_mu;
+static std::vector<BigBlock> g_hb_live, g_hb_free;
+bool cache_enabled() { return g_keep_cache; }
+void *host_big_alloc(size_t bytes) {
+  if (!g_keep_cache || bytes < BIG) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_hb_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_hb_free.size(); i++)
+      if (g_hb_free[i].bytes >= bytes && g_hb_free[i].bytes <= bytes + bytes / 4 && (best < 0 || g_hb_free[i].bytes < g_hb_free[best].bytes)) best = i;
+    if (best >= 0) {
+      BigBlock b = g_hb_free[best];
+      g_hb_free.erase(g_hb_free.begin() + best);
+      g_hb_live.push_back(b);
+      return b.p;
+    }
+  }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;  // the caller falls back to malloc
+  }
+  std::lock_guard<std::mutex> lk(g_hb_mu);
+  g_hb_live.push_back({p, bytes});
+  return p;
+}
+size_t host_big_capacity(const void *p) {
+  std::lock_guard<std::mutex> lk(g_hb_mu);
+  for (auto &b : g_hb_live)
+    if (b.p == p) return b.bytes;
+  return 0;
+}
+// true when p was one of ours (it goes back to the cache; no CUDA call: safe from a finalizer thread)
+bool host_big_release(void *p) {
+  if (p == nullptr) return false;
+  std::lock_guard<std::mutex> lk(g_hb_mu);
+  for (size_t i = 0; i < g_hb_live.size(); i++)
+    if (g_hb_live[i].p == p) {
+      g_hb_free.push_back(g_hb_live[i]);
+      g_hb_live.erase(g_hb_live.begin() + i);
+      return true;
+    }
+  return false;
+}
+static void host_big_trim() {
+  std::vector<BigBlock> blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_hb_mu);
+    blocks.swap(g_hb_free);
+  }
+  for (auto &b : blocks) cudaFreeHost(b.p);
 }
 
 void *dmalloc_bytes(size_t bytes) {
@@ -389,12 +448,15 @@ void transpose_csr(const DCsr &A, DCsr &T) {
 }  // namespace sb
 
 // give the cached large device blocks back to the driver
-extern "C" void spasm_b200_trim(void) { sb::release_cached(0); }
+extern "C" void spasm_b200_trim(void) {
+  sb::release_cached(0);
+  sb::host_big_trim();
+}
 // keep != 0: device blocks stay cached between calls (same-shaped calls in a loop allocate nothing);
 // keep == 0 (default): everything is returned to the driver when an entry point returns
 extern "C" void spasm_b200_set_cache(int keep) {
   sb::g_keep_cache = keep != 0;
-  if (!keep) sb::release_cached(0);
+  if (!keep) sb::release_cached(0), sb::host_big_trim();
 }
 // bytes of device memory this process still holds in the library's caches (0 after a trim)
 extern "C" long long spasm_b200_cached_bytes(void) {

@@ -18,6 +18,7 @@ struct Job {
   const char *src;
   size_t bytes;
   cudaEvent_t ready;
+  bool direct;  // dst is pinned: one device -> host copy, no bounce buffer
 };
 
 struct HostSink::Impl {
@@ -47,6 +48,11 @@ struct HostSink::Impl {
         jobs.pop_front();
       }
       bool ok = cudaStreamWaitEvent(cs, j.ready, 0) == cudaSuccess;
+      if (j.direct) {
+        ok = ok && cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, cs) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(cs) == cudaSuccess;
+        j.bytes = 0;
+      }
       const size_t nch = (j.bytes + CH - 1) / CH;
       auto issue = [&](size_t c) {
         size_t off = c * CH, len = std::min(CH, j.bytes - off);
@@ -121,8 +127,8 @@ HostSink::~HostSink() {
     g_pin_busy = false;
   }
   cudaStreamDestroy(impl->cs);
-  free(hj);
-  free(hx);
+  if (!host_big_release(hj)) free(hj);
+  if (!host_big_release(hx)) free(hx);
   delete impl;
 }
 
@@ -136,8 +142,28 @@ void HostSink::ensure(long long entries) {
   if (entries <= cap) return;
   wait_all();  // nobody may be writing into the old arrays
   long long ncap = entries + entries / 8 + 1024;
-  hj = (int *)spasm_realloc(hj, ncap * (i64)sizeof(int));
-  hx = (int *)spasm_realloc(hx, ncap * (i64)sizeof(int));
+  int *nj = (int *)host_big_alloc((size_t)ncap * sizeof(int)), *nx = nullptr;
+  if (nj != nullptr) nx = (int *)host_big_alloc((size_t)ncap * sizeof(int));
+  if (nj != nullptr && nx != nullptr) {
+    // cache mode: pinned blocks (the device writes into them directly; they return to the cache in spasm_csr_free)
+    if (submitted > 0) memcpy(nj, hj, (size_t)submitted * sizeof(int)), memcpy(nx, hx, (size_t)submitted * sizeof(int));
+    if (!host_big_release(hj)) free(hj);
+    if (!host_big_release(hx)) free(hx);
+    hj = nj, hx = nx;
+    pinned = true;
+  } else {
+    if (nj != nullptr) host_big_release(nj);
+    if (pinned) {  // (cannot happen in practice: a pinned pair that has to grow while pinned memory ran out)
+      int *mj = (int *)spasm_malloc(ncap * (i64)sizeof(int)), *mx = (int *)spasm_malloc(ncap * (i64)sizeof(int));
+      memcpy(mj, hj, (size_t)submitted * sizeof(int)), memcpy(mx, hx, (size_t)submitted * sizeof(int));
+      host_big_release(hj), host_big_release(hx);
+      hj = mj, hx = mx;
+      pinned = false;
+    } else {
+      hj = (int *)spasm_realloc(hj, ncap * (i64)sizeof(int));
+      hx = (int *)spasm_realloc(hx, ncap * (i64)sizeof(int));
+    }
+  }
   cap = ncap;
 }
 
@@ -153,6 +179,7 @@ void HostSink::submit(const int *dev_j, const int *dev_x, long long first, long 
     CK(cudaEventCreateWithFlags(&j.ready, cudaEventDisableTiming));
     CK(cudaEventRecord(j.ready, stream()));
     j.dst = (char *)dsts[a], j.src = (const char *)srcs[a], j.bytes = (size_t)count * 4;
+    j.direct = pinned;
     {
       std::lock_guard<std::mutex> lk(impl->mu);
       impl->jobs.push_back(j);

@@ -10,6 +10,7 @@ struct HostSink {
   int *hj = nullptr, *hx = nullptr;  // host arrays being filled (malloc family)
   long long cap = 0;                 // their capacity in entries
   long long submitted = 0;           // entries [0, submitted) are on their way / done
+  bool pinned = false;               // hj / hx are pinned blocks of the host cache (cache mode): direct device -> host copies
   HostSink();
   ~HostSink();
   HostSink(const HostSink &) = delete;

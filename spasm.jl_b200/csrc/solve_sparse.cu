@@ -350,11 +350,13 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T) k_solve_smem(KArgs a) {
     if (tid == 0) {
       a.cnt[k] = nout + npre;
       if (a.want_L) a.lcnt[k] = nl;
-      atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
-      atomicAdd(&a.stats[1], macs);
     }
     if (a.count_only) {
-      if (tid == 0) a.status[k] = ST_OK;
+      if (tid == 0) {
+        a.status[k] = ST_OK;
+        atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
+        atomicAdd(&a.stats[1], macs);
+      }
       Grp<T>::sync();
       continue;
     }
@@ -396,6 +398,9 @@ __global__ void __launch_bounds__(T == 32 ? 256 : T) k_solve_smem(KArgs a) {
         atomicAdd(&a.stats[3], 1ULL);
         atomicAdd(&a.stats[4], (unsigned long long)(nout + npre));
         atomicAdd(&a.stats[5], (unsigned long long)nl);
+      } else {  // the work is counted once, by the attempt whose output is kept
+        atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
+        atomicAdd(&a.stats[1], macs);
       }
       a.status[k] = st;
       a.off[k] = (a.slab_id << 56) | o;
@@ -525,8 +530,6 @@ __global__ void __launch_bounds__(T) k_solve_heavy(KArgs a, const int *__restric
     if (tid == 0) {
       a.cnt[k] = nout + npre;
       if (a.want_L) a.lcnt[k] = nl;
-      atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
-      atomicAdd(&a.stats[1], macs);
       if (!a.count_only) {
         o = atomicAdd(a.cursor, (unsigned long long)(nout + npre));
         if (o + nout + npre > a.cap) st = ST_SLAB;
@@ -541,6 +544,10 @@ __global__ void __launch_bounds__(T) k_solve_heavy(KArgs a, const int *__restric
         }
         a.off[k] = (a.slab_id << 56) | o;
         if (a.want_L) a.loff[k] = (a.slab_id << 56) | lo_;
+      }
+      if (st == ST_OK) {  // the work is counted once, by the attempt whose output is kept
+        atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
+        atomicAdd(&a.stats[1], macs);
       }
       a.status[k] = st;
     }
@@ -794,8 +801,6 @@ __global__ void __launch_bounds__(128) k_solve_global(KArgs a) {
     if (lane == 0) {
       a.cnt[k] = nout + npre;
       if (a.want_L) a.lcnt[k] = nl;
-      atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
-      atomicAdd(&a.stats[1], macs);
       if (!a.count_only) {
         o = atomicAdd(a.cursor, (unsigned long long)(nout + npre));
         if (o + nout + npre > a.cap) st = ST_SLAB;
@@ -810,6 +815,10 @@ __global__ void __launch_bounds__(128) k_solve_global(KArgs a) {
         }
         a.off[k] = (a.slab_id << 56) | o;
         if (a.want_L) a.loff[k] = (a.slab_id << 56) | lo_;
+      }
+      if (st == ST_OK) {  // the work is counted once, by the attempt whose output is kept
+        atomicAdd(&a.stats[0], bytes + 8ULL * nout + 8ULL);
+        atomicAdd(&a.stats[1], macs);
       }
       a.status[k] = st;
     }
@@ -1002,6 +1011,18 @@ __global__ void k_gather_rows(const int *__restrict__ cnt, const unsigned long l
     ox[d + i] = sx[o + i];
   }
 }
+__global__ void k_rows_io_bytes(const long long *__restrict__ Bp, const int *__restrict__ rows_sel, const int *__restrict__ todo, int off, int nr,
+                                const int *__restrict__ cnt, unsigned long long *__restrict__ work) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long b = 0;
+  if (i < nr) {
+    const int row = rows_sel[i];
+    b = 8ULL * (unsigned long long)(Bp[row + 1] - Bp[row]) + 8ULL + 8ULL * (unsigned long long)cnt[todo[off + i]] + 8ULL;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&work[0], b);
+}
 __global__ void k_prio2col(const PDesc *__restrict__ pdesc, int width, int *__restrict__ prio2col) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < width && pdesc[c].len >= 0) prio2col[pdesc[c].prio] = c;
@@ -1094,6 +1115,13 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
   // one kernel stage over the current todo list, with exact-slab retries; returns with status[] final for the stage
   auto run_stage = [&](Stage stage, long long budget) {
     long long need = guess, lneed = guess;
+    if (stage == GLOBAL && !E.count_only) {
+      // a row that does not fit the slab is eliminated AGAIN with an exact slab: rows of this stage are the expensive ones,
+      // so give the first attempt room for the average case seen so far times a safety factor, within a quarter of the free memory
+      const long long cap_entries = (long long)(dev_free_bytes() / 4 / 8);
+      need = std::min(std::max<long long>(guess, 16384LL * ntodo), std::max<long long>(cap_entries, guess));
+      lneed = need;
+    }
     for (int attempt = 0; attempt < 4 && ntodo > 0; attempt++) {
       unsigned long long h_ctrs[8];
       if (!E.count_only) {
@@ -1240,7 +1268,7 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
     for (int off2 = 0; off2 < ntodo; off2 += (int)ch) {
       const int nr = (int)std::min<long long>(ch, ntodo - off2);
       DenseSchur D;
-      build_dense_schur_raw(B.Bp, B.Bj, B.Bx, G.width, rows_sel.p + off2, nr, U, G.qinv_dense, F, D, E.want_L);
+      build_dense_schur_raw(B.Bp, B.Bj, B.Bx, G.width, rows_sel.p + off2, nr, U, G.qinv_dense, F, D, E.want_L, ctrs.p);
       if (E.count_only) {
         DBuf<int> oj0;
         DBuf<uint32_t> ox0;
@@ -1258,8 +1286,10 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
           LSP.j[sid] = slabs_lj.back().p, LSP.x[sid] = slabs_lx.back().p;
         }
       }
+      // input and output rows of these eliminations: 8 nnz(A_k) + 8 and 8 nnz(S_k) + 8 bytes
+      k_rows_io_bytes<<<cdiv(nr, 256), 256, 0, stream()>>>(B.Bp, rows_sel.p + off2, todo, off2, nr, R.cnt.p, ctrs.p);
       R.stats.heavy += nr;
-      g_launches += 8;
+      g_launches += 9;
     }
     ntodo = 0;
   };

@@ -73,6 +73,14 @@ def test_schur_and_density(pkg, gpu, oracle, case):
         S = pkg.CSR(api, api.lib.spasm_schur(A.data, pp, nrest, C.byref(lu), 0.0, None, None, pout.ctypes.data_as(C.POINTER(C.c_int32))))
         outs.append((S.arrays(), pout[:nrest].copy(), S.shape))
     (so, po, sho), (sg, pg, shg) = outs
+    # the algorithmic work behind the Schur GB/s figure: the kernels' own count (whichever stage solved a
+    # row: shared-memory tier, global tier or the SpTRSM engine) equals the oracle's, byte for byte
+    Ls = (C.c_longlong * 7)()
+    gpu.lib.spasm_b200_last_stats.argtypes = [C.POINTER(C.c_longlong)]
+    gpu.lib.spasm_b200_last_stats(Ls)
+    ob = C.c_int64.in_dll(oracle.lib, "spasm_b200_last_bytes").value
+    om = C.c_int64.in_dll(oracle.lib, "spasm_b200_last_macs").value
+    assert (Ls[0], Ls[1]) == (ob, om), f"work counters: gpu {Ls[0]} B / {Ls[1]} MACs, oracle {ob} B / {om} MACs"
     assert sho == shg == (nrest, m)
     assert np.array_equal(po, pg)
     for a, b, name in zip(so, sg, "pjx"):
