@@ -370,9 +370,11 @@ def run_ours(args):
         "kernel": "k_gemm_i8limb (tcgen05.mma.kind::i8, SASS UTCIMMA; TMA-fed, TMEM accumulators)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if achieved else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture (profiles/), see traffic_note
-        "traffic": 5.429282e9 + 2.143989e9,
-        "traffic_note": "ncu capture of the kernel alone at M=32768 N=16384 K=4096: 7.57e9 B of DRAM traffic vs 4.70e9 B algorithmic (x1.6); "
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
+        # profiles/r02_ncu_gemm_i8limb_k4096.csv (M=32768 N=16384 K=4096, the depth of the deferred trailing updates)
+        "traffic": 4.938201e9 + 2.137045e9,
+        "traffic_note": "ncu capture of the kernel alone at M=32768 N=16384 K=4096 (tools/gemm_probe.py): 7.08e9 B of DRAM traffic for "
+                        "4.70e9 B algorithmic (4.29e9 B of C read + written, 0.40e9 B of u8 limb planes): x1.5; 6.57 ms, tensor pipe 55 % active; "
                         "the bench's launches have other M and N",
         "peak_source": peak_source,
         "proxy_2x_bf16_sustained": 2.0 * bf16_sust,
