@@ -1199,6 +1199,15 @@ static void echelonize_GPLU(const struct spasm_csr *A, const int *p, int n, cons
 /* dense tail (prototypes src/SpaSM.jl:765-766, :805): blocks of dense_block_size
  * rows are eliminated against U, gathered on the non-pivotal columns, put in RREF; the reduced
  * rows are appended to U as (pivot col, 1) then the non-pivot part in increasing column order. */
+static void echelonize_dense_lowrank(const struct spasm_csr *A, const int *p, int n, struct spasm_lu *fact, struct echelonize_opts *opts);
+
+/* SURVEY.md A.7 (prototype spasm_schur_dense_randomized, src/SpaSM.jl:767-769): a dense block whose rank is below
+ * low_rank_ratio times its row count says that the rows still to come are mostly dependent — the dense loop hands them
+ * to the low-rank mode (random combinations of ALL remaining rows) instead of eliminating them block by block. */
+static int dense_switch_to_lowrank(const struct echelonize_opts *opts, int rr, int Sn, int rows_left, int cols_left) {
+  return opts->enable_tall_and_skinny && rows_left > 0 && cols_left > 0 && (double)rr < opts->low_rank_ratio * (double)Sn;
+}
+
 static void echelonize_dense_rowwise(const struct spasm_csr *A, const int *p, int n, const int *p_in, struct spasm_lu *fact,
                              struct echelonize_opts *opts) {
   (void)p_in;
@@ -1263,6 +1272,11 @@ static void echelonize_dense_rowwise(const struct spasm_csr *A, const int *p, in
     free(pivcol);
     processed += Sn;
     logprintf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U->n);
+    if (dense_switch_to_lowrank(opts, rr, Sn, n - processed, m - U->n)) {
+      logprintf("[echelonize/dense] %d pivots in a block of %d rows: switching to low-rank mode\n", rr, Sn);
+      echelonize_dense_lowrank(A, p + processed, n - processed, fact, opts);
+      break;
+    }
   }
   free(x);
   free(xj);
@@ -1497,6 +1511,15 @@ static void echelonize_dense(const struct spasm_csr *A, const int *p, int n, con
       U->p[U->n] = unz;
     }
     processed += Sn;
+    if (dense_switch_to_lowrank(opts, rr, Sn, n - processed, m - U->n)) {
+      /* the low-rank mode eliminates its combinations against U itself: the rows of D are not needed any more */
+      logprintf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U->n);
+      logprintf("[echelonize/dense] %d pivots in a block of %d rows: switching to low-rank mode\n", rr, Sn);
+      free(D);
+      D = NULL;
+      echelonize_dense_lowrank(A, p + processed, n - processed, fact, opts);
+      break;
+    }
     t0 = spasm_wtime();
     if (U->n < m) dense_trailing_update(D + (i64)processed * Sm0, n - processed, Sm0, Sm0, S, Sm0, pivcol, rr, A->field);
     t_upd += spasm_wtime() - t0;

@@ -207,10 +207,20 @@ __global__ void k_write_rows(const uint32_t *__restrict__ S, long long ld, int m
   }
 }
 
-void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);
+void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
+                     const TailOpts &opts);
+// how the rows of the low-rank mode are spread when the dense loop switches to it on several ranks
+struct LowRankShard {
+  const int *gidx = nullptr;         // device: global index (in the remaining-row list) of local row i; nullptr = identity
+  const int *loc_of_glob = nullptr;  // device: local row of global row k, -1 when another rank holds it; nullptr = identity
+  bool reduce = false;               // a combined block is the sum (mod p) of the ranks' parts
+  long long panel_base = 0;          // panel counter for the who-materialises rule of the sharded factor
+};
+void lowrank_core(DenseSchur &D, long long row0, int nloc, int nglob, const LowRankShard &sh, unsigned char *colpiv, DCsr &U,
+                  DBuf<int> &Uqinv, const Fp &F, int block_size, double start_weight, int m_total);
 // counters of the deferred trailing updates since the last reset (tests assert that the far-row path ran):
 // [0] far flushes with far rows  [1] multiplier-correction GEMMs  [2] far rows x depth flushed  [3] near updates
-long long g_tail_stats[4] = {0, 0, 0, 0};
+long long g_tail_stats[5] = {0, 0, 0, 0, 0};
 
 void make_free_columns(const int *qinv, int m, int *flag, long long *pos, int *q, int *qpos) {
   cudaStream_t s = stream();
@@ -861,7 +871,8 @@ __global__ void k_register_pivots_only(const int *__restrict__ pivcol, const int
 // complement; the owner of panel b factors it and broadcasts the reduced rows R_b (NCCL over
 // NVLink); every rank then updates its own later rows with the tensor-core GEMM.  Rank 0
 // materialises the rows of U; the other ranks only track the pivots.
-void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size) {
+void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
+                             const TailOpts &opts) {
   cudaStream_t s = stream();
   if (block_size <= 0) block_size = 1000;
   if (nrows == 0 || A.m == U.n) return;
@@ -889,11 +900,12 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
   build_dense_schur(A, my_rows, n_local, U, Uqinv.p, F, D);
   logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)%s\n", nrows, D.Sm0, spasm_wtime() - t0, D.levels,
        NR > 1 ? " [sharded]" : "");
-  dense_tail_core(D, nrows, n_local, A.m, U, Uqinv, F, block_size);
+  dense_tail_core(D, nrows, n_local, A.m, U, Uqinv, F, block_size, opts);
 }
 
 // the blocked elimination itself, on a dense Schur complement that is already in HBM (D holds MY rows)
-void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size) {
+void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
+                     const TailOpts &opts) {
   cudaStream_t s = stream();
   const Dist &dd = dist();
   const int me = dd.rank, NR = dd.nranks;
@@ -1119,6 +1131,32 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     }
     logf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U.n);
     if (U.n == m_total) break;
+    // ---- a block far below full rank hands the rows still to come to the low-rank mode
+    const long long rows_left = (long long)nrows - (kg + Sn);
+    if (opts.tall_skinny && rows_left > 0 && (double)rr < opts.low_rank_ratio * (double)Sn) {
+      logf("[echelonize/dense] %d pivots in a block of %d rows: switching to low-rank mode\n", rr, Sn);
+      if (lazy) flush_far();  // every remaining row up to date
+      const long long kb = lb * block_size;  // my remaining rows are [kb, n_local)
+      const int nloc = (int)std::max<long long>(0, n_local - kb);
+      LowRankShard sh;
+      DBuf<int> gidx, locg;
+      if (NR > 1) {
+        // global index (among the rows_left remaining rows) of my local rows, and the inverse map
+        std::vector<int> pos = local_positions(nrows, block_size, NR, me), g(std::max(nloc, 1)), inv((size_t)rows_left, -1);
+        for (int i = 0; i < nloc; i++) {
+          g[i] = (int)(pos[kb + i] - (kg + Sn));
+          inv[g[i]] = i;
+        }
+        gidx.alloc(std::max(nloc, 1)), locg.alloc((size_t)rows_left);
+        if (nloc) gidx.upload(g.data(), nloc);
+        locg.upload(inv.data(), (size_t)rows_left);
+        sync();
+        sh.gidx = gidx.p, sh.loc_of_glob = locg.p, sh.reduce = true, sh.panel_base = b + 1;
+      }
+      g_tail_stats[4] += 1;
+      lowrank_core(D, kb, nloc, (int)rows_left, sh, colpiv.p, U, Uqinv, F, block_size, opts.start_weight, m_total);
+      break;
+    }
   }
   if (prof_ev) {
     sync();
@@ -1155,18 +1193,24 @@ __host__ __device__ inline unsigned long long lowrank_hash(unsigned long long bl
   z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
   return z ^ (z >> 31);
 }
-__global__ void k_coef_full(uint32_t *__restrict__ coef, long long ldc, int B, int n, unsigned long long blk, uint32_t p, int negate) {
+// gidx (optional): global index, in the remaining-row list, of local row k (rows spread over several ranks)
+__global__ void k_coef_full(uint32_t *__restrict__ coef, long long ldc, int B, int n, unsigned long long blk, uint32_t p, int negate,
+                            const int *__restrict__ gidx) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
   if (k >= n || t >= B) return;
-  uint32_t c = (uint32_t)(lowrank_hash(blk, t, k) % p);
+  uint32_t c = (uint32_t)(lowrank_hash(blk, t, (unsigned long long)(gidx ? gidx[k] : k)) % p);
   coef[(long long)t * ldc + k] = (negate && c) ? p - c : c;
 }
-__global__ void k_coef_sparse(uint32_t *__restrict__ coef, long long ldc, int B, int n, int w, unsigned long long blk, Fp F) {
+// n = number of remaining rows over all ranks; loc_of_glob (optional): local row of global row k, -1 = another rank's
+__global__ void k_coef_sparse(uint32_t *__restrict__ coef, long long ldc, int B, int n, int w, unsigned long long blk, Fp F,
+                              const int *__restrict__ loc_of_glob) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;  // one combination per thread: its w terms may collide
   if (t >= B) return;
   for (int s = 0; s < w; s++) {
-    const int k = (int)(lowrank_hash(blk, t, 2ULL * s) % (unsigned long long)n);
+    int k = (int)(lowrank_hash(blk, t, 2ULL * s) % (unsigned long long)n);
     const uint32_t c = (uint32_t)(1 + lowrank_hash(blk, t, 2ULL * s + 1) % (unsigned long long)(F.p - 1));
+    if (loc_of_glob) k = loc_of_glob[k];
+    if (k < 0) continue;
     uint32_t *q = coef + (long long)t * ldc + k;
     *q = addmod(*q, c, F);
   }
@@ -1177,79 +1221,116 @@ __global__ void k_negate_rows(uint32_t *a, long long ld, int cols, uint32_t p) {
   uint32_t *q = a + (long long)blockIdx.y * ld + k;
   if (*q) *q = p - *q;
 }
+__global__ void k_widen_u64(const uint32_t *__restrict__ in, unsigned long long *__restrict__ out, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void k_narrow_mod(const unsigned long long *__restrict__ in, uint32_t *__restrict__ out, long long n, unsigned long long p) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)(in[i] % p);
+}
 
-void echelonize_lowrank_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
-                               double start_weight) {
+// The loop of the low-rank mode on rows [row0, row0 + nloc) of a dense Schur complement that is up to date with
+// respect to U (dead columns flagged in colpiv and zero on these rows).  nglob = remaining rows over all ranks.
+void lowrank_core(DenseSchur &D, long long row0, int nloc, int nglob, const LowRankShard &sh, unsigned char *colpiv, DCsr &U,
+                  DBuf<int> &Uqinv, const Fp &F, int block_size, double start_weight, int m_total) {
   cudaStream_t s = stream();
   if (block_size <= 0) block_size = 1000;
-  if (nrows == 0 || A.m == U.n) return;
+  if (nglob == 0 || m_total == U.n) return;
+  const Dist &dd = dist();
   const int B = block_size;
-  int w = (start_weight >= 1) ? (int)start_weight : nrows;
-  if (w > nrows) w = nrows;
-  DenseSchur D;
-  build_dense_schur(A, rows, nrows, U, Uqinv.p, F, D);  // every rank holds all rows: no exchange in this mode
+  int w = (start_weight >= 1) ? (int)start_weight : nglob;
+  if (w > nglob) w = nglob;
   const int Sm0 = D.Sm0;
   const long long ld = D.ld;
-  logf("[echelonize/low-rank] %d rows, %d columns left, block size %d, starting weight %d\n", nrows, Sm0, B, w);
+  logf("[echelonize/low-rank] %d rows, %d columns left, block size %d, starting weight %d\n", nglob, m_total - U.n, B, w);
   const long long ldb = ((long long)B + 63) / 64 * 64;
-  DBuf<uint32_t> Coef((size_t)B * ld), Blk((size_t)Sm0 * ldb), T((size_t)B * B), Tsel((size_t)B * B), R((size_t)B * Sm0), Rt, Pt;
+  const long long ldc = ((long long)std::max(nloc, 1) + 63) / 64 * 64;
+  DBuf<uint32_t> Coef((size_t)B * ldc), Blk((size_t)Sm0 * ldb), T((size_t)B * B), Tsel((size_t)B * B), R((size_t)B * Sm0), Rt, Pt;
+  DBuf<unsigned long long> wide;
   DBuf<int> ispiv, pivrow, pc_tmp, ident(B), cflag(Sm0 + 1), cand(std::max(Sm0, 1));
   DBuf<long long> cpos(Sm0 + 1);
-  DBuf<unsigned char> colpiv(std::max(Sm0, 1));
-  colpiv.zero();
   k_iota2<<<cdiv(B, 256), 256, 0, s>>>(ident.p, B);
   const int KCH = gemm_max_k(F);  // depth one tensor-core launch takes (int32 accumulator bound of the limb kernel)
   for (unsigned long long blk = 0;; blk++) {
-    if (U.n == A.m) break;
+    if (U.n == m_total) break;
     // ---- coefficients and the combined block  Blk[c][t] = sum_k Dt[c][k] * Coef[t][k]
-    if (w >= nrows) {
-      k_coef_full<<<dim3(cdiv(nrows, 256), B), 256, 0, s>>>(Coef.p, ld, B, nrows, blk, F.p, 0);
-    } else {
-      Coef.zero();
-      k_coef_sparse<<<cdiv(B, 128), 128, 0, s>>>(Coef.p, ld, B, nrows, w, blk, F);
-    }
-    for (int kc = 0; kc < nrows; kc += KCH) {
-      const int kk = std::min(KCH, nrows - kc);
-      if (kc > 0) {  // C += A.B as C -= A.(-B)
-        k_negate_rows<<<dim3(cdiv(kk, 256), B), 256, 0, s>>>(Coef.p + kc, ld, kk, F.p);
+    if (nloc > 0) {
+      if (w >= nglob) {
+        k_coef_full<<<dim3(cdiv(nloc, 256), B), 256, 0, s>>>(Coef.p, ldc, B, nloc, blk, F.p, 0, sh.gidx);
+      } else {
+        Coef.zero();
+        k_coef_sparse<<<cdiv(B, 128), 128, 0, s>>>(Coef.p, ldc, B, nglob, w, blk, F, sh.loc_of_glob);
       }
-      gemm_nt(Blk.p, ldb, Sm0, B, D.Dt.p + kc, ld, Coef.p + kc, ld, kk, kc > 0, F);
+      for (int kc = 0; kc < nloc; kc += KCH) {
+        const int kk = std::min(KCH, nloc - kc);
+        if (kc > 0) {  // C += A.B as C -= A.(-B)
+          k_negate_rows<<<dim3(cdiv(kk, 256), B), 256, 0, s>>>(Coef.p + kc, ldc, kk, F.p);
+        }
+        gemm_nt(Blk.p, ldb, Sm0, B, D.Dt.p + row0 + kc, ld, Coef.p + kc, ldc, kk, kc > 0, F);
+      }
+    } else
+      Blk.zero();
+    if (sh.reduce && dd.nranks > 1) {  // my rows' part of every combination -> the combination
+      const long long cnt = (long long)Sm0 * ldb;
+      wide.alloc((size_t)cnt);
+      k_widen_u64<<<cdiv(cnt, 256), 256, 0, s>>>(Blk.p, wide.p, cnt);
+      dist_allreduce_sum_u64(wide.p, (size_t)cnt);
+      k_narrow_mod<<<cdiv(cnt, 256), 256, 0, s>>>(wide.p, Blk.p, cnt, (unsigned long long)F.p);
     }
     // ---- factor the block like a panel
-    k_not_flag<<<cdiv(Sm0 + 1, 256), 256, 0, s>>>(colpiv.p, Sm0, cflag.p);
+    k_not_flag<<<cdiv(Sm0 + 1, 256), 256, 0, s>>>(colpiv, Sm0, cflag.p);
     exclusive_scan_i32_to_i64(cflag.p, cpos.p, Sm0 + 1);
     k_compact_flags_i32(cflag.p, cpos.p, Sm0, cand.p);
     const int ncand = (int)fetch(cpos.p + Sm0);
     const int rr = panel_factor(Blk.p, ldb, cand.p, ncand, 0, B, T.p, ispiv, pivrow, pc_tmp, F);
     if (rr == 0) {
-      if (w >= nrows) break;
-      w = (2 * w < nrows) ? 2 * w : nrows;
+      if (w >= nglob) break;
+      w = (2 * w < nglob) ? 2 * w : nglob;
       continue;
     }
     k_gather_T_rows<<<dim3(cdiv(B, 256), rr), 256, 0, s>>>(T.p, B, pivrow.p, nullptr, rr, Tsel.p);
     gemm_nt(R.p, Sm0, rr, Sm0, Tsel.p, B, Blk.p, ldb, B, false, F);
-    k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pc_tmp.p, rr, colpiv.p);
-    {
+    k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pc_tmp.p, rr, colpiv);
+    // who materialises these rows: everybody when every rank holds all rows, else as the dense panels do
+    const bool emit = !sh.reduce || dd.nranks == 1 || (dd.shard_factor ? panel_owner(sh.panel_base + (long long)blk, dd.nranks) == dd.rank : dd.rank == 0);
+    if (emit) {
       DBuf<int> cnt(rr + 1);
       DBuf<long long> rpos(rr + 1);
       k_count_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, rr, cnt.p);
       exclusive_scan_i32_to_i64(cnt.p, rpos.p, rr + 1);
       const long long add = fetch(rpos.p + rr);
+      if (g_sink && (size_t)(U.nnz + add) > U.j.n) g_sink->wait_all();  // the arrays are about to move
       csr_reserve(U, U.nnz + add, U.n + rr);
       k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pc_tmp.p, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
       CK(cudaGetLastError());
       U.nnz += add;
-      U.n += rr;
+    } else {
+      csr_reserve(U, U.nnz, U.n + rr);
+      k_register_pivots_only<<<cdiv(rr, 256), 256, 0, s>>>(pc_tmp.p, D.q0.p, rr, U.n, U.nnz, U.p.p, Uqinv.p);
     }
+    U.n += rr;
     // ---- trailing update of EVERY row:  Dt[c][k] -= sum_s R[s][c] * Dt[pivcol[s]][k]
-    const long long ldk = ((long long)rr + 15) / 16 * 16;
-    Rt.alloc((size_t)Sm0 * ldk);
-    Pt.alloc((size_t)nrows * ldk);
-    k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
-    k_gather_pivot_cols_T<<<dim3(cdiv(nrows, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pc_tmp.p, rr, 0, nrows, Pt.p, ldk);
-    gemm_nt(D.Dt.p, ld, Sm0, nrows, Rt.p, ldk, Pt.p, ldk, rr, true, F);
+    if (nloc > 0) {
+      const long long ldk = ((long long)rr + 15) / 16 * 16;
+      Rt.alloc((size_t)Sm0 * ldk);
+      Pt.alloc((size_t)nloc * ldk);
+      k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
+      k_gather_pivot_cols_T<<<dim3(cdiv(nloc, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pc_tmp.p, rr, row0, nloc, Pt.p, ldk);
+      gemm_nt(D.Dt.p + row0, ld, Sm0, nloc, Rt.p, ldk, Pt.p, ldk, rr, true, F);
+    }
     logf("[echelonize/low-rank] block %d: %d new pivots (weight %d), rank %d\n", (int)blk, rr, w, U.n);
   }
+}
+
+void echelonize_lowrank_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
+                               double start_weight) {
+  if (nrows == 0 || A.m == U.n) return;
+  DenseSchur D;
+  build_dense_schur(A, rows, nrows, U, Uqinv.p, F, D);  // every rank holds all rows: no exchange in this mode
+  DBuf<unsigned char> colpiv(std::max(D.Sm0, 1));
+  colpiv.zero();
+  lowrank_core(D, 0, nrows, nrows, LowRankShard(), colpiv.p, U, Uqinv, F, block_size, start_weight, A.m);
 }
 
 __global__ void k_fill_random(uint32_t *__restrict__ a, long long n, uint32_t p, unsigned long long seed) {
@@ -1307,7 +1388,7 @@ static int dense_tail_bench_impl(long long prime, int n, int m, int planted_rank
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, stream()));
-    dense_tail_core(D, n, n, m, U, Uqinv, F, block_size);
+    dense_tail_core(D, n, n, m, U, Uqinv, F, block_size, TailOpts());
     CK(cudaEventRecord(e1, stream()));
     CK(cudaEventSynchronize(e1));
     float t = 0;
@@ -1325,6 +1406,12 @@ extern "C" void spasm_b200_tail_stats(long long *out, int reset) {
   for (int i = 0; i < 4; i++) out[i] = sb::g_tail_stats[i];
   if (reset)
     for (int i = 0; i < 4; i++) sb::g_tail_stats[i] = 0;
+}
+// how often the dense loop switched to the low-rank mode since the last reset
+extern "C" long long spasm_b200_lowrank_switches(int reset) {
+  const long long v = sb::g_tail_stats[4];
+  if (reset) sb::g_tail_stats[4] = 0;
+  return v;
 }
 
 // the dense-tail entry point of the ABI (replaces spasm_ffpack_rref, src/SpaSM.jl:805)

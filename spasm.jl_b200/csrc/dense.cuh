@@ -36,8 +36,16 @@ void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long l
 // largest K one tcgen05 launch takes for this prime (int32 accumulator bound of the 2 / 3 / 4 limb kernels)
 int gemm_max_k(const Fp &F);
 
+// the knobs of EchelonizeOpts (src/SpaSM.jl:325-343) the dense loop looks at: a block of Sn rows that yields fewer than
+// low_rank_ratio * Sn pivots hands the remaining rows to the low-rank mode
+struct TailOpts {
+  bool tall_skinny = false;
+  double low_rank_ratio = 0.5;
+  double start_weight = -1;
+};
 // eliminate the rows `rows` of A against U block by block, RREF each block, append to U
-void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size);
+void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
+                             const TailOpts &opts = TailOpts());
 // low-rank / tall-and-skinny mode: blocks of random combinations of ALL remaining rows
 void echelonize_lowrank_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
                                double start_weight);

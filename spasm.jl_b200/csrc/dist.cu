@@ -14,6 +14,8 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -25,9 +27,11 @@ static NcclApi &nccl() {
     api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
     api.Broadcast = (decltype(api.Broadcast))dlsym(api.h, "ncclBroadcast");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+    api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.CommDestroy) throw Error("libnccl.so.2 lacks the expected symbols");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.AllReduce || !api.AllGather || !api.CommDestroy) throw Error("libnccl.so.2 lacks the expected symbols");
   }
   return api;
 }
@@ -45,6 +49,23 @@ void dist_broadcast(void *dev_buf, size_t bytes, int root) {
     size_t len = std::min(CH, bytes - off);
     NCK(nccl().Broadcast((char *)dev_buf + off, (char *)dev_buf + off, len, ncclUint8, root, (ncclComm_t)g_dist.comm, stream()));
   }
+}
+
+void dist_allreduce_sum_u64(unsigned long long *dev_buf, size_t count) {
+  if (g_dist.nranks <= 1 || count == 0) return;
+  const size_t CH = (size_t)1 << 27;  // elements per call (1 GiB)
+  for (size_t off = 0; off < count; off += CH) {
+    size_t len = std::min(CH, count - off);
+    NCK(nccl().AllReduce(dev_buf + off, dev_buf + off, len, ncclUint64, ncclSum, (ncclComm_t)g_dist.comm, stream()));
+  }
+}
+void dist_allgather(const void *send, void *recv, size_t bytes_per_rank) {
+  if (bytes_per_rank == 0) return;
+  if (g_dist.nranks <= 1) {
+    if (send != recv) CK(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, stream()));
+    return;
+  }
+  NCK(nccl().AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)g_dist.comm, stream()));
 }
 
 std::vector<int> local_positions(long long n_rem, int block, int nranks, int rank) {

@@ -15,6 +15,9 @@ struct Dist {
 };
 Dist &dist();
 void dist_broadcast(void *dev_buf, size_t bytes, int root);  // on the library stream
+void dist_allreduce_sum_u64(unsigned long long *dev_buf, size_t count);  // in place, on the library stream
+// recv = the ranks' `bytes_per_rank`-byte pieces in rank order (send may alias recv + rank * bytes_per_rank)
+void dist_allgather(const void *send, void *recv, size_t bytes_per_rank);
 
 // block-cyclic ownership of the dense panels (pure host logic, also exported for the CPU tests)
 inline int panel_owner(long long b, int nranks) { return (int)(b % nranks); }

@@ -543,16 +543,18 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     struct SinkGuard {
       ~SinkGuard() { g_sink = nullptr; }
     } sink_guard;
+    TailOpts topt;
+    topt.tall_skinny = opts->enable_tall_and_skinny, topt.low_rank_ratio = opts->low_rank_ratio, topt.start_weight = opts->low_rank_start_weight;
     if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
       echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
     else if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio)
       echelonize_lowrank_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, opts->low_rank_start_weight);
     else if (opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
-      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size);
+      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, topt);
     else if (opts->enable_GPLU)
       echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
     else if (opts->enable_dense)
-      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size);
+      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, topt);
     else
       logf("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
     sync();

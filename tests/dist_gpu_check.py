@@ -22,10 +22,24 @@ pkg = e.load_package()
 gpu = pkg.SpaSM()
 gpu.log(False)
 cases = [(1500, 1500, 5, 42013, 3, {}), (2600, 2400, 6, 65521, 4, dict(dense_block_size=300)), (900, 1000, 4, 4294967291, 5, dict(dense_block_size=128)),
-         (5000, 5000, 10, 42013, 6, {})]
+         (5000, 5000, 10, 42013, 6, {}),
+         # the dense loop switches to the low-rank mode with the remaining rows spread over the ranks
+         (2000, 2000, 3, 42013, 4, dict(dense_block_size=100, sparsity_threshold=0.0, max_round=0), 300),
+         (1200, 1000, 4, 65521, 5, dict(dense_block_size=64)),
+         (1500, 1400, 3, 4294967291, 8, dict(dense_block_size=50, sparsity_threshold=0.0, max_round=0, low_rank_start_weight=2), 200)]
+
+
+def make_input(case):
+    n, m, k, prime, seed = case[:5]
+    if len(case) > 6:
+        return synth.planted_rank(n, m, case[6], 0.5, prime, seed)
+    return synth.random_rows(n, m, k, prime, seed)
+
+
 single = []
-for (n, m, k, prime, seed, kw) in cases:  # single-GPU results first (no communicator yet)
-    p, j, x = synth.random_rows(n, m, k, prime, seed)
+for case in cases:  # single-GPU results first (no communicator yet)
+    n, m, k, prime, seed, kw = case[:6]
+    p, j, x = make_input(case)
     A = gpu.from_arrays(n, m, p, j, x, prime)
     single.append(checks.lu_arrays(gpu.echelonize(A, **kw)))
 # second axis (src/blocks.jl): independent blocks, one owner rank each, no data-path collective
@@ -38,8 +52,9 @@ dist.all_reduce(part)
 assert int(part.item()) == gpu.echelonize(Ab).r, (rank, int(part.item()))
 bench.dist_init(gpu.lib, dist, rank, world)
 ok = True
-for idx, (n, m, k, prime, seed, kw) in enumerate(cases):
-    p, j, x = synth.random_rows(n, m, k, prime, seed)
+for idx, case in enumerate(cases):
+    n, m, k, prime, seed, kw = case[:6]
+    p, j, x = make_input(case)
     A = gpu.from_arrays(n, m, p, j, x, prime)
     f = gpu.echelonize(A, **kw)
     got = checks.lu_arrays(f)
@@ -56,8 +71,9 @@ for idx, (n, m, k, prime, seed, kw) in enumerate(cases):
 # together the ranks hold exactly the single-GPU factor, and kernel / solve refuse a partial factor
 gpu.lib.spasm_b200_dist_shard_factor.argtypes = [C.c_int]
 gpu.lib.spasm_b200_dist_shard_factor(1)
-for idx, (n, m, k, prime, seed, kw) in enumerate(cases):
-    p, j, x = synth.random_rows(n, m, k, prime, seed)
+for idx, case in enumerate(cases):
+    n, m, k, prime, seed, kw = case[:6]
+    p, j, x = make_input(case)
     A = gpu.from_arrays(n, m, p, j, x, prime)
     f = gpu.echelonize(A, **kw)
     assert f.partial and f.r == single[idx]["r"]

@@ -16,11 +16,15 @@ def test_reference_arm_line():
     assert line["impl"] == "reference"
     assert line["metric"] == "echelonize_time_to_rank" and line["unit"] == "s" and line["higher_is_better"] is False
     assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 0
-    assert line["value"] > 0 and abs(line["ms_per_step"] - 1e3 * line["value"]) < 1e-6
+    # the CPU arm times a BOUNDED SAMPLE (fewer rows of the same generator): that is not the metric of the 200000-row
+    # workload, so the top-level value is null and the comparable numbers are numeric fields of cpu_baseline
+    assert line["value"] is None and "value_note" in line
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb and cb["sample_n"] >= 4000
+    assert abs(line["ms_per_step"] - 1e3 * cb["value"]) < 1e-6
+    assert "gpu_same_sample_s" in cb and "gpu_same_sample_e2e_s" in cb
     e = line["e2e"]
-    assert e["value"] == line["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert e["value"] is None and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
     assert line["vs_baseline"] is None
 

@@ -287,6 +287,27 @@ def test_low_rank_mode(gpu, oracle, case):
         checks.check_rank_and_rowspace(gpu, A, fg)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", __import__("test_oracle_invariants").MIDTAIL + [
+    (6000, 6000, 3, 42013, 21, 2300, dict(sparsity_threshold=0.0, max_round=0, dense_block_size=500)),  # deferred far rows pending at the switch
+])
+def test_mid_tail_low_rank_switch(gpu, oracle, case):
+    """the dense loop meets a block with fewer than low_rank_ratio * Sn pivots and hands the remaining
+    rows to the low-rank mode (random combinations of the rows of the dense Schur complement it already holds)"""
+    import ctypes as C
+    from test_oracle_invariants import midtail_input
+
+    A, kw = midtail_input(gpu, case)
+    fo = oracle.echelonize(A, **kw)
+    gpu.lib.spasm_b200_lowrank_switches.restype = C.c_longlong
+    gpu.lib.spasm_b200_lowrank_switches.argtypes = [C.c_int]
+    gpu.lib.spasm_b200_lowrank_switches(1)
+    fg = gpu.echelonize(A, **kw)
+    assert gpu.lib.spasm_b200_lowrank_switches(1) == 1
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg), f"{kw}: ")
+    checks.check_U_structure(gpu, fg)
+
+
 def test_blocks_gpu(gpu):
     from test_blocks import check_blocks
 

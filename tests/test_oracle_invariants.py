@@ -215,3 +215,41 @@ def test_blocked_dense_equals_rowwise(oracle, case, monkeypatch):
     monkeypatch.setenv("SPASM_ORACLE_ROWWISE", "1")
     rowwise = checks.lu_arrays(oracle.echelonize(A, **kw))
     checks.assert_same(rowwise, blocked, "blocked vs row-wise: ")
+
+
+MIDTAIL = [
+    # n, m, k, prime, seed, planted rank (None: random rows), options — inputs whose dense loop meets a block far below full rank
+    (2000, 2000, 3, 42013, 4, 300, dict(dense_block_size=100, sparsity_threshold=0.0, max_round=0)),
+    (1200, 1000, 4, 65521, 5, None, dict(dense_block_size=64)),
+    (1500, 1400, 3, 4294967291, 8, 200, dict(dense_block_size=50, sparsity_threshold=0.0, max_round=0, low_rank_start_weight=2)),
+]
+
+
+def midtail_input(api, case):
+    n, m, k, prime, seed, planted, kw = case
+    p, j, x = synth.planted_rank(n, m, planted, 0.5, prime, seed) if planted else synth.random_rows(n, m, k, prime, seed)
+    return api.from_arrays(n, m, p, j, x, prime), kw
+
+
+@pytest.mark.parametrize("case", MIDTAIL)
+def test_mid_tail_low_rank_switch_oracle(oracle, case, monkeypatch):
+    """SURVEY.md A.7 (spasm_schur_dense_randomized, src/SpaSM.jl:767-769): a dense block with fewer than low_rank_ratio * Sn
+    pivots hands the remaining rows to the low-rank mode.  The switch fires, the factor is valid, the blocked and the
+    row-by-row dense loops agree bit for bit, and without tall-and-skinny the plain dense loop gives the same canonical RREF."""
+    A, kw = midtail_input(oracle, case)
+    lines = []
+    oracle.log(lambda s: lines.append(s) or 0)
+    try:
+        fact = oracle.echelonize(A, verbose=True, **kw)
+    finally:
+        oracle.log(None)
+    assert any("switching to low-rank" in l for l in lines)
+    checks.check_U_structure(oracle, fact)
+    checks.check_rank_and_rowspace(oracle, A, fact)
+    blocked = checks.lu_arrays(fact)
+    plain = oracle.echelonize(A, enable_tall_and_skinny=False, **kw)
+    assert plain.r == fact.r
+    if case[3] < (1 << 31):  # (object arithmetic beyond: too slow for what rank + row space already say)
+        assert np.array_equal(checks.canonical_rref(oracle, fact), checks.canonical_rref(oracle, plain))
+    monkeypatch.setenv("SPASM_ORACLE_ROWWISE", "1")
+    checks.assert_same(checks.lu_arrays(oracle.echelonize(A, **kw)), blocked, "blocked vs row-wise: ")
