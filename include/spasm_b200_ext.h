@@ -28,10 +28,18 @@ long long spasm_b200_cached_bytes(void);
 int spasm_b200_nccl_unique_id(unsigned char *out128);
 int spasm_b200_dist_init(int rank, int nranks, const unsigned char *id128);
 void spasm_b200_dist_shard_factor(int on);
+/* The rows of the row engine are split over the ranks (contiguous shares, counts all-gathered, entries broadcast into place):
+ * always for the sparse Schur complements inside spasm_echelonize (src/SpaSM.jl:761-762; that call is collective already);
+ * for spasm_kernel (free columns, :876-882), spasm_rref (rows of U, :871) and spasm_gesv (right-hand sides, :915-923) after
+ * shard_rows(1) — those calls then become collective: every rank makes them, with the same complete factor, and every
+ * rank receives the complete, single-GPU-identical result. */
+void spasm_b200_dist_shard_rows(int on);
+void spasm_b200_shard_stats(long long *out2, int reset); /* row-engine calls split over the ranks, rows this rank solved in them */
 void spasm_b200_dist_finalize(void);
 /* host logic of the block-cyclic panel ownership (exported for the CPU / gloo tests) */
 long long spasm_b200_local_positions(long long n_rem, int block, int nranks, int rank, int *out, long long cap);
 int spasm_b200_panel_owner(long long b, int nranks);
+void spasm_b200_row_share(long long nrows, int nranks, int rank, long long *lo, long long *hi); /* share of the split row engine */
 
 /* ---- device-resident timing (bench.py `value`): the CSR is uploaded once; each call echelonizes from HBM, leaves the
  * factor on the device and returns the rank (ms = CUDA-event time of the call on the library's stream) */
@@ -45,6 +53,7 @@ void spasm_b200_last_stats(long long *out7);          /* last Schur / kernel sol
 void spasm_b200_mma_timing(int on);                   /* CUDA events around every tcgen05 launch (read lazily, no host stall) */
 void spasm_b200_mma_stats(double *out4, int reset);   /* ms in k_gemm_i8limb, modular MACs, launches, kernels launched by the library */
 void spasm_b200_tail_stats(long long *out4, int reset); /* deferred trailing updates: far flushes, multiplier corrections, far rows x depth, near updates */
+long long spasm_b200_lowrank_switches(int reset);      /* how often the dense loop handed its remaining rows to the low-rank mode */
 double spasm_b200_utcimma_peak(int iters, int reps);  /* measured back-to-back tcgen05.mma.kind::i8 M128 N256 K32 rate, TOP/s */
 
 /* ---- bench / test hooks */

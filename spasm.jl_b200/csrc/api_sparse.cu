@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <numeric>
 
+#include "dist.cuh"
 #include "factor.cuh"
 
 namespace sb {
@@ -123,6 +124,12 @@ void spasm_b200_last_stats(long long *out) {
   out[0] = g_last_stats.bytes, out[1] = g_last_stats.macs, out[2] = g_last_stats.rows;
   out[3] = g_last_stats.light, out[4] = g_last_stats.medium, out[5] = g_last_stats.heavy;
   out[6] = (long long)(g_last_stats.ms * 1000.0);
+}
+
+// {row-engine calls that were split over the ranks, rows THIS rank solved in them} since the last reset
+void spasm_b200_shard_stats(long long *out, int reset) {
+  out[0] = g_shard_stats[0], out[1] = g_shard_stats[1];
+  if (reset) g_shard_stats[0] = g_shard_stats[1] = 0;
 }
 
 static u64 g_prng = 0x5a5a5a5a2e6306e0ULL;
@@ -277,6 +284,7 @@ struct spasm_csr *spasm_kernel(const struct spasm_lu *fact) {
     build_kernel_system(f, K);
     SolveSystem G{K.Ut.j.p, K.Ut.x.p, K.pdesc.p, m};
     SolveRows B{K.Ut.p.p, K.Ut.j.p, K.Ut.x.p, K.freecols.p, K.nfree, nullptr};
+    B.collective = dist().shard_rows;  // free columns split over the ranks when every rank makes this call (opt-in)
     SolveEmit E;
     E.all_columns = true;
     E.prefix_col = K.freecols.p;
@@ -307,6 +315,7 @@ struct spasm_csr *spasm_rref(const struct spasm_lu *fact, int *Rqinv) {
     if (r) k_pivcol<<<cdiv(r, 256), 256, 0, stream()>>>(f.U.p.p, f.U.j.p, r, pivcol.p);
     SolveSystem G{f.U.j.p, f.U.x.p, pdesc.p, m};
     SolveRows B{f.U.p.p, f.U.j.p, f.U.x.p, nullptr, r, pivcol.p};
+    B.collective = dist().shard_rows;
     SolveEmit E;
     E.prefix_col = pivcol.p;
     E.prefix_val = 1;

@@ -106,8 +106,8 @@ int spasm_b200_dist_init(int rank, int nranks, const unsigned char *id128) {
     memcpy(&id, id128, 128);
     ncclComm_t comm;
     NCK(nccl().CommInitRank(&comm, nranks, id, rank));
-    const bool keep = dist().shard_factor;
-    dist().rank = rank, dist().nranks = nranks, dist().comm = comm, dist().shard_factor = keep;
+    const bool keep = dist().shard_factor, keep_rows = dist().shard_rows;
+    dist().rank = rank, dist().nranks = nranks, dist().comm = comm, dist().shard_factor = keep, dist().shard_rows = keep_rows;
     return 0;
   } catch (const std::exception &e) {
     errf("[spasm_b200] spasm_b200_dist_init failed: %s\n", e.what());
@@ -116,6 +116,9 @@ int spasm_b200_dist_init(int rank, int nranks, const unsigned char *id128) {
 }
 // 0 (default): rank 0 returns the complete factor; 1: every rank returns the rows of U it owns (see dist.cuh)
 void spasm_b200_dist_shard_factor(int on) { dist().shard_factor = on != 0; }
+// 1: spasm_kernel / spasm_rref / spasm_gesv become collective calls (every rank, same complete factor) whose rows
+// (free columns, rows of U, right-hand sides) are split over the ranks and all-gathered; 0 (default): each call is local
+void spasm_b200_dist_shard_rows(int on) { dist().shard_rows = on != 0; }
 void spasm_b200_dist_finalize(void) {
   if (dist().comm) nccl().CommDestroy((ncclComm_t)dist().comm);
   dist() = Dist();
@@ -128,5 +131,6 @@ long long spasm_b200_local_positions(long long n_rem, int block, int nranks, int
   return (long long)v.size();
 }
 int spasm_b200_panel_owner(long long b, int nranks) { return panel_owner(b, nranks); }
+void spasm_b200_row_share(long long nrows, int nranks, int rank, long long *lo, long long *hi) { row_share(nrows, nranks, rank, lo, hi); }
 
 }  // extern "C"

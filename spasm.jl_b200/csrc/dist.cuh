@@ -12,6 +12,9 @@ struct Dist {
   // r and qinv).  true: the owner of each dense panel materialises (and downloads) its rows — the factor is
   // distributed over the ranks, every rank's struct is flagged `partial`, and the download scales with 1/N.
   bool shard_factor = false;
+  // kernel / rref / gesv split their rows over the ranks (every rank must then make the call, with the same complete
+  // factor); the Schur complements inside spasm_echelonize are always split (that call is collective already)
+  bool shard_rows = false;
 };
 Dist &dist();
 void dist_broadcast(void *dev_buf, size_t bytes, int root);  // on the library stream
@@ -21,6 +24,12 @@ void dist_allgather(const void *send, void *recv, size_t bytes_per_rank);
 
 // block-cyclic ownership of the dense panels (pure host logic, also exported for the CPU tests)
 inline int panel_owner(long long b, int nranks) { return (int)(b % nranks); }
+// contiguous share [lo, hi) of `nrows` independent rows that `rank` solves when the row engine is split over the ranks
+inline void row_share(long long nrows, int nranks, int rank, long long *lo, long long *hi) {
+  const long long per = (nrows + nranks - 1) / nranks;
+  *lo = std::min(per * rank, nrows);
+  *hi = std::min(*lo + per, nrows);
+}
 // positions (into the remaining-row list) owned by `rank`: panels b = rank, rank+nranks, ...
 std::vector<int> local_positions(long long n_rem, int block, int nranks, int rank);
 

@@ -442,6 +442,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
   std::vector<int> p_in;  // current row -> original row (empty: identity)
   double density = (n0 > 0 && m > 0) ? (double)spasm_nnz(A) / n0 / m : 0.0;
   bool finished = false, go_dense = false;
+  bool tail_distributed = false;  // the dense tail ran with its rows (and, on the other ranks, the rows of U) spread over the ranks
   int *sink_arrays_j = nullptr, *sink_arrays_x = nullptr;
   long long sink_done = 0, sink_cap = 0;
   PivotSearch P;
@@ -487,6 +488,7 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     build_pdesc_U(E.U, E.Uqinv.p, pdesc);
     SolveSystem G{E.U.j.p, E.U.x.p, pdesc.p, m, &E.U, E.Uqinv.p};
     SolveRows B{cur->p.p, cur->j.p, cur->x.p, P.p.p + npiv, rem_rows, nullptr};
+    B.collective = true;  // spasm_echelonize is entered by every rank with the same matrix: the non-pivotal rows are split over the ranks
     SolveEmit Em;
     Em.want_L = (E.L != nullptr);
     SolveResult R;
@@ -550,11 +552,11 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     else if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio)
       echelonize_lowrank_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, opts->low_rank_start_weight);
     else if (opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
-      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, topt);
+      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, topt), tail_distributed = true;
     else if (opts->enable_GPLU)
       echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
     else if (opts->enable_dense)
-      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, topt);
+      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, topt), tail_distributed = true;
     else
       logf("[echelonize] Cannot finish (no valid method enabled). Incomplete echelonization returned\n");
     sync();
@@ -615,7 +617,8 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
   fact->complete = 0;
   {
     const Dist &dd = dist();
-    fact->partial = (dd.nranks > 1 && (dd.shard_factor || dd.rank != 0)) ? 1 : 0;
+    // only the sharded dense tail leaves rows of U on other ranks; everything else is computed identically by every rank
+    fact->partial = (dd.nranks > 1 && tail_distributed && (dd.shard_factor || dd.rank != 0)) ? 1 : 0;
   }
   fact->L = nullptr;
   fact->p = E.Lp;

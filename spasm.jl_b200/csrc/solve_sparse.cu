@@ -19,6 +19,7 @@
 // not fit the output slab are re-run with an exactly sized slab (status 2).  The heavy tier keeps
 // the accumulator as a direct-indexed array in global memory with a bitmap priority queue.
 #include "solve_sparse.cuh"
+#include "dist.cuh"
 
 #include "dense.cuh"
 
@@ -1031,7 +1032,7 @@ __global__ void k_sort_check(const int *todo, int n) {}
 
 // order-preserving compaction of a todo list is not needed: rows are written by k.
 
-void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, const Fp &F, SolveResult &R) {
+void solve_rows_local(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, const Fp &F, SolveResult &R) {
   const int nrows = B.nrows;
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0));
@@ -1331,6 +1332,120 @@ void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, co
   }
   CK(cudaEventRecord(ev1, stream()));
   sync();
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  R.stats.ms = ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+}
+
+// ------------------------------------------------------------------ rows split over the ranks
+// The rows of a Schur complement / kernel basis / rref / batch of right-hand sides are independent given the
+// system, which every rank holds.  Rank r solves the contiguous share [r*per, (r+1)*per) of the row list; the
+// ranks then exchange the counts (one all-gather) and the entries (one broadcast per rank, straight into the
+// final arrays at that rank's offset).  The result is the single-GPU result on every rank, bit for bit:
+// rows in input order, each row computed by exactly one rank with the same kernels.
+long long g_shard_stats[2] = {0, 0};
+__global__ void k_iota_from(int *a, int n, int first) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = first + i;
+}
+__global__ void k_pick_ll(const long long *__restrict__ p, const int *__restrict__ idx, int n, long long *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = p[idx[i]];
+}
+// one stream of the result (entries or multipliers): counts -> row pointers -> payload
+static long long gather_stream(const DBuf<int> &cnt_loc, const DBuf<int> &j_loc, const DBuf<uint32_t> &x_loc, int nloc, int nrows, int per,
+                               DBuf<int> &cnt, DBuf<long long> &p, DBuf<int> &j, DBuf<uint32_t> &x, bool payload) {
+  const Dist &dd = dist();
+  const int NR = dd.nranks, me = dd.rank;
+  cudaStream_t s = stream();
+  DBuf<int> send(per), all((size_t)per * NR + 1);
+  send.zero();
+  if (nloc) CK(cudaMemcpyAsync(send.p, cnt_loc.p, (size_t)nloc * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  dist_allgather(send.p, all.p, (size_t)per * sizeof(int));
+  cnt.alloc(nrows + 1);
+  CK(cudaMemcpyAsync(cnt.p, all.p, (size_t)nrows * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync(cnt.p + nrows, 0, sizeof(int), s));
+  p.alloc(nrows + 1);
+  exclusive_scan_i32_to_i64(cnt.p, p.p, nrows + 1);
+  // where each rank's share starts in the payload
+  std::vector<int> bidx(NR + 1);
+  for (int r = 0; r <= NR; r++) bidx[r] = (int)std::min<long long>((long long)r * per, nrows);
+  DBuf<int> dbidx(NR + 1);
+  DBuf<long long> dboff(NR + 1);
+  dbidx.upload(bidx.data(), NR + 1);
+  k_pick_ll<<<1, 64, 0, s>>>(p.p, dbidx.p, NR + 1, dboff.p);
+  std::vector<long long> boff(NR + 1);
+  dboff.download(boff.data(), NR + 1);
+  sync();
+  const long long nnz = boff[NR];
+  if (!payload) return nnz;
+  j.alloc(nnz);
+  x.alloc(nnz);
+  const long long mine = boff[me + 1] - boff[me];
+  if (mine) {
+    CK(cudaMemcpyAsync(j.p + boff[me], j_loc.p, (size_t)mine * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(x.p + boff[me], x_loc.p, (size_t)mine * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  }
+  for (int r = 0; r < NR; r++) {
+    const long long len = boff[r + 1] - boff[r];
+    if (len == 0) continue;
+    dist_broadcast(j.p + boff[r], (size_t)len * sizeof(int), r);
+    dist_broadcast(x.p + boff[r], (size_t)len * sizeof(uint32_t), r);
+  }
+  return nnz;
+}
+
+void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, const Fp &F, SolveResult &R) {
+  const Dist &dd = dist();
+  static const bool off = getenv("SPASM_B200_NO_SHARD_ROWS") != nullptr;
+  if (!B.collective || dd.nranks <= 1 || off || E.count_only || E.structural || B.nrows < 2 * dd.nranks) {
+    solve_rows_local(G, B, E, F, R);
+    return;
+  }
+  const int NR = dd.nranks, me = dd.rank, nrows = B.nrows;
+  cudaStream_t s = stream();
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, s));
+  const int per = (nrows + NR - 1) / NR;
+  long long lo_, hi_;
+  row_share(nrows, NR, me, &lo_, &hi_);
+  const int lo = (int)lo_, hi = (int)hi_, nloc = hi - lo;
+  SolveRows Bl = B;
+  SolveEmit El = E;
+  DBuf<int> iota;
+  if (B.rows)
+    Bl.rows = B.rows + lo;
+  else {
+    iota.alloc(std::max(nloc, 1));
+    if (nloc) k_iota_from<<<cdiv(nloc, 256), 256, 0, s>>>(iota.p, nloc, lo);
+    Bl.rows = iota.p;
+  }
+  Bl.nrows = nloc;
+  Bl.collective = false;
+  if (B.mask) Bl.mask = B.mask + lo;
+  if (E.prefix_col) El.prefix_col = E.prefix_col + lo;
+  SolveResult Rl;
+  solve_rows_local(G, Bl, El, F, Rl);
+  g_shard_stats[0] += 1, g_shard_stats[1] += nloc;
+  R.nnz = gather_stream(Rl.cnt, Rl.j, Rl.x, nloc, nrows, per, R.cnt, R.p, R.j, R.x, true);
+  R.lnnz = 0;
+  if (E.want_L) R.lnnz = gather_stream(Rl.lcnt, Rl.lj, Rl.lx, nloc, nrows, per, R.lcnt, R.lp, R.lj, R.lx, true);
+  // work counters of the whole call: the sum over the ranks
+  DBuf<unsigned long long> w(6);
+  const unsigned long long hw[6] = {(unsigned long long)Rl.stats.bytes, (unsigned long long)Rl.stats.macs, (unsigned long long)Rl.stats.rows,
+                                    (unsigned long long)Rl.stats.light, (unsigned long long)Rl.stats.medium, (unsigned long long)Rl.stats.heavy};
+  w.upload(hw, 6);
+  dist_allreduce_sum_u64(w.p, 6);
+  unsigned long long tot[6];
+  w.download(tot, 6);
+  CK(cudaEventRecord(ev1, s));
+  sync();
+  R.stats.bytes = (long long)tot[0], R.stats.macs = (long long)tot[1], R.stats.rows = (long long)tot[2];
+  R.stats.light = (long long)tot[3], R.stats.medium = (long long)tot[4], R.stats.heavy = (long long)tot[5];
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev0, ev1));
   R.stats.ms = ms;

@@ -39,6 +39,10 @@ struct SolveRows {
   int nrows = 0;
   const int *mask = nullptr;  // [nrows] optional: column treated as non-pivotal for row k (rref)
   bool few_pivots = false;    // hint: these rows reach only a handful of pivots (GPLU rows carried in reduced form): row-at-a-time tiers first
+  // every rank of the communicator makes this call with the same system and the same rows (Schur complement inside
+  // spasm_echelonize; kernel / rref / gesv when the host opted in with spasm_b200_dist_shard_rows): the rows are split
+  // into contiguous shares, one per rank, and the results all-gathered (counts first, then the payload)
+  bool collective = false;
 };
 
 // what to emit for each solved row
@@ -71,6 +75,10 @@ struct SolveResult {
 // heavy rows (more distinct columns than the shared-memory tiers hold) are delegated to this
 // callback: it must fill cnt/j/x for the listed k (dense engine, solve_dense.cu)
 void solve_rows(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, const Fp &F, SolveResult &R);
+// the same on this rank alone, whatever B.collective says
+void solve_rows_local(const SolveSystem &G, const SolveRows &B, const SolveEmit &E, const Fp &F, SolveResult &R);
+// {calls that were split over the ranks, rows this rank solved in them} since the last reset
+extern long long g_shard_stats[2];
 // every row of a device CSR sorted by column index
 void sort_csr_rows(const long long *p, int n, int *j, uint32_t *x);
 

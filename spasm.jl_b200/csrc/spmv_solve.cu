@@ -5,6 +5,7 @@
 // the same elimination on the rows of L that hold the "diagonal" entries, scaled to unit pivots.
 #include <algorithm>
 
+#include "dist.cuh"
 #include "factor.cuh"
 
 namespace sb {
@@ -308,6 +309,7 @@ struct spasm_csr *spasm_gesv(const struct spasm_lu *fact, const struct spasm_csr
     // ---- z.U = b for every row of B
     SolveSystem GU{f.U.j.p, f.U.x.p, pdesc.p, m};
     SolveRows RB{dB.p.p, dB.j.p, dB.x.p, nullptr, nb, nullptr};
+    RB.collective = dist().shard_rows;  // right-hand sides split over the ranks ("many RHS -> shard RHS")
     SolveEmit Em;
     Em.all_columns = true;
     SolveResult Z;
@@ -328,6 +330,7 @@ struct spasm_csr *spasm_gesv(const struct spasm_lu *fact, const struct spasm_csr
     if (nok > 0) {
       SolveSystem GL{S.L.j.p, S.scaled.p, S.pdesc.p, S.r};
       SolveRows RZ{Z.p.p, Z.j.p, Z.x.p, oklist.p, nok, nullptr};
+      RZ.collective = dist().shard_rows;
       solve_rows(GL, RZ, Em, f.F, X);
       // (k, v) -> (row of A that holds the k-th diagonal, v / diagonal), then by increasing row index
       if (X.nnz) {

@@ -91,8 +91,80 @@ for idx, case in enumerate(cases):
     except (RuntimeError, ValueError, AssertionError):
         pass
 gpu.lib.spasm_b200_dist_shard_factor(0)
+
+# ---- rows of the row engine split over the ranks: the sparse Schur complements inside echelonize
+# (always), kernel / rref / gesv after shard_rows(1).  Every rank must end up with the single-GPU result, bit for bit.
+gpu.lib.spasm_b200_shard_stats.argtypes = [C.c_void_p, C.c_int]
+gpu.lib.spasm_b200_dist_shard_rows.argtypes = [C.c_int]
+
+
+def shard_stats(reset=True):
+    out = (C.c_longlong * 2)()
+    gpu.lib.spasm_b200_shard_stats(out, 1 if reset else 0)
+    return out[0], out[1]
+
+
+s_ = 128
+ns, ms_, rs = 1911130 // s_, 1955309 // s_, 1033568 // s_
+ps, js, xs = synth.banded_planted(ns, ms_, rs, 12.0, 40, 42013, 0x5A5A0003, spread=16, colblock=8)
+As = gpu.from_arrays(ns, ms_, ps, js, xs, 42013)
+ora = pkg.SpaSM(e.build_oracle())
+for kw in (dict(), dict(L=True)):
+    shard_stats()
+    f = gpu.echelonize(As, **kw)
+    calls, mine = shard_stats()
+    assert calls >= 1 and 0 < mine, (rank, calls, mine)  # the Schur complement ran split over the ranks
+    assert f.r == rs and not f.partial  # no dense tail: every rank holds the complete factor
+    fo = ora.echelonize(As, **kw)
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(f), f"rank {rank}, sharded Schur {kw}: ")
+    if not kw:
+        def rref_(fact):
+            q = np.zeros(ms_, dtype=np.int32)
+            return gpu.rref(fact, q), q
+
+        K_local, (R_local, q_local) = gpu.kernel(f), rref_(f)
+        gpu.lib.spasm_b200_dist_shard_rows(1)
+        shard_stats()
+        K_sh, (R_sh, q_sh) = gpu.kernel(f), rref_(f)
+        calls, mine = shard_stats()
+        assert calls == 2 and mine < (ms_ - rs) + rs, (rank, calls, mine)
+        gpu.lib.spasm_b200_dist_shard_rows(0)
+        for a, b in zip(list(K_local.arrays()) + list(R_local.arrays()) + [q_local], list(K_sh.arrays()) + list(R_sh.arrays()) + [q_sh]):
+            assert np.array_equal(a, b), f"rank {rank}: sharded kernel / rref differ from the local ones"
+        for a, b in zip(K_sh.arrays(), ora.kernel(fo).arrays()):
+            assert np.array_equal(a, b)
+    else:
+        # 24 right-hand sides: 20 in the row space, 4 random; gesv with the right-hand sides split over the ranks
+        rng = np.random.default_rng(7)
+        rowsB = []
+        Ad = synth.csr_to_dense(ns, ms_, ps, js, xs, 42013).astype(np.int64)
+        for t in range(24):
+            if t < 20:
+                xv = rng.integers(0, 42013, size=ns)
+                xv[rng.random(ns) < 0.995] = 0
+                rowsB.append((xv @ Ad) % 42013)
+            else:
+                rowsB.append(rng.integers(0, 42013, size=ms_))
+        Bd = np.array(rowsB)
+        bp = np.zeros(25, dtype=np.int64)
+        bj, bx = [], []
+        for t in range(24):
+            nzc = np.nonzero(Bd[t])[0]
+            bj.append(nzc), bx.append(synth.balanced(Bd[t][nzc], 42013))
+            bp[t + 1] = bp[t] + len(nzc)
+        Bm = gpu.from_arrays(24, ms_, bp, np.concatenate(bj).astype(np.int32), np.concatenate(bx).astype(np.int32), 42013)
+        X_local, ok_local = gpu.gesv(f, Bm)
+        gpu.lib.spasm_b200_dist_shard_rows(1)
+        shard_stats()
+        X_sh, ok_sh = gpu.gesv(f, Bm)
+        calls, mine = shard_stats()
+        assert calls == 2, (rank, calls, mine)
+        gpu.lib.spasm_b200_dist_shard_rows(0)
+        assert list(ok_local) == list(ok_sh) and sum(ok_sh) >= 20
+        for a, b in zip(X_local.arrays(), X_sh.arrays()):
+            assert np.array_equal(a, b), f"rank {rank}: sharded gesv differs from the local one"
 dist.barrier()
 gpu.lib.spasm_b200_dist_finalize()
 dist.destroy_process_group()
 if rank == 0:
-    print(f"dist check OK on {world} GPUs: {len(cases)} cases bit-exact (single GPU == sharded == oracle)")
+    print(f"dist check OK on {world} GPUs: {len(cases)} cases bit-exact (single GPU == sharded == oracle); Schur / kernel / rref / gesv rows split over the ranks")
