@@ -43,7 +43,17 @@ struct ApiCall {
   ApiCall(const ApiCall &) = delete;
   ApiCall &operator=(const ApiCall &) = delete;
 };
-cudaStream_t stream();
+cudaStream_t stream();       // the stream the library's launches, copies and stream-ordered allocations go to right now
+cudaStream_t main_stream();  // the library stream (highest priority)
+cudaStream_t aux_stream();   // second, low-priority stream: the deferred far-row updates of the dense tail run there
+// while alive, stream() is `s` (work of a whole code path — kernels, temporaries, frees — moves to that stream)
+struct StreamScope {
+  cudaStream_t prev;
+  explicit StreamScope(cudaStream_t s);
+  ~StreamScope();
+  StreamScope(const StreamScope &) = delete;
+  StreamScope &operator=(const StreamScope &) = delete;
+};
 int sm_count();
 
 // ------------------------------------------------------------------ field

@@ -289,6 +289,15 @@ __global__ void __launch_bounds__(256) k_gemm_nt(uint32_t *__restrict__ C, long 
 
 bool gemm_nt_mma(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
                  bool subtract, const Fp &F, const int *rowmap);  // dense_mma.cu: returns false when the shape / prime is not handled
+extern int g_gemm_cta_limit;  // dense_mma.cu: > 0 caps the CTAs (= SMs) of the persistent tensor-core kernel
+// while alive, the tensor-core launches use at most `n` SMs (0: no change) so that another stream's kernels find room
+struct GemmCtaLimit {
+  int prev;
+  explicit GemmCtaLimit(int n) : prev(g_gemm_cta_limit) {
+    if (n > 0) g_gemm_cta_limit = n;
+  }
+  ~GemmCtaLimit() { g_gemm_cta_limit = prev; }
+};
 
 void gemm_nt(uint32_t *C, long long ldc, int M, int N, const uint32_t *A, long long lda, const uint32_t *B, long long ldb, int K,
              bool subtract, const Fp &F, const int *rowmap) {
@@ -919,7 +928,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   const char *prof_env = getenv("SPASM_B200_PROFILE");
   const bool prof = prof_env != nullptr;
   const bool prof_ev = prof && atoi(prof_env) == 2;
-  double tp[7] = {0, 0, 0, 0, 0, 0, 0};  // panel, R gemm, emit, gather/transposes, trailing gemm, blocks, broadcast
+  double tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // panel, R gemm, emit, gather/transposes, trailing gemm, blocks, broadcast, handover (wait for the second stream)
   std::vector<std::pair<int, cudaEvent_t>> evs;  // (slot that ENDS at this event, event); slot -1 = start marker
   auto mark = [&](int slot) {
     cudaEvent_t ev;
@@ -959,7 +968,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   }
   const int Bmax = std::min(block_size, nrows);
   DBuf<uint32_t> T((size_t)Bmax * Bmax), Tsel((size_t)Bmax * Bmax), R((size_t)Bmax * Sm0), Rt, Pt;
-  DBuf<int> ispiv, pivrow, pivcol(Bmax), ident(Bmax), hdr(1), cflag(Sm0 + 1), cand(std::max(Sm0, 1));
+  DBuf<int> ispiv, pivrow, ident(Bmax), hdr(1), cflag(Sm0 + 1), cand(std::max(Sm0, 1));
   DBuf<long long> cpos(Sm0 + 1);
   DBuf<unsigned char> colpiv(std::max(Sm0, 1));
   colpiv.zero();
@@ -978,14 +987,60 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   int kcap = 4096;
   if (const char *e = getenv("SPASM_B200_LAZY_K")) kcap = atoi(e);
   kcap = std::max(0, std::min(kcap, gemm_max_k(F) - B16));
-  while (kcap >= 2 * B16 && (size_t)(Sm0 + n_local + B16) * (size_t)(kcap + B16) * 4 > dev_free_bytes() / 4) kcap /= 2;  // keep the two factor buffers small
+  while (kcap >= 2 * B16 && (size_t)(Sm0 + n_local + B16) * (size_t)(kcap + B16) * 8 > dev_free_bytes() / 4) kcap /= 2;  // keep the (two sets of) factor buffers small
   const bool lazy = kcap >= 2 * B16 && n_local > 2 * block_size;
-  const int group = lazy ? std::max(1, kcap / std::max(block_size, 1)) : 1;
-  const long long LDK = lazy ? (long long)kcap + B16 : 0;
-  DBuf<uint32_t> Rt_acc, Pt_acc, Rsel, wire;
-  if (lazy) Rt_acc.alloc((size_t)Sm0 * LDK), Pt_acc.alloc((size_t)n_local * LDK), Rsel.alloc((size_t)B16 * LDK);
-  int Kacc = 0;                                         // depth of the pending product
-  long long gend = (long long)group * block_size;       // my local rows [.., gend) are always up to date
+  // my panels per flush: the factors of group * NR panels (mine and the other ranks') accumulate between two flushes,
+  // and a flush happens exactly when my near rows are used up — the moment the next `group` panels change hands
+  const int group = lazy ? std::max(1, kcap / std::max(block_size * NR, 1)) : 1;
+  const int kdepth = lazy ? (int)std::min<long long>(std::max<long long>(kcap, (long long)group * NR * B16), gemm_max_k(F) - B16) : 0;
+  const long long LDK = lazy ? (long long)kdepth + B16 : 0;
+  // ---- look-ahead on two streams.  Everything the NEXT panel waits for — this panel's factorisation, its
+  // broadcast, the update of the near rows — stays on the main stream (A, high priority); the far rows are only
+  // touched by the second stream (B): gathering a panel's multipliers there, correcting them, and the deep flushes.
+  // A hands rows to B never; B hands the next `group` panels to A at a flush (one event).  Two sets of accumulators:
+  // while B applies one, A already fills the other.  B's tensor-core launches leave some SMs to A's (small, latency
+  // bound) kernels, which would otherwise queue behind a persistent kernel that owns every SM's shared memory.
+  const bool two_streams = lazy && getenv("SPASM_B200_ONE_STREAM") == nullptr;
+  const int nsets = two_streams ? 2 : 1;
+  cudaStream_t sA = s, sB = two_streams ? aux_stream() : s;
+  int aux_ctas = sm_count() - (NR > 1 ? 48 : 32);  // (with several ranks the second stream has 1/N of the work: the critical path gets more room)
+  if (const char *e = getenv("SPASM_B200_AUX_SMS")) aux_ctas = atoi(e);
+  aux_ctas = std::max(8, std::min(aux_ctas, sm_count()));
+  DBuf<uint32_t> Rt_accs[2], Pt_accs[2], Rsel, wire;
+  DBuf<int> cand_snap[2];
+  if (lazy) {
+    for (int i = 0; i < nsets; i++)
+      Rt_accs[i].alloc((size_t)Sm0 * LDK), Pt_accs[i].alloc((size_t)n_local * LDK), cand_snap[i].alloc(std::max(Sm0, 1));
+    Rsel.alloc((size_t)B16 * LDK);
+  }
+  // per-panel pivot columns: the second stream reads a panel's list after the main stream has moved on
+  DBuf<int> pc_hist((size_t)std::min(nrows, Sm0) + Bmax + 1);
+  std::vector<cudaEvent_t> ev_pool;
+  auto new_event = [&]() {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_pool.push_back(e);
+    return e;
+  };
+  // `to` will not start anything enqueued after this call before `from` has finished everything enqueued before it
+  auto order = [&](cudaStream_t from, cudaStream_t to) {
+    if (from == to) return;
+    cudaEvent_t e = new_event();
+    CK(cudaEventRecord(e, from));
+    CK(cudaStreamWaitEvent(to, e, 0));
+  };
+  struct AuxGuard {  // an exception must not free buffers the second stream still works on
+    cudaStream_t b;
+    std::vector<cudaEvent_t> *pool;
+    ~AuxGuard() {
+      if (b) cudaStreamSynchronize(b);
+      for (cudaEvent_t e : *pool) cudaEventDestroy(e);
+    }
+  } aux_guard{two_streams ? sB : nullptr, &ev_pool};
+  cudaEvent_t ev_flush[2] = {nullptr, nullptr};  // end of the last flush that read accumulator set i
+  int cur = 0;                                           // accumulator set being filled
+  int Kacc = 0;                                          // depth of the pending product
+  long long gend = (long long)group * block_size;        // my local rows [.., gend) are always up to date
   // live columns: cand[0:nlive) = the columns that are not pivots of a panel factored so far, increasing.  Pivoted
   // columns are dead (zero on every remaining row): the panel factorisation scans, and the trailing products
   // update, the live columns only — the work shrinks with the elimination (n^3/3 instead of n^3/2).
@@ -996,25 +1051,57 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     k_compact_flags_i32(cflag.p, cpos.p, Sm0, cand.p);
   };
   refresh_live();
-  auto flush_far = [&]() {
+  // apply the pending product to the far rows [min(gend, n_local), n_local); the rows below next_gend first: they are
+  // the ones the main stream is about to need (it waits for that part only)
+  auto flush_far = [&](long long next_gend) {
     const long long fe = std::min<long long>(gend, n_local);
+    bool flushed = false;
     if (Kacc > 0 && fe < n_local && nlive > 0) {
-      gemm_nt(D.Dt.p + fe, ld, nlive, (int)(n_local - fe), Rt_acc.p, LDK, Pt_acc.p + fe * LDK, LDK, Kacc, true, F, cand.p);
+      uint32_t *Rt_acc = Rt_accs[cur].p, *Pt_acc = Pt_accs[cur].p;
+      const int nl = nlive;
+      const int *cmap = cand.p;
+      if (two_streams) {  // A refreshes cand with every panel: B works on a snapshot
+        CK(cudaMemcpyAsync(cand_snap[cur].p, cand.p, (size_t)nl * sizeof(int), cudaMemcpyDeviceToDevice, sA));
+        cmap = cand_snap[cur].p;
+      }
+      order(sA, sB);
+      const long long mid = std::min<long long>(std::max(next_gend, fe), n_local);
+      {
+        StreamScope on_b(sB);
+        GemmCtaLimit lim(two_streams ? aux_ctas : 0);
+        if (mid > fe) {
+          gemm_nt(D.Dt.p + fe, ld, nl, (int)(mid - fe), Rt_acc, LDK, Pt_acc + fe * LDK, LDK, Kacc, true, F, cmap);
+          order(sB, sA);  // rows [fe, mid) change hands: A goes on as soon as THEY are up to date
+        }
+        if (n_local > mid) gemm_nt(D.Dt.p + mid, ld, nl, (int)(n_local - mid), Rt_acc, LDK, Pt_acc + mid * LDK, LDK, Kacc, true, F, cmap);
+      }
+      flushed = true;
       g_tail_stats[0] += 1, g_tail_stats[2] += (n_local - fe) * (long long)Kacc;
+      if (two_streams) {
+        if (!ev_flush[cur]) ev_flush[cur] = new_event();
+        CK(cudaEventRecord(ev_flush[cur], sB));
+        cur ^= 1;  // A fills the other set meanwhile — once the flush that read it (two flushes ago) is over
+        if (ev_flush[cur]) CK(cudaStreamWaitEvent(sA, ev_flush[cur], 0));
+      }
     }
+    if (!flushed && next_gend > gend) order(sB, sA);  // rows change hands without a flush: B must be done with them
     Kacc = 0;
   };
+  long long pc_off = 0;
   for (long long b = 0; b < nb; b++) {
     const long long kg = b * block_size;
     const int Sn = (int)std::min<long long>(block_size, nrows - kg);
     const int owner = panel_owner(b, NR);
     if (lazy && owner == me && lb * block_size >= gend) {  // the near rows are used up: bring the far rows up to date
       double tf = spasm_wtime();
-      flush_far();
+      if (prof_ev) mark(-1);
+      flush_far(lb * block_size + (long long)group * block_size);
       gend = lb * block_size + (long long)group * block_size;
-      if (prof) {
+      if (prof_ev)
+        mark(7);
+      else if (prof) {
         sync();
-        tp[4] += spasm_wtime() - tf;
+        tp[7] += spasm_wtime() - tf;
       }
     }
     logf("[echelonize/dense] processing dense schur complement of dimension %lld x %d; block size=%d\n", (long long)nrows - kg, m_total - U.n,
@@ -1022,12 +1109,13 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     double t1 = spasm_wtime();
     if (prof_ev) mark(-1);
     int rr = 0;
+    int *pc_b = pc_hist.p + pc_off;  // this panel's pivot columns (kept: the second stream reads them later)
     if (owner == me) {
       const long long k0 = lb * block_size;
       DBuf<int> pc_tmp;
       // candidate columns of this panel: everything that is not a pivot of an earlier panel
       rr = panel_factor(D.Dt.p, ld, cand.p, nlive, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F);
-      if (rr > 0) CK(cudaMemcpyAsync(pivcol.p, pc_tmp.p, (size_t)rr * sizeof(int), cudaMemcpyDeviceToDevice, s));
+      if (rr > 0) CK(cudaMemcpyAsync(pc_b, pc_tmp.p, (size_t)rr * sizeof(int), cudaMemcpyDeviceToDevice, s));
       tick(0, t1);
       if (rr > 0) {
         // reduced rows  R[s][c] = sum_t T[pivrow[s]][t] * Dt[c][k0+t]
@@ -1043,7 +1131,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       dist_broadcast(hdr.p, sizeof(int), owner);
       rr = fetch(hdr.p);
       if (rr > 0) {
-        dist_broadcast(pivcol.p, (size_t)rr * sizeof(int), owner);
+        dist_broadcast(pc_b, (size_t)rr * sizeof(int), owner);
         // R_b travels packed: the nlive columns that were live before this panel (all others are zero), u16 when p < 2^16
         const size_t esz = F.small ? 2 : 4;
         wire.alloc(((size_t)rr * nlive * esz + 3) / 4);
@@ -1067,7 +1155,8 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       tick(6, t1);
     }
     if (rr > 0) {
-      k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pivcol.p, rr, colpiv.p);
+      pc_off += rr;
+      k_mark_cols<<<cdiv(rr, 256), 256, 0, s>>>(pc_b, rr, colpiv.p);
       refresh_live();
       nlive -= rr;
       if (emits(b)) {
@@ -1079,7 +1168,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         const long long add = fetch(rpos.p + rr);
         if (sink && (size_t)(U.nnz + add) > U.j.n) sink->wait_all();  // the arrays are about to move
         csr_reserve(U, U.nnz + add, U.n + rr);
-        k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pivcol.p, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
+        k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pc_b, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
         CK(cudaGetLastError());
         if (sink) {
           convert_to_balanced(U.x.p + U.nnz, (int *)U.x.p + U.nnz, add, F);
@@ -1087,7 +1176,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         }
         U.nnz += add;
       } else {
-        k_register_pivots_only<<<cdiv(rr, 256), 256, 0, s>>>(pivcol.p, D.q0.p, rr, U.n, U.nnz, U.p.p, Uqinv.p);
+        k_register_pivots_only<<<cdiv(rr, 256), 256, 0, s>>>(pc_b, D.q0.p, rr, U.n, U.nnz, U.p.p, Uqinv.p);
       }
       U.n += rr;
       g_launches += 6;
@@ -1100,31 +1189,44 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         Rt.alloc((size_t)Sm0 * ldk);
         Pt.alloc((size_t)nk * ldk);
         k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt.p, ldk);
-        k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt.p, ldk);
-        k_zero_pivot_cols<<<dim3(cdiv(nk, 256), rr), 256, 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk);
+        k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pc_b, rr, kb, nk, Pt.p, ldk);
+        k_zero_pivot_cols<<<dim3(cdiv(nk, 256), rr), 256, 0, s>>>(D.Dt.p, ld, pc_b, rr, kb, nk);
         tick(3, t1);
         if (nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F, cand.p);
         tick(4, t1);
       } else if (nk > 0) {
         const int rr16 = (rr + 15) / 16 * 16;
-        const long long fe = std::min<long long>(std::max(gend, kb), n_local);  // near rows [kb, fe), far rows [fe, n_local)
-        uint32_t *Rt_b = Rt_acc.p + Kacc, *Pt_b = Pt_acc.p + kb * LDK + Kacc;
+        const long long fe = std::min<long long>(std::max(gend, kb), n_local);  // near rows [kb, fe) (stream A), far rows [fe, n_local) (stream B)
+        const int nnear = (int)(fe - kb), nfar = (int)(n_local - fe);
+        uint32_t *Rt_acc = Rt_accs[cur].p, *Pt_acc = Pt_accs[cur].p;
+        uint32_t *Rt_b = Rt_acc + Kacc, *Pt_b = Pt_acc + kb * LDK + Kacc;
         k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, Rt_b, LDK);
         if (rr16 > rr) CK(cudaMemset2DAsync(Rt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, Sm0, s));  // zero pad columns: the pad of Pt may hold anything
-        k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk, Pt_b, LDK);
-        k_zero_pivot_cols<<<dim3(cdiv(nk, 256), rr), 256, 0, s>>>(D.Dt.p, ld, pivcol.p, rr, kb, nk);
-        if (rr16 > rr) CK(cudaMemset2DAsync(Pt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, nk, s));  // and the pad of Pt: no garbage x 0
-        if (Kacc > 0 && fe < n_local) {
-          // the far rows of these pivot columns still miss the pending updates
-          k_gather_rows_ld<<<dim3(cdiv(Kacc, 256), rr), 256, 0, s>>>(Rt_acc.p, LDK, pivcol.p, rr, Kacc, Rsel.p, LDK);
-          gemm_nt(Pt_acc.p + fe * LDK + Kacc, LDK, (int)(n_local - fe), rr, Pt_acc.p + fe * LDK, LDK, Rsel.p, LDK, Kacc, true, F);
-          g_launches += 1;
-          g_tail_stats[1] += 1;
+        if (nnear > 0) {
+          k_gather_pivot_cols_T<<<dim3(cdiv(nnear, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pc_b, rr, kb, nnear, Pt_b, LDK);
+          k_zero_pivot_cols<<<dim3(cdiv(nnear, 256), rr), 256, 0, s>>>(D.Dt.p, ld, pc_b, rr, kb, nnear);
+          if (rr16 > rr) CK(cudaMemset2DAsync(Pt_b + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, nnear, s));  // and the pad of Pt: no garbage x 0
+        }
+        if (nfar > 0) {
+          // the far rows of these pivot columns (they still miss the pending updates: corrected with what is accumulated)
+          order(sA, sB);
+          StreamScope on_b(sB);
+          GemmCtaLimit lim(two_streams ? aux_ctas : 0);
+          uint32_t *Pt_f = Pt_acc + fe * LDK + Kacc;
+          k_gather_pivot_cols_T<<<dim3(cdiv(nfar, 32), cdiv(rr, 32)), dim3(32, 8), 0, sB>>>(D.Dt.p, ld, pc_b, rr, fe, nfar, Pt_f, LDK);
+          k_zero_pivot_cols<<<dim3(cdiv(nfar, 256), rr), 256, 0, sB>>>(D.Dt.p, ld, pc_b, rr, fe, nfar);
+          if (rr16 > rr) CK(cudaMemset2DAsync(Pt_f + rr, (size_t)LDK * 4, 0, (size_t)(rr16 - rr) * 4, nfar, sB));
+          if (Kacc > 0) {
+            k_gather_rows_ld<<<dim3(cdiv(Kacc, 256), rr), 256, 0, sB>>>(Rt_acc, LDK, pc_b, rr, Kacc, Rsel.p, LDK);
+            gemm_nt(Pt_f, LDK, nfar, rr, Pt_acc + fe * LDK, LDK, Rsel.p, LDK, Kacc, true, F);
+            g_launches += 1;
+            g_tail_stats[1] += 1;
+          }
         }
         tick(3, t1);
-        if (fe > kb && nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, (int)(fe - kb), Rt_b, LDK, Pt_b, LDK, rr, true, F, cand.p), g_tail_stats[3] += 1;
+        if (nnear > 0 && nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, nnear, Rt_b, LDK, Pt_b, LDK, rr, true, F, cand.p), g_tail_stats[3] += 1;
         Kacc += rr16;
-        if (Kacc + B16 > kcap || fe >= n_local) flush_far();
+        if (Kacc > kdepth || fe >= n_local) flush_far(gend);  // (accumulators full before my near rows are used up: rare)
         tick(4, t1);
       }
       g_launches += 2;
@@ -1135,7 +1237,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     const long long rows_left = (long long)nrows - (kg + Sn);
     if (opts.tall_skinny && rows_left > 0 && (double)rr < opts.low_rank_ratio * (double)Sn) {
       logf("[echelonize/dense] %d pivots in a block of %d rows: switching to low-rank mode\n", rr, Sn);
-      if (lazy) flush_far();  // every remaining row up to date
+      if (lazy) flush_far(n_local);  // every remaining row up to date (the main stream waits for all of it)
       const long long kb = lb * block_size;  // my remaining rows are [kb, n_local)
       const int nloc = (int)std::max<long long>(0, n_local - kb);
       LowRankShard sh;
@@ -1158,6 +1260,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       break;
     }
   }
+  order(sB, sA);  // whatever the second stream still does is part of this call
   if (prof_ev) {
     sync();
     for (size_t i = 1; i < evs.size(); i++) {
@@ -1170,8 +1273,8 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     for (auto &e_ : evs) cudaEventDestroy(e_.second);
   }
   if (prof)
-    fprintf(stderr, "[dense] rank %d/%d blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs trailing=%.3fs bcast=%.3fs\n", me, NR,
-            (int)tp[5], tp[0], tp[1], tp[2], tp[3], tp[4], tp[6]);
+    fprintf(stderr, "[dense] rank %d/%d blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs near=%.3fs bcast=%.3fs handover=%.3fs (%s)\n", me, NR,
+            (int)tp[5], tp[0], tp[1], tp[2], tp[3], tp[4], tp[6], tp[7], two_streams ? "two streams" : "one stream");
 }
 
 }  // namespace sb

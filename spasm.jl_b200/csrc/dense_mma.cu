@@ -415,6 +415,7 @@ double g_mma_macs = 0;       // modular MACs
 double g_mma_int8_macs = 0;  // int8 MACs issued for them (x L^2: 4, 9 or 16)
 long long g_mma_calls = 0;
 static bool g_mma_disabled = false;
+int g_gemm_cta_limit = 0;  // > 0: the persistent kernel uses at most this many CTAs (the second stream of the dense tail leaves SMs to the first)
 
 // optional timing of the tcgen05 launches (bench.py / SPASM_B200_PROFILE): events are recorded around each launch
 // and only read when the statistics are queried — no host synchronisation on the launch path
@@ -458,7 +459,7 @@ static void launch_limb_gemm(uint32_t *C, long long ldc, int M, int N, const uin
     attr_set = true;
   }
   const int tiles_m = Mp / TILE, tiles_n = Np / TN;
-  const int grid = (int)std::min<long long>((long long)tiles_m * tiles_n, sm_count());
+  const int grid = (int)std::min<long long>((long long)tiles_m * tiles_n, g_gemm_cta_limit > 0 ? std::min(g_gemm_cta_limit, sm_count()) : sm_count());
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
   if (g_mma_timing) {
     if (g_ev_pending.size() >= 4096) mma_collect_timings();

@@ -10,7 +10,9 @@
 namespace sb {
 
 long long g_launches = 0;
-static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_stream = nullptr;  // main stream
+static cudaStream_t g_aux = nullptr;     // second stream, created on first use
+static cudaStream_t g_cur = nullptr;     // override set by StreamScope (nullptr: the main stream)
 static int g_sms = 0;
 static bool g_ready = false;
 // Memory policy.  By default the library holds device memory only while one of its entry points runs: a
@@ -34,7 +36,9 @@ void require_gpu() {
   CK(cudaGetDeviceProperties(&prop, dev));
   if (prop.major < 10) throw Error("spasm_b200: built for sm_100a (B200) only");
   g_sms = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CK(cudaStreamCreateWithPriority(&g_stream, cudaStreamNonBlocking, prio_hi));
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, dev));
   // freed blocks stay cached in the pool WHILE a call runs (thousands of stream-ordered allocations per
@@ -44,9 +48,20 @@ void require_gpu() {
   if (const char *e = getenv("SPASM_B200_KEEP_CACHE")) g_keep_cache = atoi(e) != 0;
   g_ready = true;
 }
-cudaStream_t stream() { return g_stream; }
+cudaStream_t stream() { return g_cur ? g_cur : g_stream; }
+cudaStream_t main_stream() { return g_stream; }
+cudaStream_t aux_stream() {
+  if (!g_aux) {
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&g_aux, cudaStreamNonBlocking, prio_lo));
+  }
+  return g_aux;
+}
+StreamScope::StreamScope(cudaStream_t s) : prev(g_cur) { g_cur = s; }
+StreamScope::~StreamScope() { g_cur = prev; }
 int sm_count() { return g_sms; }
-void sync() { CK(cudaStreamSynchronize(g_stream)); }
+void sync() { CK(cudaStreamSynchronize(stream())); }
 
 // Large blocks (>= 256 MiB: the dense Schur complement, the reserved U, the SpTRSM workspace) are
 // kept in a small best-fit cache across calls: an echelonization of the same shape then allocates
@@ -54,13 +69,18 @@ void sync() { CK(cudaStreamSynchronize(g_stream)); }
 struct BigBlock {
   void *p;
   size_t bytes;
+  cudaStream_t last = nullptr;  // stream whose work used the block last (set when it is parked in the cache)
+  cudaEvent_t ev = nullptr;     // recorded on `last` at that moment: another stream waits for it before reusing the block
 };
 static std::vector<BigBlock> g_big_free;
 static std::vector<BigBlock> g_big_live;
 static const size_t BIG = (size_t)256 << 20;
 
 static void big_trim() {
-  for (auto &b : g_big_free) cudaFreeAsync(b.p, g_stream);
+  for (auto &b : g_big_free) {
+    cudaFreeAsync(b.p, b.last ? b.last : g_stream);
+    if (b.ev) cudaEventDestroy(b.ev);
+  }
   g_big_free.clear();
 }
 
@@ -68,6 +88,7 @@ static void release_cached(size_t keep) {
   if (!g_stream) return;
   big_trim();
   cudaStreamSynchronize(g_stream);
+  if (g_aux) cudaStreamSynchronize(g_aux);
   cudaMemPool_t pool;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -147,21 +168,23 @@ void *dmalloc_bytes(size_t bytes) {
     if (best >= 0) {
       BigBlock b = g_big_free[best];
       g_big_free.erase(g_big_free.begin() + best);
+      if (b.ev && b.last != stream()) CK(cudaStreamWaitEvent(stream(), b.ev, 0));  // its last user ran on another stream
       g_big_live.push_back(b);
       return b.p;
     }
   }
   void *p = nullptr;
-  cudaError_t e = cudaMallocAsync(&p, bytes, g_stream);
+  cudaError_t e = cudaMallocAsync(&p, bytes, stream());
   if (e != cudaSuccess) {  // give the cached blocks and the idle part of the pool back to the driver and retry
     cudaGetLastError();
     big_trim();
     cudaStreamSynchronize(g_stream);
+    if (g_aux) cudaStreamSynchronize(g_aux);
     cudaMemPool_t pool;
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    e = cudaMallocAsync(&p, bytes, g_stream);
+    e = cudaMallocAsync(&p, bytes, stream());
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -182,17 +205,26 @@ void *dmalloc_bytes(size_t bytes) {
                 " MiB; large blocks in use " + std::to_string(live >> 20) + " MiB in " + std::to_string(g_big_live.size()) + "): " +
                 cudaGetErrorString(e));
   }
-  if (bytes >= BIG) g_big_live.push_back({p, bytes});
+  if (bytes >= BIG) {
+    BigBlock b;
+    b.p = p, b.bytes = bytes;
+    g_big_live.push_back(b);
+  }
   return p;
 }
 void dfree(void *p) {
   for (size_t i = 0; i < g_big_live.size(); i++)
     if (g_big_live[i].p == p) {
-      g_big_free.push_back(g_big_live[i]);  // all work is on one stream: reuse is stream-ordered
+      // reuse on the same stream is stream-ordered; a different stream waits for the event recorded here
+      BigBlock b = g_big_live[i];
+      b.last = stream();
+      if (!b.ev && cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) b.ev = nullptr;
+      if (b.ev) cudaEventRecord(b.ev, b.last);
+      g_big_free.push_back(b);
       g_big_live.erase(g_big_live.begin() + i);
       return;
     }
-  cudaFreeAsync(p, g_stream);
+  cudaFreeAsync(p, stream());
 }
 size_t dev_free_bytes() {  // what a new allocation could get: free memory + our own cached blocks
   size_t f = 0, t = 0;
@@ -204,9 +236,9 @@ size_t dev_free_bytes() {  // what a new allocation could get: free memory + our
 // ------------------------------------------------------------------ scans
 void exclusive_scan_i64(const long long *in, long long *out, size_t n) {
   size_t tmp = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, g_stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, stream());
   DBuf<char> t(tmp);
-  cub::DeviceScan::ExclusiveSum(t.p, tmp, in, out, n, g_stream);
+  cub::DeviceScan::ExclusiveSum(t.p, tmp, in, out, n, stream());
 }
 struct I32ToI64 {
   __device__ long long operator()(int v) const { return (long long)v; }
@@ -214,17 +246,17 @@ struct I32ToI64 {
 void exclusive_scan_i32_to_i64(const int *in, long long *out, size_t n_plus_one) {
   cub::TransformInputIterator<long long, I32ToI64, const int *> it(in, I32ToI64());
   size_t tmp = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, out, n_plus_one, g_stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, out, n_plus_one, stream());
   DBuf<char> t(tmp);
-  cub::DeviceScan::ExclusiveSum(t.p, tmp, it, out, n_plus_one, g_stream);
+  cub::DeviceScan::ExclusiveSum(t.p, tmp, it, out, n_plus_one, stream());
 }
 long long reduce_sum_i32(const int *in, size_t n) {
   cub::TransformInputIterator<long long, I32ToI64, const int *> it(in, I32ToI64());
   DBuf<long long> out(1);
   size_t tmp = 0;
-  cub::DeviceReduce::Sum(nullptr, tmp, it, out.p, n, g_stream);
+  cub::DeviceReduce::Sum(nullptr, tmp, it, out.p, n, stream());
   DBuf<char> t(tmp);
-  cub::DeviceReduce::Sum(t.p, tmp, it, out.p, n, g_stream);
+  cub::DeviceReduce::Sum(t.p, tmp, it, out.p, n, stream());
   return fetch(out.p);
 }
 
@@ -236,7 +268,7 @@ static int g_copy_threads = std::max(1, std::min(16, omp_get_num_procs()));
 void download_large(void *dst, const void *src_dev, size_t bytes) {
   const size_t CH = (size_t)128 << 20;
   if (bytes < CH / 2) {
-    CK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream()));
     sync();
     return;
   }
@@ -251,8 +283,8 @@ void download_large(void *dst, const void *src_dev, size_t bytes) {
   const size_t nch = (bytes + CH - 1) / CH;
   auto issue = [&](size_t c) {
     size_t off = c * CH, len = std::min(CH, bytes - off);
-    CK(cudaMemcpyAsync(pin[c & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaEventRecord(ev[c & 1], g_stream));
+    CK(cudaMemcpyAsync(pin[c & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaEventRecord(ev[c & 1], stream()));
   };
   issue(0);
   for (size_t c = 0; c < nch; c++) {
@@ -281,11 +313,11 @@ __global__ void k_to_bal(const uint32_t *in, int *out, long long n, Fp F) {  // 
 }
 
 void convert_to_balanced(const uint32_t *in, int *out, long long n, const Fp &F) {
-  if (n) k_to_bal<<<cdiv(n, 256), 256, 0, g_stream>>>(in, out, n, F);
+  if (n) k_to_bal<<<cdiv(n, 256), 256, 0, stream()>>>(in, out, n, F);
   CK(cudaGetLastError());
 }
 void convert_to_residues(const int *in, uint32_t *out, long long n, const Fp &F) {
-  if (n) k_to_u<<<cdiv(n, 256), 256, 0, g_stream>>>(in, out, n, F);
+  if (n) k_to_u<<<cdiv(n, 256), 256, 0, stream()>>>(in, out, n, F);
   CK(cudaGetLastError());
 }
 
@@ -299,7 +331,7 @@ void upload_csr(const spasm_csr *A, DCsr &D, const Fp &F) {
     D.j.upload(A->j, D.nnz);
     DBuf<int> tmp(D.nnz);
     tmp.upload(A->x, D.nnz);
-    k_to_u<<<cdiv(D.nnz, 256), 256, 0, g_stream>>>(tmp.p, D.x.p, D.nnz, F);
+    k_to_u<<<cdiv(D.nnz, 256), 256, 0, stream()>>>(tmp.p, D.x.p, D.nnz, F);
     CK(cudaGetLastError());
   }
 }
@@ -310,7 +342,7 @@ spasm_csr *download_csr(const DCsr &D, int64_t prime, const Fp &F) {
   if (D.nnz) {
     D.j.download(A->j, D.nnz);
     DBuf<int> tmp(D.nnz);
-    k_to_bal<<<cdiv(D.nnz, 256), 256, 0, g_stream>>>(D.x.p, tmp.p, D.nnz, F);
+    k_to_bal<<<cdiv(D.nnz, 256), 256, 0, stream()>>>(D.x.p, tmp.p, D.nnz, F);
     CK(cudaGetLastError());
     tmp.download(A->x, D.nnz);
   }
@@ -426,20 +458,20 @@ void transpose_csr(const DCsr &A, DCsr &T) {
   T.x.alloc(A.nnz);
   DBuf<int> cnt(A.m + 1);
   cnt.zero();
-  if (A.nnz) k_count_cols<<<cdiv(A.nnz, 256), 256, 0, g_stream>>>(A.j.p, A.nnz, cnt.p);
+  if (A.nnz) k_count_cols<<<cdiv(A.nnz, 256), 256, 0, stream()>>>(A.j.p, A.nnz, cnt.p);
   exclusive_scan_i32_to_i64(cnt.p, T.p.p, A.m + 1);
   if (A.nnz == 0) return;
   cnt.zero();  // now the scatter cursors
-  k_scatter_t<<<cdiv((long long)A.n * 32, 256), 256, 0, g_stream>>>(A.p.p, A.j.p, A.x.p, A.n, T.p.p, cnt.p, T.j.p, T.x.p);
-  k_sort_t_rows_short<<<cdiv((long long)A.m * 32, 256), 256, 0, g_stream>>>(T.p.p, A.m, T.j.p, T.x.p);
+  k_scatter_t<<<cdiv((long long)A.n * 32, 256), 256, 0, stream()>>>(A.p.p, A.j.p, A.x.p, A.n, T.p.p, cnt.p, T.j.p, T.x.p);
+  k_sort_t_rows_short<<<cdiv((long long)A.m * 32, 256), 256, 0, stream()>>>(T.p.p, A.m, T.j.p, T.x.p);
   DBuf<int> flag(A.m + 1), list(std::max(A.m, 1));
   DBuf<long long> pos(A.m + 1);
-  k_flag_long_rows<<<cdiv(A.m + 1, 256), 256, 0, g_stream>>>(T.p.p, A.m, flag.p);
+  k_flag_long_rows<<<cdiv(A.m + 1, 256), 256, 0, stream()>>>(T.p.p, A.m, flag.p);
   exclusive_scan_i32_to_i64(flag.p, pos.p, A.m + 1);
   const int nlong = (int)fetch(pos.p + A.m);
   if (nlong > 0) {
-    k_compact_long<<<cdiv(A.m, 256), 256, 0, g_stream>>>(flag.p, pos.p, A.m, list.p);
-    k_sort_t_rows_long<<<std::min(nlong, g_sms * 8), 256, 0, g_stream>>>(T.p.p, list.p, nlong, T.j.p, T.x.p);
+    k_compact_long<<<cdiv(A.m, 256), 256, 0, stream()>>>(flag.p, pos.p, A.m, list.p);
+    k_sort_t_rows_long<<<std::min(nlong, g_sms * 8), 256, 0, stream()>>>(T.p.p, list.p, nlong, T.j.p, T.x.p);
   }
   CK(cudaGetLastError());
   g_launches += 6;
@@ -462,7 +494,7 @@ extern "C" void spasm_b200_set_cache(int keep) {
 extern "C" long long spasm_b200_cached_bytes(void) {
   long long tot = 0;
   for (auto &b : sb::g_big_free) tot += (long long)b.bytes;
-  if (sb::g_stream) {
+  if (sb::stream()) {
     cudaMemPool_t pool;
     int dev = 0;
     cudaGetDevice(&dev);
