@@ -45,6 +45,10 @@ void require_gpu() {
   // echelonization); ApiCall gives everything back to the driver when the outermost call returns.
   uint64_t thresh = UINT64_MAX;
   CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  // never let an allocation on one stream wait for the other stream's queue in order to reuse a block freed there
+  // (the dense tail's main stream would stall behind the deferred updates of the second stream)
+  int no = 0;
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &no));
   if (const char *e = getenv("SPASM_B200_KEEP_CACHE")) g_keep_cache = atoi(e) != 0;
   g_ready = true;
 }
@@ -162,13 +166,22 @@ static void host_big_trim() {
 
 void *dmalloc_bytes(size_t bytes) {
   if (bytes >= BIG) {
+    // best fit among the blocks this stream may take without waiting: its own (stream order), or another stream's
+    // whose last use is already over (a block freed by the second stream must not make the main stream wait for
+    // everything the second stream still has queued)
     int best = -1;
-    for (int i = 0; i < (int)g_big_free.size(); i++)
-      if (g_big_free[i].bytes >= bytes && g_big_free[i].bytes <= bytes + bytes / 4 && (best < 0 || g_big_free[i].bytes < g_big_free[best].bytes)) best = i;
+    for (int i = 0; i < (int)g_big_free.size(); i++) {
+      const BigBlock &c = g_big_free[i];
+      if (c.bytes < bytes || c.bytes > bytes + bytes / 4) continue;
+      if (c.last != nullptr && c.last != stream() && c.ev != nullptr && cudaEventQuery(c.ev) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      if (best < 0 || c.bytes < g_big_free[best].bytes) best = i;
+    }
     if (best >= 0) {
       BigBlock b = g_big_free[best];
       g_big_free.erase(g_big_free.begin() + best);
-      if (b.ev && b.last != stream()) CK(cudaStreamWaitEvent(stream(), b.ev, 0));  // its last user ran on another stream
       g_big_live.push_back(b);
       return b.p;
     }
