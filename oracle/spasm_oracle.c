@@ -1532,6 +1532,172 @@ static void echelonize_dense(const struct spasm_csr *A, const int *p, int n, con
   free(qpos);
 }
 
+/* ---- dense tail WITH L (prototype spasm_ffpack_LU, src/SpaSM.jl:806-812; SURVEY.md A.7 "or ffpack_LU when L").
+ * FFPACK's PLUQ is not available here, so the restatement fixes ONE elimination order (parity unpinned, like the rest
+ * of the dense tail) and the CUDA library reproduces it bit for bit:
+ *   - the dense Schur complement D of all remaining rows w.r.t. the structural U is built once; the multipliers on
+ *     the structural pivots go to L as in spasm_schur (A.6);
+ *   - blocks of dense_block_size rows, in order.  Inside a block the free columns are scanned left to right; the
+ *     pivot of a column is the FIRST row of the block that is not a pivot yet and is non-zero there; that row is
+ *     normalised and becomes a row of U AS IT IS (row echelon, not reduced: later pivots are not eliminated from
+ *     it — this is what keeps L triangular); the column is eliminated from the rows of the block that are not pivots
+ *     yet, the multiplier going to L; the pivot value itself is the diagonal entry of L;
+ *   - every later row is then eliminated against the block's pivots in the same order (multipliers to L).
+ * A[p] = L.U holds with L lower-trapezoidal in the order of Lp, which is all spasm_solve needs. */
+static void echelonize_dense_L(const struct spasm_csr *A, const int *p, int n, const int *p_in, struct spasm_lu *fact,
+                               struct echelonize_opts *opts) {
+  const int m = A->m;
+  struct spasm_csr *U = fact->U;
+  struct spasm_triplet *L = fact->Ltmp;
+  int *Uqinv = fact->qinv;
+  int *Lp = fact->p;
+  const struct spasm_field_struct *Fq = A->field;
+  const int block = opts->dense_block_size > 0 ? opts->dense_block_size : 1000;
+  const int Sm0 = m - U->n;
+  if (Sm0 == 0 || n == 0) return;
+  int *q = spasm_malloc((i64)m * sizeof(int));
+  int *qpos = spasm_malloc((i64)m * sizeof(int));
+  int c = 0;
+  for (int j = 0; j < m; j++) {
+    qpos[j] = -1;
+    if (Uqinv[j] < 0) {
+      q[c] = j;
+      qpos[j] = c++;
+    }
+  }
+  assert(c == Sm0);
+  spasm_ZZp *D = spasm_calloc((i64)n * Sm0, sizeof(spasm_ZZp));
+  int *orig = spasm_malloc((i64)n * sizeof(int));
+  {
+    spasm_ZZp *x = spasm_malloc((i64)m * sizeof(*x));
+    int *xj = spasm_calloc(3 * (i64)m, sizeof(int));
+    int *lc = spasm_malloc((i64)m * sizeof(int));
+    for (int k = 0; k < n; k++) { /* sequential: the entries of L are appended row by row */
+      const int i = p[k];
+      orig[k] = (p_in != NULL) ? p_in[i] : i;
+      int top = spasm_sparse_triangular_solve(U, A, i, xj, x, Uqinv);
+      int nl = 0;
+      for (int px = top; px < m; px++) {
+        int j = xj[px];
+        if (Uqinv[j] < 0)
+          D[(i64)k * Sm0 + qpos[j]] = x[j];
+        else if (x[j] != 0)
+          lc[nl++] = Uqinv[j];
+      }
+      sort_ints(lc, nl);
+      for (int t = 0; t < nl; t++) spasm_add_entry(L, orig[k], lc[t], x[U->j[U->p[lc[t]]]]);
+    }
+    free(x);
+    free(xj);
+    free(lc);
+  }
+  logprintf("[echelonize/dense] dense schur complement %d x %d built (with L)\n", n, Sm0);
+  char *dead = spasm_calloc(Sm0, 1); /* columns pivoted by an earlier block: zero on every remaining row */
+  char *used = spasm_malloc(block);
+  int *prow = spasm_malloc((i64)block * sizeof(int)), *pcol = spasm_malloc((i64)block * sizeof(int));
+  int processed = 0;
+  while (processed < n && U->n < m) {
+    const int Sn = (n - processed < block) ? n - processed : block;
+    logprintf("[echelonize/dense] processing dense schur complement of dimension %d x %d; block size=%d\n", n - processed, m - U->n, block);
+    spasm_ZZp *S = D + (i64)processed * Sm0;
+    memset(used, 0, Sn);
+    int rr = 0;
+    const int ubase = U->n;
+    for (int cc = 0; cc < Sm0 && rr < Sn; cc++) {
+      if (dead[cc]) continue;
+      int r = -1;
+      for (int t = 0; t < Sn; t++)
+        if (!used[t] && S[(i64)t * Sm0 + cc] != 0) {
+          r = t;
+          break;
+        }
+      if (r < 0) continue;
+      used[r] = 1;
+      spasm_ZZp *Ur = S + (i64)r * Sm0;
+      const spasm_ZZp v = Ur[cc];
+      const spasm_ZZp beta = spasm_ZZp_inverse(Fq, v);
+      for (int k = 0; k < Sm0; k++)
+        if (Ur[k] != 0) Ur[k] = spasm_ZZp_mul(Fq, beta, Ur[k]);
+      prow[rr] = r, pcol[rr] = cc;
+      Lp[ubase + rr] = orig[processed + r];
+      spasm_add_entry(L, orig[processed + r], ubase + rr, v);
+      /* the rows of the block that are not pivots yet (sequential over rows: L entries in a fixed order) */
+#pragma omp parallel for schedule(static)
+      for (int t = 0; t < Sn; t++) {
+        if (used[t]) continue;
+        spasm_ZZp *row = S + (i64)t * Sm0;
+        const spasm_ZZp l = row[cc];
+        if (l == 0) continue;
+        const spasm_ZZp ml = spasm_ZZp_sub(Fq, 0, l);
+        for (int k = 0; k < Sm0; k++)
+          if (Ur[k] != 0) row[k] = spasm_ZZp_axpy(Fq, ml, Ur[k], row[k]);
+        row[cc] = l; /* kept for the L entry below (the column is dead from now on) */
+      }
+      for (int t = 0; t < Sn; t++)
+        if (!used[t] && S[(i64)t * Sm0 + cc] != 0) {
+          spasm_add_entry(L, orig[processed + t], ubase + rr, S[(i64)t * Sm0 + cc]);
+          S[(i64)t * Sm0 + cc] = 0;
+        }
+      rr++;
+    }
+    /* the pivot rows go to U in pivot order: (pivot column, 1) first, then the other entries by increasing column */
+    for (int s_ = 0; s_ < rr; s_++) {
+      const spasm_ZZp *row = S + (i64)prow[s_] * Sm0;
+      i64 cntnz = 0;
+      for (int k = 0; k < Sm0; k++)
+        if (row[k] != 0) cntnz++;
+      csr_ensure_room(U, spasm_nnz(U) + cntnz);
+      i64 unz = U->p[U->n];
+      const int jp = q[pcol[s_]];
+      Uqinv[jp] = U->n;
+      U->j[unz] = jp;
+      U->x[unz] = 1;
+      unz++;
+      for (int k = 0; k < Sm0; k++) {
+        if (k == pcol[s_] || row[k] == 0) continue;
+        U->j[unz] = q[k];
+        U->x[unz] = row[k];
+        unz++;
+      }
+      U->n += 1;
+      U->p[U->n] = unz;
+    }
+    for (int s_ = 0; s_ < rr; s_++) dead[pcol[s_]] = 1;
+    processed += Sn;
+    /* every later row against the block's pivots, in pivot order; multipliers recorded per row, appended in row order */
+    const i64 later = n - processed;
+    if (later > 0 && rr > 0) { /* (also when U just reached full column rank: the multipliers of the rows still to come belong to L) */
+      spasm_ZZp *mult = spasm_malloc(later * (i64)rr * sizeof(spasm_ZZp));
+#pragma omp parallel for schedule(dynamic, 8)
+      for (i64 t = 0; t < later; t++) {
+        spasm_ZZp *row = D + (processed + t) * Sm0;
+        for (int s_ = 0; s_ < rr; s_++) {
+          const spasm_ZZp l = row[pcol[s_]];
+          mult[t * rr + s_] = l;
+          if (l == 0) continue;
+          const spasm_ZZp ml = spasm_ZZp_sub(Fq, 0, l);
+          const spasm_ZZp *Ur = S + (i64)prow[s_] * Sm0;
+          for (int k = 0; k < Sm0; k++)
+            if (Ur[k] != 0) row[k] = spasm_ZZp_axpy(Fq, ml, Ur[k], row[k]);
+        }
+      }
+      for (i64 t = 0; t < later; t++)
+        for (int s_ = 0; s_ < rr; s_++)
+          if (mult[t * rr + s_] != 0) spasm_add_entry(L, orig[processed + t], ubase + s_, mult[t * rr + s_]);
+      free(mult);
+    }
+    logprintf("[echelonize/dense] block done: %d new pivots, rank %d\n", rr, U->n);
+  }
+  free(dead);
+  free(used);
+  free(prow);
+  free(pcol);
+  free(orig);
+  free(D);
+  free(q);
+  free(qpos);
+}
+
 /* counter-based random numbers for the low-rank mode (no sequential state: the CUDA code evaluates the
  * same function in parallel) */
 static u64 lowrank_hash(u64 blk, u64 t, u64 k) {
@@ -1712,7 +1878,9 @@ struct spasm_lu *spasm_echelonize(const struct spasm_csr *A, struct echelonize_o
     int rem_rows = n - npiv;
     double aspect_ratio = (double)rem_rows / m;
     logprintf("[echelonize] finishing; density = %.3f; aspect ratio = %.1f\n", density, aspect_ratio);
-    if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
+    if (opts->L && opts->enable_dense && (go_dense || density > opts->sparsity_threshold))
+      echelonize_dense_L(cur, p + npiv, rem_rows, p_in, fact, opts);
+    else if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
       echelonize_GPLU(cur, p + npiv, rem_rows, p_in, fact, opts);
     else if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio)
       echelonize_dense_lowrank(cur, p + npiv, rem_rows, fact, opts);

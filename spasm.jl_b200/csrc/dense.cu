@@ -349,7 +349,8 @@ template <bool SMALL>
 __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, int Sn, int wc, long long ldw, int c0,
                                                       int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
                                                       uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
-                                                      const unsigned char *__restrict__ colflag, const int *__restrict__ cand, Fp F) {
+                                                      const unsigned char *__restrict__ colflag, const int *__restrict__ cand, Fp F,
+                                                      uint32_t *__restrict__ GjT, long long ldg, int *__restrict__ pividx) {
   __shared__ int red[32];
   __shared__ int s_piv;
   __shared__ uint32_t prow[WMAX], gprow[PB];
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, 
         pivcol[npiv] = cand[c0 + cc];
         tilepiv[found] = best;
         Gc[(long long)found * ldw + best] = 1;
+        if (pividx) pividx[best] = npiv;
       }
     }
     __syncthreads();
@@ -403,6 +405,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, 
       if (r == pr) continue;
       const uint32_t f = Wt[(long long)cc * ldw + r];
       if (f == 0) continue;
+      if (GjT != nullptr && pividx[r] >= 0) GjT[(long long)npiv * ldg + pividx[r]] = f;  // what this pivot removes from an earlier pivot row
       const uint32_t nf = negmod(f, F);
       for (int k = cc; k < wc; k++) {
         uint32_t *w = Wt + (long long)k * ldw + r;
@@ -424,7 +427,8 @@ __global__ void __launch_bounds__(1024) k_tile_gauss(uint32_t *__restrict__ Wt, 
 __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long ldw,
                                                            int *__restrict__ ispiv, int *__restrict__ pivrow, int *__restrict__ pivcol,
                                                            uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
-                                                           const int *__restrict__ cand, Fp F) {
+                                                           const int *__restrict__ cand, Fp F, uint32_t *__restrict__ GjT, long long ldg,
+                                                           int *__restrict__ pividx) {
   extern __shared__ unsigned short tile[];  // [32 + PB][SP]
   __shared__ int red[32];
   __shared__ int s_piv;
@@ -449,6 +453,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
   }
   for (int s = 0; s < PB; s++) tile[(32 + s) * SP + r] = 0;
   int my_ispiv = live ? ispiv[r] : 1;
+  int my_pividx = (live && pividx != nullptr) ? pividx[r] : -1;
   int npiv = ctl->npiv, found = 0, cc = 0;
   __syncthreads();
   for (; cc < wc && found < PB && npiv < Sn; cc++) {
@@ -471,6 +476,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
       pivcol[npiv] = cand[c0 + cc];
       tilepiv[found] = r;
       tile[(32 + found) * SP + r] = 1;
+      if (pividx != nullptr) pividx[r] = npiv, my_pividx = npiv;
     }
     __syncthreads();
     if (r < 32 + PB) {
@@ -491,6 +497,7 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
       } else {
         const uint32_t f = tile[cc * SP + r];
         if (f != 0) {
+          if (GjT != nullptr && my_pividx >= 0) GjT[(long long)npiv * ldg + my_pividx] = f;
           const uint32_t nf = F.p - f;
           for (int k = cc; k < wc; k++) {
             uint32_t t = (uint32_t)tile[k * SP + r] + mulmod<true>(nf, prow[k], F);
@@ -525,7 +532,7 @@ static constexpr int GRP = 128;  // rows (= threads) per CTA
 __global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(GRP)
 k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long ldw, int *__restrict__ ispiv, int *__restrict__ pivrow,
                      int *__restrict__ pivcol, uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
-                     const int *__restrict__ cand, Fp F) {
+                     const int *__restrict__ cand, Fp F, uint32_t *__restrict__ GjT, long long ldg, int *__restrict__ pividx) {
   namespace cgx = cooperative_groups;
   cgx::cluster_group cluster = cgx::this_cluster();
   __shared__ unsigned short tile[32 + PB][GRP];
@@ -553,6 +560,7 @@ k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long
   }
   for (int sx = 0; sx < PB; sx++) tile[32 + sx][tid] = 0;
   int my_ispiv = live ? ispiv[r] : 1;
+  int my_pividx = (live && pividx != nullptr) ? pividx[r] : -1;
   int npiv = npiv0, found = 0, cc = 0, step = 0;
   cluster.sync();
   for (; cc < wc && found < PB && npiv < Sn; cc++) {
@@ -584,6 +592,7 @@ k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long
         pivcol[npiv] = cand[c0 + cc];
         tilepiv[found] = r;
         tile[32 + found][tid] = 1;
+        if (pividx != nullptr) pividx[r] = npiv, my_pividx = npiv;
       }
       __syncthreads();
       if (tid < 32 + PB) {
@@ -607,6 +616,7 @@ k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long
       } else {
         const uint32_t f = tile[cc][tid];
         if (f != 0) {
+          if (GjT != nullptr && my_pividx >= 0) GjT[(long long)npiv * ldg + my_pividx] = f;
           const uint32_t nf = F.p - f;
           for (int k = cc; k < wc; k++) {
             uint32_t t = (uint32_t)tile[k][tid] + mulmod<true>(nf, prow[k], F);
@@ -783,8 +793,43 @@ __global__ void k_mark_cols(const int *__restrict__ pivcol, int rr, unsigned cha
 }
 
 // cand[0:Sm0) = the columns that are not pivots of an earlier panel (those are zero on this panel), increasing
+// ---- with-L mode.  The panel is factored in REDUCED form as always (R = reduced rows); the row echelon form the
+// factorisation A = L.U needs is recovered from the Jordan multipliers G (strictly upper: G[s][s'] = what pivot s' removed
+// from pivot row s):  R = (I - G).Ub  =>  Ub = U_M.R  with  U_M = (I - G)^-1  (= the pivot columns of Ub, unit upper
+// triangular), and the multipliers of ANY row on the panel's pivots are  (its entries on the pivot columns).(I - G).
+// U_M[s][j], one thread per column j, by back substitution:  U_M[s][j] = sum_{s < t <= j} G[s][t] . U_M[t][j]
+template <bool SMALL>
+__global__ void k_um_from_gT(const uint32_t *__restrict__ GjT, long long ldg, int rr, uint32_t *__restrict__ UM, long long ldu, Fp F) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= rr) return;
+  for (int s = rr - 1; s > j; s--) UM[(long long)s * ldu + j] = 0;
+  UM[(long long)j * ldu + j] = 1;
+  for (int s = j - 1; s >= 0; s--) {
+    uint32_t acc = 0;
+    for (int t = s + 1; t <= j; t++) {
+      const uint32_t g = GjT[(long long)t * ldg + s];
+      if (g) acc = addmod(acc, mulmod<SMALL>(g, UM[(long long)t * ldu + j], F), F);
+    }
+    UM[(long long)s * ldu + j] = acc;
+  }
+}
+// in place:  GjT -> (I - G)^T   (row s', column s:  1 on the diagonal, -G[s][s'] below it, 0 above)
+__global__ void k_make_uinvT(uint32_t *__restrict__ GjT, long long ldg, int rr, uint32_t p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, s2 = blockIdx.y;
+  if (s >= rr || s2 >= rr) return;
+  uint32_t *q = GjT + (long long)s2 * ldg + s;
+  const uint32_t g = *q;
+  *q = (s == s2) ? 1u : (s < s2 ? (g ? p - g : 0u) : 0u);
+}
+__global__ void k_fill_int(int *a, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// GjT / pividx (optional, with-L mode): GjT[s'][s] = what pivot s' removed from the earlier pivot row s (Gauss-JORDAN
+// multipliers; zero-initialised by the caller), pividx[row] = index of the pivot that row holds (-1-initialised)
 static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int Sm0, long long k0, int Sn, uint32_t *T, DBuf<int> &ispiv,
-                        DBuf<int> &pivrow, DBuf<int> &pivcol, const Fp &F) {
+                        DBuf<int> &pivrow, DBuf<int> &pivcol, const Fp &F, uint32_t *GjT = nullptr, long long ldg = 0, int *pividx = nullptr) {
   cudaStream_t s = stream();
   const long long ldw = ((long long)Sn + 31) / 32 * 32;
   DBuf<uint32_t> Wt((size_t)WMAX * ldw), Gc((size_t)PB * ldw), Tp((size_t)PB * Sn), Agather((size_t)WMAX * Sn);
@@ -818,9 +863,9 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
     for (int g = 0; g < 8; g++) {
       k_wtile<true><<<dim3(cdiv(Sn, 32), 4, WKS), 256, 0, s>>>(Dt + k0, ld, T, Sn, Sm0, ctl.p, cand, Wt.p, ldw, F);
       if (use_cluster)
-        k_tile_gauss_cluster<<<GC, GRP, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
+        k_tile_gauss_cluster<<<GC, GRP, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F, GjT, ldg, pividx);
       else
-        k_tile_gauss_smem<<<1, 1024, gsm, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F);
+        k_tile_gauss_smem<<<1, 1024, gsm, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F, GjT, ldg, pividx);
       apply_T();
     }
     CK(cudaGetLastError());
@@ -837,9 +882,9 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
     gemm_nt(Wt.p, ldw, wc, Sn, Agather.p, Sn, T, Sn, Sn, false, F);
     k_col_flags<<<wc, 256, 0, s>>>(Wt.p, ldw, Sn, ispiv.p, colflag.p);
     if (F.small)
-      k_tile_gauss<true><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, cand, F);
+      k_tile_gauss<true><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, cand, F, GjT, ldg, pividx);
     else
-      k_tile_gauss<false><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, cand, F);
+      k_tile_gauss<false><<<1, 1024, 0, s>>>(Wt.p, Sn, wc, ldw, c0, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, colflag.p, cand, F, GjT, ldg, pividx);
     apply_T();
     CK(cudaGetLastError());
     g_launches += 5;
@@ -886,8 +931,7 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
   if (block_size <= 0) block_size = 1000;
   if (nrows == 0 || A.m == U.n) return;
   const Dist &dd = dist();
-  const int me = dd.rank, NR = dd.nranks;
-  const bool emit_rows = (me == 0);
+  const int me = opts.lsink ? 0 : dd.rank, NR = opts.lsink ? 1 : dd.nranks;
   double t0 = spasm_wtime();
   // ---- my rows
   DBuf<int> rows_local;
@@ -906,9 +950,22 @@ void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U,
     my_rows = rows_local.p;
   }
   DenseSchur D;
-  build_dense_schur(A, my_rows, n_local, U, Uqinv.p, F, D);
+  if (opts.lsink) {
+    // with L: the multipliers on the structural pivots are part of the result (as in spasm_schur)
+    build_dense_schur_raw(A.p.p, A.j.p, A.x.p, A.m, my_rows, n_local, U, Uqinv.p, F, D, true);
+    if (U.n > 0 && n_local > 0) {
+      DBuf<int> iota(n_local), lcnt(n_local), oj;
+      DBuf<unsigned long long> loffs(n_local);
+      DBuf<uint32_t> ox;
+      k_iota2<<<cdiv(n_local, 256), 256, 0, s>>>(iota.p, n_local);
+      dense_rows_to_sparse(D.Vp.p, D.ldv, U.n, nullptr, n_local, iota.p, 0, lcnt.p, loffs.p, 0ULL, oj, ox);
+      opts.lsink->rows(0, n_local, 0, lcnt.p, loffs.p, oj.p, ox.p);
+    }
+    D.Vp = DBuf<uint32_t>();
+  } else
+    build_dense_schur(A, my_rows, n_local, U, Uqinv.p, F, D);
   logf("[echelonize/dense] dense schur complement %d x %d built in %.2fs (%d levels)%s\n", nrows, D.Sm0, spasm_wtime() - t0, D.levels,
-       NR > 1 ? " [sharded]" : "");
+       NR > 1 ? " [sharded]" : (opts.lsink ? " (with L)" : ""));
   dense_tail_core(D, nrows, n_local, A.m, U, Uqinv, F, block_size, opts);
 }
 
@@ -917,7 +974,8 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
                      const TailOpts &opts) {
   cudaStream_t s = stream();
   const Dist &dd = dist();
-  const int me = dd.rank, NR = dd.nranks;
+  LSink *const ls = opts.lsink;  // with-L mode: row echelon form + multipliers; every rank computes the whole tail
+  const int me = ls ? 0 : dd.rank, NR = ls ? 1 : dd.nranks;
   // who materialises the rows of U of panel b: rank 0 (complete factor on rank 0) or the panel's owner (sharded factor)
   auto emits = [&](long long b) { return NR == 1 || (dd.shard_factor ? panel_owner(b, NR) == me : me == 0); };
   const bool emit_rows = NR == 1 || dd.shard_factor || me == 0;  // this rank materialises at least some panels
@@ -1000,7 +1058,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   // A hands rows to B never; B hands the next `group` panels to A at a flush (one event).  Two sets of accumulators:
   // while B applies one, A already fills the other.  B's tensor-core launches leave some SMs to A's (small, latency
   // bound) kernels, which would otherwise queue behind a persistent kernel that owns every SM's shared memory.
-  const bool two_streams = lazy && getenv("SPASM_B200_ONE_STREAM") == nullptr;
+  const bool two_streams = lazy && ls == nullptr && getenv("SPASM_B200_ONE_STREAM") == nullptr;
   const int nsets = two_streams ? 2 : 1;
   cudaStream_t sA = s, sB = two_streams ? aux_stream() : s;
   int aux_ctas = sm_count() - (NR > 1 ? 48 : 32);  // (with several ranks the second stream has 1/N of the work: the critical path gets more room)
@@ -1088,6 +1146,26 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     Kacc = 0;
   };
   long long pc_off = 0;
+  // with-L mode buffers
+  DBuf<uint32_t> GjT, UM, PanelPt, Ub, RtL, LT;
+  DBuf<int> pividx, iota_rows, lcnt;
+  DBuf<unsigned long long> loffs;
+  const long long ldlt = ((long long)std::max(Bmax, n_local) + 63) / 64 * 64;
+  if (ls) {
+    GjT.alloc((size_t)Bmax * Bmax), UM.alloc((size_t)Bmax * Bmax), PanelPt.alloc((size_t)Bmax * B16), Ub.alloc((size_t)Bmax * Sm0);
+    RtL.alloc((size_t)Sm0 * B16), LT.alloc((size_t)B16 * ldlt), pividx.alloc(Bmax), iota_rows.alloc(std::max(n_local, Bmax));
+    lcnt.alloc(std::max(n_local, Bmax)), loffs.alloc(std::max(n_local, Bmax));
+    k_iota2<<<cdiv(std::max(n_local, Bmax), 256), 256, 0, s>>>(iota_rows.p, std::max(n_local, Bmax));
+  }
+  // multipliers of the tail rows [row0, row0 + nr) on the rr pivots of this panel:  LT[s][k] = sum_s' (I - G)^T[s][s'] . cols[k][s']
+  auto emit_L = [&](const uint32_t *cols, long long ldcols, int row0, int nr, int rr_, int ubase) {
+    if (nr <= 0 || rr_ <= 0) return;
+    gemm_nt(LT.p, ldlt, rr_, nr, GjT.p, Bmax, cols, ldcols, rr_, false, F);
+    DBuf<int> oj;
+    DBuf<uint32_t> ox;
+    dense_rows_to_sparse(LT.p, ldlt, rr_, nullptr, nr, iota_rows.p, 0, lcnt.p, loffs.p, 0ULL, oj, ox);
+    ls->rows(row0, nr, ubase, lcnt.p, loffs.p, oj.p, ox.p);
+  };
   for (long long b = 0; b < nb; b++) {
     const long long kg = b * block_size;
     const int Sn = (int)std::min<long long>(block_size, nrows - kg);
@@ -1114,13 +1192,33 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       const long long k0 = lb * block_size;
       DBuf<int> pc_tmp;
       // candidate columns of this panel: everything that is not a pivot of an earlier panel
-      rr = panel_factor(D.Dt.p, ld, cand.p, nlive, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F);
+      if (ls) {
+        CK(cudaMemsetAsync(GjT.p, 0, (size_t)Bmax * Bmax * sizeof(uint32_t), s));
+        k_fill_int<<<cdiv(Bmax, 256), 256, 0, s>>>(pividx.p, Bmax, -1);
+      }
+      rr = panel_factor(D.Dt.p, ld, cand.p, nlive, k0, Sn, T.p, ispiv, pivrow, pc_tmp, F, ls ? GjT.p : nullptr, Bmax, ls ? pividx.p : nullptr);
       if (rr > 0) CK(cudaMemcpyAsync(pc_b, pc_tmp.p, (size_t)rr * sizeof(int), cudaMemcpyDeviceToDevice, s));
       tick(0, t1);
       if (rr > 0) {
         // reduced rows  R[s][c] = sum_t T[pivrow[s]][t] * Dt[c][k0+t]
         k_gather_T_rows<<<dim3(cdiv(Sn, 256), rr), 256, 0, s>>>(T.p, Sn, pivrow.p, nullptr, rr, Tsel.p);
         gemm_nt(R.p, Sm0, rr, Sm0, Tsel.p, Sn, D.Dt.p + k0, ld, Sn, false, F);
+      }
+      if (ls && rr > 0) {
+        // ---- with L: U_M = (I - G)^-1, then GjT <- (I - G)^T; the panel's own multipliers; the row echelon rows Ub = U_M . R
+        if (F.small)
+          k_um_from_gT<true><<<cdiv(rr, 64), 64, 0, s>>>(GjT.p, Bmax, rr, UM.p, Bmax, F);
+        else
+          k_um_from_gT<false><<<cdiv(rr, 64), 64, 0, s>>>(GjT.p, Bmax, rr, UM.p, Bmax, F);
+        k_make_uinvT<<<dim3(cdiv(rr, 256), rr), 256, 0, s>>>(GjT.p, Bmax, rr, F.p);
+        k_gather_pivot_cols_T<<<dim3(cdiv(Sn, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pc_b, rr, k0, Sn, PanelPt.p, B16);
+        emit_L(PanelPt.p, B16, (int)kg, Sn, rr, U.n);
+        k_transpose_u32<<<dim3(cdiv(Sm0, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(R.p, Sm0, rr, Sm0, RtL.p, B16);
+        gemm_nt(Ub.p, Sm0, rr, Sm0, UM.p, Bmax, RtL.p, B16, rr, false, F);
+        std::vector<int> hpr(rr);
+        pivrow.download(hpr.data(), rr);
+        sync();
+        ls->pivots(U.n, hpr.data(), rr, (int)kg);
       }
       tick(1, t1);
       lb++;
@@ -1163,12 +1261,13 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         // append to U: (q0[pivcol[s]], 1) then the other nonzeros by increasing column
         DBuf<int> cnt(rr + 1);
         DBuf<long long> rpos(rr + 1);
-        k_count_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, rr, cnt.p);
+        const uint32_t *Urows = ls ? Ub.p : R.p;  // with L: the rows as they were when they became pivots (row echelon form)
+        k_count_rows<<<rr, 256, 0, s>>>(Urows, Sm0, Sm0, ident.p, rr, cnt.p);
         exclusive_scan_i32_to_i64(cnt.p, rpos.p, rr + 1);
         const long long add = fetch(rpos.p + rr);
         if (sink && (size_t)(U.nnz + add) > U.j.n) sink->wait_all();  // the arrays are about to move
         csr_reserve(U, U.nnz + add, U.n + rr);
-        k_write_rows<<<rr, 256, 0, s>>>(R.p, Sm0, Sm0, ident.p, pc_b, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
+        k_write_rows<<<rr, 256, 0, s>>>(Urows, Sm0, Sm0, ident.p, pc_b, D.q0.p, rpos.p, U.nnz, U.n, U.p.p, U.j.p, U.x.p, Uqinv.p);
         CK(cudaGetLastError());
         if (sink) {
           convert_to_balanced(U.x.p + U.nnz, (int *)U.x.p + U.nnz, add, F);
@@ -1192,6 +1291,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
         k_gather_pivot_cols_T<<<dim3(cdiv(nk, 32), cdiv(rr, 32)), dim3(32, 8), 0, s>>>(D.Dt.p, ld, pc_b, rr, kb, nk, Pt.p, ldk);
         k_zero_pivot_cols<<<dim3(cdiv(nk, 256), rr), 256, 0, s>>>(D.Dt.p, ld, pc_b, rr, kb, nk);
         tick(3, t1);
+        if (ls) emit_L(Pt.p, ldk, (int)kb, nk, rr, U.n - rr);
         if (nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, nk, Rt.p, ldk, Pt.p, ldk, rr, true, F, cand.p);
         tick(4, t1);
       } else if (nk > 0) {
@@ -1224,6 +1324,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
           }
         }
         tick(3, t1);
+        if (ls) emit_L(Pt_b, LDK, (int)kb, nk, rr, U.n - rr);  // (one stream in this mode: the far rows' multipliers are corrected by now)
         if (nnear > 0 && nlive > 0) gemm_nt(D.Dt.p + kb, ld, nlive, nnear, Rt_b, LDK, Pt_b, LDK, rr, true, F, cand.p), g_tail_stats[3] += 1;
         Kacc += rr16;
         if (Kacc > kdepth || fe >= n_local) flush_far(gend);  // (accumulators full before my near rows are used up: rare)
@@ -1235,7 +1336,7 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
     if (U.n == m_total) break;
     // ---- a block far below full rank hands the rows still to come to the low-rank mode
     const long long rows_left = (long long)nrows - (kg + Sn);
-    if (opts.tall_skinny && rows_left > 0 && (double)rr < opts.low_rank_ratio * (double)Sn) {
+    if (opts.tall_skinny && ls == nullptr && rows_left > 0 && (double)rr < opts.low_rank_ratio * (double)Sn) {
       logf("[echelonize/dense] %d pivots in a block of %d rows: switching to low-rank mode\n", rr, Sn);
       if (lazy) flush_far(n_local);  // every remaining row up to date (the main stream waits for all of it)
       const long long kb = lb * block_size;  // my remaining rows are [kb, n_local)

@@ -38,10 +38,20 @@ int gemm_max_k(const Fp &F);
 
 // the knobs of EchelonizeOpts (src/SpaSM.jl:325-343) the dense loop looks at: a block of Sn rows that yields fewer than
 // low_rank_ratio * Sn pivots hands the remaining rows to the low-rank mode
+// with-L mode of the dense tail (replaces spasm_ffpack_LU, src/SpaSM.jl:806): receives the multipliers and the row permutation
+struct LSink {
+  virtual ~LSink() {}
+  // sparse rows of L for the tail rows [row0, row0 + nrows) (positions in the tail's row list): row i has cnt[i] entries
+  // (label, value) starting at offs[i] in (oj, ox); the entry belongs to column ubase + label of L.  Device pointers.
+  virtual void rows(int row0, int nrows, int ubase, const int *cnt, const unsigned long long *offs, const int *oj, const uint32_t *ox) = 0;
+  // U rows [ubase, ubase + rr) were produced by the tail rows row0 + pivrow[s] (host array)
+  virtual void pivots(int ubase, const int *pivrow, int rr, int row0) = 0;
+};
 struct TailOpts {
   bool tall_skinny = false;
   double low_rank_ratio = 0.5;
   double start_weight = -1;
+  LSink *lsink = nullptr;  // not null: row echelon form + L instead of the reduced form (every rank computes everything)
 };
 // eliminate the rows `rows` of A against U block by block, RREF each block, append to U
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,

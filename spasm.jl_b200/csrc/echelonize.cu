@@ -121,6 +121,34 @@ static void add_L_entries(Echelon &E, const SolveResult &R, const std::vector<in
     for (long long e = lp[k]; e < lp[k + 1]; e++) spasm_add_entry(E.L, orig_rows[k], lj[e], (i64)lx[e]);
 }
 
+// the dense tail's multipliers and row permutation (with-L mode, dense.cuh) go to the host triplet / Lp of the factor
+struct HostLSink : LSink {
+  Echelon &E;
+  const std::vector<int> &orig;  // tail row -> original row
+  HostLSink(Echelon &E_, const std::vector<int> &o) : E(E_), orig(o) {}
+  void rows(int row0, int nrows, int ubase, const int *cnt, const unsigned long long *offs, const int *oj, const uint32_t *ox) override {
+    if (nrows <= 0) return;
+    std::vector<int> hc(nrows);
+    std::vector<unsigned long long> ho(nrows);
+    CK(cudaMemcpyAsync(hc.data(), cnt, (size_t)nrows * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    CK(cudaMemcpyAsync(ho.data(), offs, (size_t)nrows * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream()));
+    sync();
+    unsigned long long total = 0;
+    for (int i = 0; i < nrows; i++) total = std::max(total, ho[i] + (unsigned long long)hc[i]);
+    if (total == 0) return;
+    std::vector<int> hj(total);
+    std::vector<uint32_t> hx(total);
+    download_large(hj.data(), oj, (size_t)total * sizeof(int));
+    download_large(hx.data(), ox, (size_t)total * sizeof(uint32_t));
+    sync();
+    for (int i = 0; i < nrows; i++)
+      for (unsigned long long e = ho[i]; e < ho[i] + (unsigned long long)hc[i]; e++) spasm_add_entry(E.L, orig[row0 + i], ubase + hj[e], (i64)hx[e]);
+  }
+  void pivots(int ubase, const int *pivrow, int rr, int row0) override {
+    for (int s = 0; s < rr; s++) E.Lp[ubase + s] = orig[row0 + pivrow[s]];
+  }
+};
+
 // ------------------------------------------------------------------ GPLU tail
 // Row-by-row semantics (README.md:34-36) reproduced by speculative batches: a batch of rows is reduced against
 // the current U in parallel; one warp then walks the batch IN ORDER and decides every row:
@@ -547,7 +575,13 @@ static spasm_lu *echelonize_impl(const spasm_csr *A, echelonize_opts *opts, cons
     } sink_guard;
     TailOpts topt;
     topt.tall_skinny = opts->enable_tall_and_skinny, topt.low_rank_ratio = opts->low_rank_ratio, topt.start_weight = opts->low_rank_start_weight;
-    if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
+    if (opts->L && opts->enable_dense && (go_dense || density > opts->sparsity_threshold)) {
+      // dense tail with L (replaces spasm_ffpack_LU, src/SpaSM.jl:806): row echelon form on the tensor cores
+      HostLSink lsink(E, orig);
+      topt.lsink = &lsink;
+      topt.tall_skinny = false;
+      echelonize_dense_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, topt);
+    } else if (opts->L || (!opts->enable_dense && opts->enable_GPLU))
       echelonize_GPLU(E, *cur, P.p.p + npiv, rem_rows, orig);
     else if (opts->enable_tall_and_skinny && aspect_ratio > opts->tall_and_skinny_ratio)
       echelonize_lowrank_device(*cur, P.p.p + npiv, rem_rows, E.U, E.Uqinv, E.F, opts->dense_block_size, opts->low_rank_start_weight);

@@ -308,6 +308,45 @@ def test_mid_tail_low_rank_switch(gpu, oracle, case):
     checks.check_U_structure(gpu, fg)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", __import__("test_oracle_invariants").DENSE_L + [
+    (3000, 3000, 8, 42013, 31, dict(dense_block_size=300)),      # several panels, tcgen05 products
+    (2600, 2400, 6, 2147483647, 32, dict(dense_block_size=256)),
+    (5200, 5000, 9, 65521, 33, dict(dense_block_size=500)),       # deferred far rows (default depth) under the with-L mode
+])
+def test_dense_tail_with_L(gpu, oracle, case):
+    """echelonize(L=true) on a matrix that goes dense: the tail runs on the tensor cores (row echelon form recovered from the
+    reduced panels, multipliers through the same limb GEMM) and equals the oracle's restatement of spasm_ffpack_LU
+    (src/SpaSM.jl:806) bit for bit: U, L, Lp, qinv; A = L.U; solve / gesv work on the factor"""
+    from test_oracle_invariants import check_A_equals_LU
+
+    n, m, k, prime, seed, kw = case
+    p, j, x = synth.random_rows(n, m, k, prime, seed)
+    A = gpu.from_arrays(n, m, p, j, x, prime)
+    gpu.lib.spasm_b200_mma_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
+    st = (C.c_double * 4)()
+    gpu.lib.spasm_b200_mma_stats(st, 1)
+    fg = gpu.echelonize(A, L=True, **kw)
+    gpu.lib.spasm_b200_mma_stats(st, 0)
+    if n >= 2600:
+        assert st[2] > 0, "the tensor-core kernel did not run for the with-L tail"
+    fo = oracle.echelonize(A, L=True, **kw)
+    checks.assert_same(checks.lu_arrays(fo), checks.lu_arrays(fg), f"L, {kw}: ")
+    if n <= 900:
+        check_A_equals_LU(gpu, (n, m, p, j, x, prime), fg)
+    rng = np.random.default_rng(seed)
+    xv = np.zeros(n, dtype=np.int64)
+    xv[rng.integers(0, n, size=20)] = rng.integers(1, prime, size=20)
+    Ad_rows = {}
+    b = np.zeros(m, dtype=object)
+    for i in np.nonzero(xv)[0]:
+        for e in range(p[i], p[i + 1]):
+            b[j[e]] = (b[j[e]] + int(xv[i]) * int(x[e])) % prime
+    bb = synth.balanced(np.array(b, dtype=np.int64), prime)
+    sg, so = gpu.solve(fg, bb), oracle.solve(fo, bb)
+    assert sg is not None and so is not None and np.array_equal(np.asarray(sg), np.asarray(so))
+
+
 def test_blocks_gpu(gpu):
     from test_blocks import check_blocks
 

@@ -253,3 +253,53 @@ def test_mid_tail_low_rank_switch_oracle(oracle, case, monkeypatch):
         assert np.array_equal(checks.canonical_rref(oracle, fact), checks.canonical_rref(oracle, plain))
     monkeypatch.setenv("SPASM_ORACLE_ROWWISE", "1")
     checks.assert_same(checks.lu_arrays(oracle.echelonize(A, **kw)), blocked, "blocked vs row-wise: ")
+
+
+DENSE_L = [
+    # n, m, k, prime, seed, options: L = True on inputs whose Schur complement is dense
+    (600, 600, 5, 42013, 3, {}),
+    (900, 700, 6, 65521, 4, dict(dense_block_size=100)),     # full column rank reached before the rows run out
+    (500, 800, 5, 4294967291, 5, dict(dense_block_size=64)),
+    (400, 400, 4, 7, 6, dict(dense_block_size=50)),          # tiny field: many cancellations, rank-deficient blocks
+]
+
+
+def check_A_equals_LU(api, A_arrays, fact):
+    n, m, p, j, x, prime = A_arrays
+    Ld = checks.dense_of(api, fact.L).astype(object)
+    Ud = checks.dense_of(api, fact.U).astype(object)
+    Ad = synth.csr_to_dense(n, m, p, j, x, prime).astype(object)
+    assert np.array_equal(Ld.dot(Ud) % prime, Ad % prime), "A != L.U"
+    # L is lower-trapezoidal in the order of Lp: the row that holds the diagonal of column c has nothing in later columns
+    Lp = fact.p
+    for c in range(fact.r):
+        row = Ld[Lp[c]]
+        assert row[c] % prime != 0 and not any(v % prime for v in row[c + 1:]), f"L is not triangular at column {c}"
+
+
+@pytest.mark.parametrize("case", DENSE_L)
+def test_dense_tail_with_L_oracle(oracle, case):
+    """dense tail with L (prototype spasm_ffpack_LU, src/SpaSM.jl:806-812): A = L.U, L triangular under Lp, same rank and row
+    space as without L, and solve() works on it"""
+    n, m, k, prime, seed, kw = case
+    p, j, x = synth.random_rows(n, m, k, prime, seed)
+    A = oracle.from_arrays(n, m, p, j, x, prime)
+    lines = []
+    oracle.log(lambda s: lines.append(s) or 0)
+    try:
+        fact = oracle.echelonize(A, verbose=True, L=True, **kw)
+    finally:
+        oracle.log(None)
+    assert any("with L" in l for l in lines), "the dense tail with L did not run"
+    assert fact.r == oracle.echelonize(A, **kw).r
+    checks.check_U_structure(oracle, fact)
+    checks.check_rank_and_rowspace(oracle, A, fact)
+    check_A_equals_LU(oracle, (n, m, p, j, x, prime), fact)
+    rng = np.random.default_rng(seed)
+    Ad = synth.csr_to_dense(n, m, p, j, x, prime).astype(object)
+    xv = rng.integers(0, prime, size=n)
+    b = synth.balanced(np.array(xv.astype(object).dot(Ad) % prime, dtype=np.int64), prime)
+    sol = oracle.solve(fact, b)
+    assert sol is not None
+    got = np.array(np.asarray(sol).astype(object).dot(Ad) % prime, dtype=np.int64)
+    assert np.array_equal(got, np.array(b.astype(object) % prime, dtype=np.int64))
