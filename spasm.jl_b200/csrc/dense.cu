@@ -522,26 +522,30 @@ __global__ void __launch_bounds__(1024) k_tile_gauss_smem(const uint32_t *__rest
   }
 }
 
-// CLUSTER version of the tile Gauss-Jordan: the (<= 1024) rows are split over a thread-block cluster
-// of 8 CTAs (one row per thread, the tile slice in each CTA's shared memory).  Per pivot: every CTA
-// publishes its best candidate row into all eight CTAs' shared memory (DSMEM), cluster.sync, the
-// owner of the winning row broadcasts the scaled pivot row the same way, cluster.sync, everybody
-// eliminates its own rows.  The arithmetic per pivot drops 8x against the single-CTA kernel.
+// CLUSTER version of the tile Gauss-Jordan: the (<= 1024) rows are split over a thread-block cluster of 8 CTAs, the
+// tile slice of 128 rows in each CTA's shared memory, FOUR threads per row (each owns every fourth column).
+// ONE cluster barrier per pivot: every CTA finds its own first candidate row, scales it (one modular inverse, computed
+// while the other CTAs do the same) and publishes candidate index + scaled row into all eight CTAs' shared memory
+// (DSMEM); after the barrier everybody knows the winner (smallest row index) and already holds its scaled row, and
+// eliminates its own rows.  (The version of round 1 needed two barriers per pivot — candidates, then the winner's row —
+// with the inverse on the path between them, and one thread per row: 4.7 us per pivot.)
 static constexpr int GC = 8;     // CTAs per cluster
-static constexpr int GRP = 128;  // rows (= threads) per CTA
-__global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(GRP)
+static constexpr int GRP = 128;  // rows per CTA
+static constexpr int TPR = 4;    // threads per row
+__global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(GRP * TPR)
 k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long ldw, int *__restrict__ ispiv, int *__restrict__ pivrow,
                      int *__restrict__ pivcol, uint32_t *__restrict__ Gc, int *__restrict__ tilepiv, PanelCtl *__restrict__ ctl,
                      const int *__restrict__ cand, Fp F, uint32_t *__restrict__ GjT, long long ldg, int *__restrict__ pividx) {
   namespace cgx = cooperative_groups;
   cgx::cluster_group cluster = cgx::this_cluster();
   __shared__ unsigned short tile[32 + PB][GRP];
-  __shared__ int s_best[2][GC];          // candidate of every CTA (double buffered by pivot parity)
-  __shared__ uint32_t s_prow[2][32 + PB];  // scaled pivot row
+  __shared__ int s_best[2][GC];                  // candidate row of every CTA (double buffered by pivot parity)
+  __shared__ uint32_t s_rows[2][GC][32 + PB];    // ... and that row, scaled: columns of W, then the recorded operations
   __shared__ int red[GRP / 32];
   const int cta = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int r = cta * GRP + tid;  // my row
+  const int rl = tid & (GRP - 1), q = tid / GRP;  // my row (local) and which columns of it I own
+  const int r = cta * GRP + rl;
   const bool live = r < Sn;
   const int c0 = ctl->c0;
   const int npiv0 = ctl->npiv;
@@ -550,31 +554,46 @@ k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long
     return;
   }
   const int wc = min(32, Sm0 - c0);
-  for (int c = 0; c < 32; c++) {
+  for (int c = q; c < 32; c += TPR) {
     uint32_t v = 0;
     if (live && c < wc) {
       for (int z = 0; z < WKS; z++) v += Wt[((long long)z * 32 + c) * ldw + r];  // KS partial products, each < p < 2^16
       v %= F.p;
     }
-    tile[c][tid] = (unsigned short)v;
+    tile[c][rl] = (unsigned short)v;
   }
-  for (int sx = 0; sx < PB; sx++) tile[32 + sx][tid] = 0;
+  for (int sx = q; sx < PB; sx += TPR) tile[32 + sx][rl] = 0;
   int my_ispiv = live ? ispiv[r] : 1;
   int my_pividx = (live && pividx != nullptr) ? pividx[r] : -1;
   int npiv = npiv0, found = 0, cc = 0, step = 0;
   cluster.sync();
   for (; cc < wc && found < PB && npiv < Sn; cc++) {
     const int par = step & 1;
-    // ---- best candidate of this CTA, published to every CTA of the cluster
-    int best = (!my_ispiv && tile[cc][tid] != 0) ? r : 0x7fffffff;
-    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane == 0) red[wid] = best;
+    // ---- this CTA's candidate: its first row that is not a pivot yet and is non-zero on this column
+    if (tid < GRP) {
+      int best = (!my_ispiv && tile[cc][rl] != 0) ? rl : 0x7fffffff;
+      for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (lane == 0) red[wid] = best;
+    }
     __syncthreads();
-    if (tid < GC) {
-      int b2 = red[0];
-      for (int i = 1; i < GRP / 32; i++) b2 = min(b2, red[i]);
-      int *remote = cluster.map_shared_rank(&s_best[par][0], tid);  // CTA `tid` of the cluster
-      remote[cta] = b2;
+    int b2 = red[0];
+#pragma unroll
+    for (int i = 1; i < GRP / 32; i++) b2 = min(b2, red[i]);
+    // ---- publish it (index + scaled row) to every CTA of the cluster
+    if (tid < 32 + PB) {
+      uint32_t v = 0;
+      if (b2 != 0x7fffffff) {
+        const bool used = (tid < 32) ? (tid > cc && tid < wc) : (tid - 32 <= found);
+        if (used) {
+          const uint32_t alpha = dev_inv_small(tile[cc][b2], F);
+          const uint32_t e = (tid - 32 == found) ? 1u : (uint32_t)tile[tid][b2];  // (the new operation column starts as the unit vector of the pivot row)
+          v = mulmod<true>(alpha, e, F);
+        }
+      }
+#pragma unroll
+      for (int dst = 0; dst < GC; dst++) cluster.map_shared_rank(&s_rows[par][cta][0], dst)[tid] = v;
+    } else if (tid >= 96 && tid < 96 + GC) {
+      cluster.map_shared_rank(&s_best[par][0], tid - 96)[cta] = (b2 == 0x7fffffff) ? 0x7fffffff : cta * GRP + b2;
     }
     cluster.sync();
     int pr = s_best[par][0];
@@ -582,58 +601,43 @@ k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long
     for (int i = 1; i < GC; i++) pr = min(pr, s_best[par][i]);
     step++;
     if (pr == 0x7fffffff) continue;  // no pivot on this column (uniform decision)
-    // ---- the owner scales its pivot row and broadcasts it
-    if (pr / GRP == cta) {
-      const int pt = pr - cta * GRP;
-      if (tid == pt) {
-        my_ispiv = 1;
-        ispiv[r] = 1;
-        pivrow[npiv] = r;
-        pivcol[npiv] = cand[c0 + cc];
-        tilepiv[found] = r;
-        tile[32 + found][tid] = 1;
-        if (pividx != nullptr) pividx[r] = npiv, my_pividx = npiv;
-      }
-      __syncthreads();
-      if (tid < 32 + PB) {
-        const bool used = (tid < 32) ? (tid >= cc && tid < wc) : (tid - 32 <= found);
-        uint32_t v = 0;
-        if (used) {
-          const uint32_t alpha = dev_inv_small(tile[cc][pt], F);
-          v = mulmod<true>(alpha, tile[tid][pt], F);
-        }
-#pragma unroll
-        for (int dst = 0; dst < GC; dst++) cluster.map_shared_rank(&s_prow[par][0], dst)[tid] = v;
-      }
-    }
-    cluster.sync();
-    // ---- everybody eliminates its own row
+    const uint32_t *prow = s_rows[par][pr / GRP];
     if (live) {
-      const uint32_t *prow = s_prow[par];
       if (r == pr) {
-        for (int k = cc; k < wc; k++) tile[k][tid] = (unsigned short)prow[k];
-        for (int sx = 0; sx <= found; sx++) tile[32 + sx][tid] = (unsigned short)prow[32 + sx];
+        my_ispiv = 1;
+        my_pividx = npiv;
+        if (q == 0) {
+          ispiv[r] = 1;
+          pivrow[npiv] = r;
+          pivcol[npiv] = cand[c0 + cc];
+          tilepiv[found] = r;
+          if (pividx != nullptr) pividx[r] = npiv;
+        }
+        for (int k = cc + 1 + q; k < wc; k += TPR) tile[k][rl] = (unsigned short)prow[k];
+        for (int sx = q; sx <= found; sx += TPR) tile[32 + sx][rl] = (unsigned short)prow[32 + sx];
       } else {
-        const uint32_t f = tile[cc][tid];
+        const uint32_t f = tile[cc][rl];  // (column cc itself is never read again: it is not updated)
         if (f != 0) {
-          if (GjT != nullptr && my_pividx >= 0) GjT[(long long)npiv * ldg + my_pividx] = f;
+          if (q == 0 && GjT != nullptr && my_pividx >= 0) GjT[(long long)npiv * ldg + my_pividx] = f;
           const uint32_t nf = F.p - f;
-          for (int k = cc; k < wc; k++) {
-            uint32_t t = (uint32_t)tile[k][tid] + mulmod<true>(nf, prow[k], F);
-            tile[k][tid] = (unsigned short)(t >= F.p ? t - F.p : t);
+          for (int k = cc + 1 + q; k < wc; k += TPR) {
+            uint32_t t = (uint32_t)tile[k][rl] + mulmod<true>(nf, prow[k], F);
+            tile[k][rl] = (unsigned short)(t >= F.p ? t - F.p : t);
           }
-          for (int sx = 0; sx <= found; sx++) {
-            uint32_t t = (uint32_t)tile[32 + sx][tid] + mulmod<true>(nf, prow[32 + sx], F);
-            tile[32 + sx][tid] = (unsigned short)(t >= F.p ? t - F.p : t);
+          for (int sx = q; sx <= found; sx += TPR) {
+            uint32_t t = (uint32_t)tile[32 + sx][rl] + mulmod<true>(nf, prow[32 + sx], F);
+            tile[32 + sx][rl] = (unsigned short)(t >= F.p ? t - F.p : t);
           }
         }
       }
     }
     found++;
     npiv++;
+    __syncthreads();  // the next column is read by threads that did not write it
   }
+  __syncthreads();
   if (live)
-    for (int sx = 0; sx < found; sx++) Gc[(long long)sx * ldw + r] = tile[32 + sx][tid];
+    for (int sx = q; sx < found; sx += TPR) Gc[(long long)sx * ldw + r] = tile[32 + sx][rl];
   if (cta == 0 && tid == 0) {
     ctl->npiv = npiv, ctl->found = found, ctl->consumed = cc, ctl->c0 = c0 + cc;
     if (found < PB / 2 && npiv < Sn) ctl->low += 1;
@@ -641,7 +645,6 @@ k_tile_gauss_cluster(const uint32_t *__restrict__ Wt, int Sn, int Sm0, long long
   cluster.sync();  // nobody leaves while its shared memory may still be written remotely
 }
 
-// Wt[c][r] = sum_t Dt[c0+c][k0+t] * T[r][t]  for a narrow tile (c < wc <= 32): one CTA per 32 rows r
 template <bool SMALL>
 __global__ void __launch_bounds__(256) k_wtile(const uint32_t *__restrict__ Dt_panel, long long ld, const uint32_t *__restrict__ T, int Sn, int Sm0,
                                                 const PanelCtl *__restrict__ ctl, const int *__restrict__ cand, uint32_t *__restrict__ Wt,
@@ -863,7 +866,7 @@ static int panel_factor(const uint32_t *Dt, long long ld, const int *cand, int S
     for (int g = 0; g < 8; g++) {
       k_wtile<true><<<dim3(cdiv(Sn, 32), 4, WKS), 256, 0, s>>>(Dt + k0, ld, T, Sn, Sm0, ctl.p, cand, Wt.p, ldw, F);
       if (use_cluster)
-        k_tile_gauss_cluster<<<GC, GRP, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F, GjT, ldg, pividx);
+        k_tile_gauss_cluster<<<GC, GRP * TPR, 0, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F, GjT, ldg, pividx);
       else
         k_tile_gauss_smem<<<1, 1024, gsm, s>>>(Wt.p, Sn, Sm0, ldw, ispiv.p, pivrow.p, pivcol.p, Gc.p, tilepiv.p, ctl.p, cand, F, GjT, ldg, pividx);
       apply_T();
