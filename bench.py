@@ -118,6 +118,8 @@ def gpu_same_sample(pkg, entry, n, p, j, x, expect_rank):
         lib.spasm_b200_echelonize_resident.restype = C.c_int
         lib.spasm_b200_echelonize_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         lib.spasm_b200_release.argtypes = [C.c_void_p]
+        # fresh caches: the pinned / device blocks of the full-size runs (tens of GB) must not shape the sample's timing
+        lib.spasm_b200_trim()
         Ag = gpu.from_arrays(n, n, p, j, x, PRIME)
         opts = gpu.EchelonizeOpts()
         h = lib.spasm_b200_upload(C.cast(Ag.data, C.c_void_p))
@@ -129,7 +131,7 @@ def gpu_same_sample(pkg, entry, n, p, j, x, expect_rank):
             if it:
                 res.append(ms.value / 1e3)
         lib.spasm_b200_release(h)
-        for it in range(3):
+        for it in range(4):
             t = time.perf_counter()
             f = gpu.echelonize(Ag)
             rk = f.r
@@ -138,7 +140,7 @@ def gpu_same_sample(pkg, entry, n, p, j, x, expect_rank):
             del f
             if it:
                 e2e.append(dt)
-        return sum(res) / len(res), sum(e2e) / len(e2e)
+        return sorted(res)[len(res) // 2], sorted(e2e)[len(e2e) // 2]  # medians (first call of each kind discarded)
     except Exception as exc:  # the reference arm must not die because of the product
         print(f"bench.py: same-sample GPU leg skipped: {exc}", file=sys.stderr)
         return None, None
@@ -366,10 +368,25 @@ def run_ours(args):
     peak_source = "measured in this run: back-to-back UTCIMMA M128xN256xK32, operands in shared memory, 148 CTAs (spasm_b200_utcimma_peak)"
     if not peak or peak <= 0:
         peak, peak_source = 2.0 * bf16_sust, f"fallback: 2 x bf16_tflops_sustained of {src}"
+    # the same kernel ALONE on the GPU at a mid-elimination shape of the deferred updates (live columns x far rows x depth):
+    # inside the step its launches share the SMs with the panel factorisation running on the main stream
+    alone = None
+    if world == 1:
+        lib.spasm_b200_gemm_probe.restype = C.c_double
+        lib.spasm_b200_gemm_probe.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
+        pm, pn, pk = 57344, 49152, 4032
+        t_alone = lib.spasm_b200_gemm_probe(PRIME, pm, pn, pk, 3)
+        if t_alone and t_alone > 0:
+            alone = {"shape_MxNxK": [pm, pn, pk], "kernel_ms": t_alone, "achieved": 8.0 * pm * pn * pk / (t_alone * 1e-3) / 1e12}
+            alone["frac"] = alone["achieved"] / peak
     roofline = {
         "kernel": "k_gemm_i8limb (tcgen05.mma.kind::i8, SASS UTCIMMA; TMA-fed, TMEM accumulators)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if achieved else None,
+        "in_step_note": "launch durations inside the step (CUDA events on the launching stream): since the look-ahead, the deep updates run on a "
+                        "second stream restricted to 116 of the 148 SMs and overlap the panel factorisation of the main stream, so a launch "
+                        "takes longer than alone although the step is shorter; `alone` is the same kernel by itself on the GPU",
+        "alone": alone,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
         # profiles/r02_ncu_gemm_i8limb_k4096.csv (M=32768 N=16384 K=4096, the depth of the deferred trailing updates)
         "traffic": 4.938201e9 + 2.137045e9,

@@ -54,6 +54,7 @@ void spasm_b200_mma_timing(int on);                   /* CUDA events around ever
 void spasm_b200_mma_stats(double *out4, int reset);   /* ms in k_gemm_i8limb, modular MACs, launches, kernels launched by the library */
 void spasm_b200_tail_stats(long long *out4, int reset); /* deferred trailing updates: far flushes, multiplier corrections, far rows x depth, near updates */
 long long spasm_b200_lowrank_switches(int reset);      /* how often the dense loop handed its remaining rows to the low-rank mode */
+double spasm_b200_gemm_probe(long long prime, int M, int N, int K, int reps); /* ms of k_gemm_i8limb alone on the GPU for C (M x N) -= A . B^T of depth K */
 double spasm_b200_utcimma_peak(int iters, int reps);  /* measured back-to-back tcgen05.mma.kind::i8 M128 N256 K32 rate, TOP/s */
 
 /* ---- bench / test hooks */

@@ -1609,6 +1609,37 @@ static int dense_tail_bench_impl(long long prime, int n, int m, int planted_rank
   }
 }
 
+// the tensor-core kernel ALONE on the GPU at one shape of the dense tail's deferred updates:  C (M x N) -= A (M x K) . B^T
+// with device-generated operands.  Returns the mean duration of k_gemm_i8limb in ms over `reps` launches (limb split
+// excluded, as in spasm_b200_mma_stats), < 0 on error or when the shape does not take the tensor-core path.
+extern "C" void spasm_b200_mma_timing(int on);
+extern "C" void spasm_b200_mma_stats(double *out, int reset);
+extern "C" double spasm_b200_gemm_probe(long long prime, int M, int N, int K, int reps) {
+  using namespace sb;
+  try {
+    ApiCall api_scope_;
+    Fp F = make_field(prime);
+    const long long ldk = ((long long)K + 15) / 16 * 16, ldc = ((long long)N + 63) / 64 * 64;
+    DBuf<uint32_t> A((size_t)M * ldk), B((size_t)N * ldk), Cm((size_t)M * ldc);
+    k_fill_random<<<cdiv((long long)M * ldk, 256), 256, 0, stream()>>>(A.p, (long long)M * ldk, F.p, 0x1111);
+    k_fill_random<<<cdiv((long long)N * ldk, 256), 256, 0, stream()>>>(B.p, (long long)N * ldk, F.p, 0x2222);
+    k_fill_random<<<cdiv((long long)M * ldc, 256), 256, 0, stream()>>>(Cm.p, (long long)M * ldc, F.p, 0x3333);
+    gemm_nt(Cm.p, ldc, M, N, A.p, ldk, B.p, ldk, K, true, F);  // warm-up
+    sb::sync();
+    double st0[4], st1[4];
+    spasm_b200_mma_timing(1);
+    spasm_b200_mma_stats(st0, 0);
+    for (int i = 0; i < reps; i++) gemm_nt(Cm.p, ldc, M, N, A.p, ldk, B.p, ldk, K, true, F);
+    sb::sync();
+    spasm_b200_mma_stats(st1, 0);
+    const double calls = st1[2] - st0[2];
+    return calls > 0 ? (st1[0] - st0[0]) / calls : -1.0;
+  } catch (const std::exception &e) {
+    errf("[spasm_b200] spasm_b200_gemm_probe failed: %s\n", e.what());
+    return -1.0;
+  }
+}
+
 extern "C" void spasm_b200_tail_stats(long long *out, int reset) {
   for (int i = 0; i < 4; i++) out[i] = sb::g_tail_stats[i];
   if (reset)
