@@ -368,8 +368,7 @@ def run_ours(args):
     peak_source = "measured in this run: back-to-back UTCIMMA M128xN256xK32, operands in shared memory, 148 CTAs (spasm_b200_utcimma_peak)"
     if not peak or peak <= 0:
         peak, peak_source = 2.0 * bf16_sust, f"fallback: 2 x bf16_tflops_sustained of {src}"
-    # the same kernel ALONE on the GPU at a mid-elimination shape of the deferred updates (live columns x far rows x depth):
-    # inside the step its launches share the SMs with the panel factorisation running on the main stream
+    # the same kernel ALONE on the GPU at a mid-elimination shape of the deferred updates (live columns x far rows x depth)
     alone = None
     if world == 1:
         lib.spasm_b200_gemm_probe.restype = C.c_double
@@ -383,9 +382,11 @@ def run_ours(args):
         "kernel": "k_gemm_i8limb (tcgen05.mma.kind::i8, SASS UTCIMMA; TMA-fed, TMEM accumulators)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if achieved else None,
-        "in_step_note": "launch durations inside the step (CUDA events on the launching stream): since the look-ahead, the deep updates run on a "
-                        "second stream restricted to 116 of the 148 SMs and overlap the panel factorisation of the main stream, so a launch "
-                        "takes longer than alone although the step is shorter; `alone` is the same kernel by itself on the GPU",
+        "in_step_note": ("launch durations inside the step, CUDA events on the launching stream; one stream on a single GPU, so a launch has the "
+                         "GPU to itself; `alone` is the same kernel at one mid-elimination shape of the deferred updates" if world == 1 else
+                         "launch durations inside the step, CUDA events on the launching stream: with several ranks the deep updates run on a second "
+                         "stream restricted to 100 of the 148 SMs and overlap the panel factorisation / broadcast chain of the main stream, so a "
+                         "launch takes longer than alone although the step is shorter"),
         "alone": alone,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
         # profiles/r02_ncu_gemm_i8limb_k4096.csv (M=32768 N=16384 K=4096, the depth of the deferred trailing updates)

@@ -1053,7 +1053,8 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   // my panels per flush: the factors of group * NR panels (mine and the other ranks') accumulate between two flushes,
   // and a flush happens exactly when my near rows are used up — the moment the next `group` panels change hands
   const int group = lazy ? std::max(1, kcap / std::max(block_size * NR, 1)) : 1;
-  const int kdepth = lazy ? (int)std::min<long long>(std::max<long long>(kcap, (long long)group * NR * B16), gemm_max_k(F) - B16) : 0;
+  // (rank r's FIRST interval is r panels longer — the ranks' groups are staggered by one panel each — hence the NR - 1)
+  const int kdepth = lazy ? (int)std::min<long long>(std::max<long long>(kcap, ((long long)group * NR + NR - 1) * B16), gemm_max_k(F) - B16) : 0;
   const long long LDK = lazy ? (long long)kdepth + B16 : 0;
   // ---- look-ahead on two streams.  Everything the NEXT panel waits for — this panel's factorisation, its
   // broadcast, the update of the near rows — stays on the main stream (A, high priority); the far rows are only
@@ -1061,7 +1062,13 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   // A hands rows to B never; B hands the next `group` panels to A at a flush (one event).  Two sets of accumulators:
   // while B applies one, A already fills the other.  B's tensor-core launches leave some SMs to A's (small, latency
   // bound) kernels, which would otherwise queue behind a persistent kernel that owns every SM's shared memory.
-  const bool two_streams = lazy && ls == nullptr && getenv("SPASM_B200_ONE_STREAM") == nullptr;
+  // Default: two streams when the tail is spread over several ranks (the second stream then has 1/N of the work and the
+  // serial chain panel -> broadcast -> near rows is what bounds the step: 4 GPUs 5.1 -> 3.6 s).  On ONE GPU the second
+  // stream carries as much work as the first, the two share the SMs, and the measured gain at 200 000 rows is within the
+  // run-to-run spread (+-0.4 s under the power cap) — one stream stays the default there; SPASM_B200_TWO_STREAMS=1 /
+  // SPASM_B200_ONE_STREAM=1 override either way.
+  const bool want_two = getenv("SPASM_B200_TWO_STREAMS") != nullptr || (NR > 1 && getenv("SPASM_B200_ONE_STREAM") == nullptr);
+  const bool two_streams = lazy && ls == nullptr && want_two;
   const int nsets = two_streams ? 2 : 1;
   cudaStream_t sA = s, sB = two_streams ? aux_stream() : s;
   int aux_ctas = sm_count() - (NR > 1 ? 48 : 32);  // (with several ranks the second stream has 1/N of the work: the critical path gets more room)
@@ -1375,6 +1382,15 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
       }
     }
     for (auto &e_ : evs) cudaEventDestroy(e_.second);
+  }
+  if (prof) {
+    extern void alloc_diagnostics(long long out[4]);
+    long long ad[4];
+    alloc_diagnostics(ad);
+    size_t fr = 0, to = 0;
+    cudaMemGetInfo(&fr, &to);
+    fprintf(stderr, "[dense] rank %d allocator: %lld retries so far, %.1f GB in the block cache, pool %.1f GB reserved / %.1f GB in use, %.1f GB free on the device\n",
+            me, ad[0], ad[1] / 1e9, ad[2] / 1e9, ad[3] / 1e9, fr / 1e9);
   }
   if (prof)
     fprintf(stderr, "[dense] rank %d/%d blocks=%d panel=%.3fs Rgemm=%.3fs emit=%.3fs gather=%.3fs near=%.3fs bcast=%.3fs handover=%.3fs (%s)\n", me, NR,

@@ -76,6 +76,7 @@ struct BigBlock {
   cudaStream_t last = nullptr;  // stream whose work used the block last (set when it is parked in the cache)
   cudaEvent_t ev = nullptr;     // recorded on `last` at that moment: another stream waits for it before reusing the block
 };
+long long g_alloc_retries = 0;  // allocations that only succeeded after the caches were emptied (a full stall of both streams)
 static std::vector<BigBlock> g_big_free;
 static std::vector<BigBlock> g_big_live;
 static const size_t BIG = (size_t)256 << 20;
@@ -189,6 +190,7 @@ void *dmalloc_bytes(size_t bytes) {
   void *p = nullptr;
   cudaError_t e = cudaMallocAsync(&p, bytes, stream());
   if (e != cudaSuccess) {  // give the cached blocks and the idle part of the pool back to the driver and retry
+    g_alloc_retries++;
     cudaGetLastError();
     big_trim();
     cudaStreamSynchronize(g_stream);
@@ -238,6 +240,22 @@ void dfree(void *p) {
       return;
     }
   cudaFreeAsync(p, stream());
+}
+// {allocation retries, bytes parked in the block cache, pool reserved, pool in use} — diagnostics (SPASM_B200_PROFILE)
+void alloc_diagnostics(long long out[4]) {
+  out[0] = g_alloc_retries;
+  size_t c = 0;
+  for (auto &b : g_big_free) c += b.bytes;
+  out[1] = (long long)c;
+  uint64_t reserved = 0, used = 0;
+  cudaMemPool_t pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+  }
+  out[2] = (long long)reserved, out[3] = (long long)used;
 }
 size_t dev_free_bytes() {  // what a new allocation could get: free memory + our own cached blocks
   size_t f = 0, t = 0;

@@ -19,7 +19,7 @@ f.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(
 g.lib.spasm_b200_set_cache.argtypes = [C.c_int]
 g.lib.spasm_b200_set_cache(1)
 os.environ["SPASM_B200_PROFILE"] = "2"
-configs = [("one stream", {"SPASM_B200_ONE_STREAM": "1"}), ("two streams, 116 SMs", {"SPASM_B200_AUX_SMS": "116"}),
+configs = [("one stream", {"SPASM_B200_ONE_STREAM": "1"}), ("two streams, 116 SMs", {"SPASM_B200_TWO_STREAMS": "1", "SPASM_B200_AUX_SMS": "116"}),
            ("two streams, 132 SMs", {"SPASM_B200_AUX_SMS": "132"}), ("two streams, 100 SMs", {"SPASM_B200_AUX_SMS": "100"}),
            ("two streams, 148 SMs", {"SPASM_B200_AUX_SMS": "148"})]
 for name, env in configs:
