@@ -106,4 +106,21 @@ function solve(f::LU, b::Vector{Int32})
     ok ? x : nothing
 end
 
+# ---- several GPUs of one box: one Julia process per GPU (include/spasm_b200_ext.h).  Rank 0 creates the 128-byte NCCL id,
+# the host framework (MPI.jl / Distributed) ships it to the other ranks, every rank calls dist_init!.  From then on
+# `echelonize` is a collective call (every rank, same matrix and options): the dense panels and the non-pivotal rows of the
+# Schur complements are split over the ranks.  rank(f) and qinv are valid everywhere; kernel / solve need a complete factor
+# (rank 0's by default) and raise on a partial one.
+nccl_unique_id() = (id = zeros(UInt8, 128); ccall((:spasm_b200_nccl_unique_id, lib), Cint, (Ptr{UInt8},), id) == 0 || error("NCCL id"); id)
+dist_init!(rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    ccall((:spasm_b200_dist_init, lib), Cint, (Cint, Cint, Ptr{UInt8}), rank, nranks, id) == 0 || error("spasm_b200_dist_init failed (see stderr)")
+dist_finalize!() = ccall((:spasm_b200_dist_finalize, lib), Cvoid, ())
+"every rank keeps (and downloads) the rows of U of the dense panels it owns instead of rank 0 holding all of them"
+shard_factor!(on::Bool) = ccall((:spasm_b200_dist_shard_factor, lib), Cvoid, (Cint,), on)
+"kernel / rref / gesv become collective calls whose rows are split over the ranks (every rank gets the complete result)"
+shard_rows!(on::Bool) = ccall((:spasm_b200_dist_shard_rows, lib), Cvoid, (Cint,), on)
+"memory policy: keep the device / pinned caches between calls (a loop of same-shaped calls), give them back with trim!()"
+set_cache!(on::Bool) = ccall((:spasm_b200_set_cache, lib), Cvoid, (Cint,), on)
+trim!() = ccall((:spasm_b200_trim, lib), Cvoid, ())
+
 end # module
