@@ -93,6 +93,8 @@ int main(int argc, char **argv) {
   spasm_lu_free_(fact);
   if (B != A) spasm_csr_free_(B);
   spasm_csr_free_(A);
-  dlclose(h);
+  /* no dlclose: the library's OpenMP workers (and, for the CUDA library, the runtime's own threads) are still parked in
+   * code that unloading would unmap — one run in five died with SIGSEGV at exit.  A Julia host never unloads it either. */
+  (void)h;
   return 0;
 }
