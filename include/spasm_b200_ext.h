@@ -57,6 +57,11 @@ long long spasm_b200_lowrank_switches(int reset);      /* how often the dense lo
 double spasm_b200_gemm_probe(long long prime, int M, int N, int K, int reps); /* ms of k_gemm_i8limb alone on the GPU for C (M x N) -= A . B^T of depth K */
 double spasm_b200_utcimma_peak(int iters, int reps);  /* measured back-to-back tcgen05.mma.kind::i8 M128 N256 K32 rate, TOP/s */
 
+/* ---- triplets -> CSR on the device (csrc/compress.cu; the role of spasm_compress, src/SpaSM.jl:479-493, which stays host
+ * code as in the reference): rows in the order of the triplet list, duplicates summed into the first occurrence, zero sums
+ * dropped — the same arrays as spasm_compress, bit for bit.  NULL (message on stderr) without a GPU. */
+struct spasm_csr *spasm_b200_compress(const struct spasm_triplet *T);
+
 /* ---- bench / test hooks */
 /* BASELINE configs[3]: n x m matrix mod prime generated on the device (iid, or of planted rank r), through the blocked dense tail */
 int spasm_b200_dense_tail_bench(long long prime, int n, int m, int block_size, unsigned long long seed, double *ms);

@@ -496,6 +496,18 @@ class SpaSM:
         libc.fclose.argtypes = [C.c_void_p]
         return libc, f
 
+    def compress(self, T, device=False) -> CSR:
+        """compress(T::Triplet) (src/SpaSM.jl:479-493): triplets -> CSR, duplicates summed into the first occurrence, zero sums
+        dropped.  device=True runs it on the GPU (spasm_b200_compress, csrc/compress.cu; CUDA library only) — same arrays."""
+        if device:
+            f = self.lib.spasm_b200_compress
+            f.restype, f.argtypes = _P(_CSR), [_P(_Triplet)]
+            ptr = f(T)
+            if not ptr:
+                raise RuntimeError("spasm_b200_compress failed (see stderr)")
+            return CSR(self, ptr)
+        return CSR(self, self.lib.spasm_compress(T))
+
     def load(self, path, prime=PRIME0) -> CSR:
         """fileio_load(...; csr = true) (src/SpaSM.jl:506-512): spasm_triplet_load + spasm_compress"""
         libc, f = self._fopen(path, "r")

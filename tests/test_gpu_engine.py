@@ -169,3 +169,40 @@ def test_sparse_triangular_solve(pkg, gpu, oracle, case):
                 for cc in Uj[Up[i] : Up[i + 1]]:
                     if cc != c and qinv[cc] >= 0:
                         assert posn[int(cc)] > posn[int(c)]
+
+
+def _triplets(api, n, m, nz, prime, seed):
+    """a triplet list built directly in the library's host arrays: many duplicate (row, column) pairs, sums that vanish
+    (small primes), empty rows and rows far longer than 64 entries"""
+    rng = np.random.default_rng(seed)
+    T = api.lib.spasm_triplet_alloc(n, m, max(nz, 1), prime, True)
+    if nz:
+        ti = rng.integers(0, n, size=nz)
+        ti[rng.random(nz) < 0.3] = rng.integers(0, max(1, n // 50), size=int((rng.random(nz) < 0.3).sum()) or 1)[0]  # one crowded row
+        tj = rng.integers(0, m, size=nz)
+        dup = rng.random(nz) < 0.5
+        tj[dup] = rng.integers(0, min(m, 37), size=int(dup.sum()))  # collisions
+        tx = synth.balanced(rng.integers(1, prime, size=nz), prime)
+        np.ctypeslib.as_array(T.contents.i, shape=(nz,))[:] = ti
+        np.ctypeslib.as_array(T.contents.j, shape=(nz,))[:] = tj
+        np.ctypeslib.as_array(T.contents.x, shape=(nz,))[:] = tx
+    T.contents.nz = nz
+    return T
+
+
+@pytest.mark.parametrize("case", [(50, 40, 400, 7, 1), (2000, 3000, 30000, 42013, 2), (300, 5000, 60000, 3, 3), (1000, 800, 0, 42013, 4),
+                                  (5, 100000, 3000, 65521, 5), (4000, 4000, 20000, 4294967291, 6)])
+def test_compress_on_device(pkg, gpu, oracle, case):
+    """triplets -> CSR on the device (csrc/compress.cu; spasm_compress, src/SpaSM.jl:479-493): the same arrays, bit for bit, as the
+    oracle's and the library's own host code — rows in the order of the triplet list, duplicates summed into the first
+    occurrence, zero sums dropped"""
+    n, m, nz, prime, seed = case
+    T = _triplets(oracle, n, m, nz, prime, seed)
+    ref, host, dev = oracle.compress(T), gpu.compress(T), gpu.compress(T, device=True)
+    assert ref.shape == host.shape == dev.shape == (n, m)
+    for a, b, c, name in zip(ref.arrays(), host.arrays(), dev.arrays(), "pjx"):
+        assert np.array_equal(a, b), f"host compress: {name} differs from the oracle"
+        assert np.array_equal(a, c), f"device compress: {name} differs from the oracle"
+    if nz:
+        assert ref.nnz() < nz  # duplicates / cancellations really occurred
+    oracle.lib.spasm_triplet_free(T)
