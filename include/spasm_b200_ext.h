@@ -39,6 +39,8 @@ void spasm_b200_dist_finalize(void);
 /* host logic of the block-cyclic panel ownership (exported for the CPU / gloo tests) */
 long long spasm_b200_local_positions(long long n_rem, int block, int nranks, int rank, int *out, long long cap);
 int spasm_b200_panel_owner(long long b, int nranks);
+void spasm_b200_tail_plan(int Sm0, int n_local, int block_size, int nranks, int kcap, int max_k, long long free_bytes,
+                          long long *out4); /* deferred updates of the dense tail: {lazy, my panels per flush, accumulator depth, its leading dimension} */
 void spasm_b200_row_share(long long nrows, int nranks, int rank, long long *lo, long long *hi); /* share of the split row engine */
 
 /* ---- device-resident timing (bench.py `value`): the CSR is uploaded once; each call echelonizes from HBM, leaves the

@@ -209,6 +209,19 @@ __global__ void k_write_rows(const uint32_t *__restrict__ S, long long ld, int m
 
 void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
                      const TailOpts &opts);
+// The arithmetic of the deferred trailing updates (pure host logic, exported as spasm_b200_tail_plan for the CPU tests):
+// kcap = wanted flush depth, max_k = deepest product one tensor-core launch takes for this prime.
+TailPlan plan_tail(int Sm0, int n_local, int block_size, int Bmax, int NR, int kcap, int max_k, size_t free_bytes) {
+  TailPlan pl;
+  const int B16 = (Bmax + 15) / 16 * 16;
+  kcap = std::max(0, std::min(kcap, max_k - B16));
+  while (kcap >= 2 * B16 && (size_t)(Sm0 + n_local + B16) * (size_t)(kcap + B16) * 8 > free_bytes / 4) kcap /= 2;  // keep the (two sets of) factor buffers small
+  pl.lazy = kcap >= 2 * B16 && n_local > 2 * block_size;
+  pl.group = pl.lazy ? std::max(1, kcap / std::max(block_size * NR, 1)) : 1;
+  pl.kdepth = pl.lazy ? (int)std::min<long long>(std::max<long long>(kcap, ((long long)pl.group * NR + NR - 1) * B16), max_k - B16) : 0;
+  pl.LDK = pl.lazy ? (long long)pl.kdepth + B16 : 0;
+  return pl;
+}
 // how the rows of the low-rank mode are spread when the dense loop switches to it on several ranks
 struct LowRankShard {
   const int *gidx = nullptr;         // device: global index (in the remaining-row list) of local row i; nullptr = identity
@@ -1047,15 +1060,14 @@ void dense_tail_core(DenseSchur &D, int nrows, int n_local, int m_total, DCsr &U
   const int B16 = (Bmax + 15) / 16 * 16;
   int kcap = 4096;
   if (const char *e = getenv("SPASM_B200_LAZY_K")) kcap = atoi(e);
-  kcap = std::max(0, std::min(kcap, gemm_max_k(F) - B16));
-  while (kcap >= 2 * B16 && (size_t)(Sm0 + n_local + B16) * (size_t)(kcap + B16) * 8 > dev_free_bytes() / 4) kcap /= 2;  // keep the (two sets of) factor buffers small
-  const bool lazy = kcap >= 2 * B16 && n_local > 2 * block_size;
+  const TailPlan plan = plan_tail(Sm0, n_local, block_size, Bmax, NR, kcap, gemm_max_k(F), dev_free_bytes());
+  const bool lazy = plan.lazy;
   // my panels per flush: the factors of group * NR panels (mine and the other ranks') accumulate between two flushes,
   // and a flush happens exactly when my near rows are used up — the moment the next `group` panels change hands
-  const int group = lazy ? std::max(1, kcap / std::max(block_size * NR, 1)) : 1;
   // (rank r's FIRST interval is r panels longer — the ranks' groups are staggered by one panel each — hence the NR - 1)
-  const int kdepth = lazy ? (int)std::min<long long>(std::max<long long>(kcap, ((long long)group * NR + NR - 1) * B16), gemm_max_k(F) - B16) : 0;
-  const long long LDK = lazy ? (long long)kdepth + B16 : 0;
+  const int group = plan.group;
+  const int kdepth = plan.kdepth;
+  const long long LDK = plan.LDK;
   // ---- look-ahead on two streams.  Everything the NEXT panel waits for — this panel's factorisation, its
   // broadcast, the update of the near rows — stays on the main stream (A, high priority); the far rows are only
   // touched by the second stream (B): gathering a panel's multipliers there, correcting them, and the deep flushes.
@@ -1656,6 +1668,12 @@ extern "C" double spasm_b200_gemm_probe(long long prime, int M, int N, int K, in
   }
 }
 
+// host logic of the deferred updates for the CPU tests: out = {lazy, group, kdepth, LDK}
+extern "C" void spasm_b200_tail_plan(int Sm0, int n_local, int block_size, int nranks, int kcap, int max_k, long long free_bytes, long long *out) {
+  const int Bmax = std::min(block_size, std::max(n_local, 1) * std::max(nranks, 1));
+  const sb::TailPlan pl = sb::plan_tail(Sm0, n_local, block_size, Bmax, nranks, kcap, max_k, (size_t)free_bytes);
+  out[0] = pl.lazy, out[1] = pl.group, out[2] = pl.kdepth, out[3] = pl.LDK;
+}
 extern "C" void spasm_b200_tail_stats(long long *out, int reset) {
   for (int i = 0; i < 4; i++) out[i] = sb::g_tail_stats[i];
   if (reset)

@@ -53,6 +53,13 @@ struct TailOpts {
   double start_weight = -1;
   LSink *lsink = nullptr;  // not null: row echelon form + L instead of the reduced form (every rank computes everything)
 };
+// deferred trailing updates of the dense tail: my panels per flush, capacity of the accumulators (dense.cu: plan_tail)
+struct TailPlan {
+  bool lazy = false;
+  int group = 1, kdepth = 0;
+  long long LDK = 0;
+};
+TailPlan plan_tail(int Sm0, int n_local, int block_size, int Bmax, int NR, int kcap, int max_k, size_t free_bytes);
 // eliminate the rows `rows` of A against U block by block, RREF each block, append to U
 void echelonize_dense_device(const DCsr &A, const int *rows, int nrows, DCsr &U, DBuf<int> &Uqinv, const Fp &F, int block_size,
                              const TailOpts &opts = TailOpts());
