@@ -11,9 +11,16 @@ already resident in HBM and the factor left on the device; `e2e` is the same cal
 reference-facing C ABI (`spasm_echelonize` on host structs: CSR upload and the whole factor U
 downloaded into malloc'd host arrays inside the timed region).
 
+`roofline` is the tensor-core kernel of the dense tail (`k_gemm_i8limb`): `achieved` from CUDA events around every launch of
+the timed region, `peak` the back-to-back `UTCIMMA` rate measured on this box in this run, `alone` the same kernel by itself at
+one mid-elimination shape (with several ranks the in-step launches overlap the main stream's work on a capped number of SMs).
+`secondary` (1 GPU): configs[3] through the dense-tail entry point, a GL7d19-shaped instance with its Schur GB/s,
+configs[4] at 1/100 (echelonize with L, kernel basis, 20 right-hand sides).
+
 The real reference (SpaSM.jl -> libspasm) cannot run here or on the GPU box (no Julia, no libspasm
 sources): the CPU arm is the oracle restatement in oracle/, on a bounded sample of the same
-generator (the full 200k case needs ~1e15 scalar modular operations on a CPU).
+generator (the full 200k case needs ~1e15 scalar modular operations on a CPU); its line carries `value: null` and the
+like-for-like numbers in `cpu_baseline` (oracle seconds next to the CUDA library's seconds on the SAME sample).
 """
 from __future__ import annotations
 
